@@ -1,0 +1,289 @@
+// C ABI of libbvb.so (see include/bvb.h).  Host orchestration only: every
+// number a caller sees is produced by the sm_100a kernels; there is no CPU path.
+#include "bvb_internal.cuh"
+
+#include <string.h>
+#include <new>
+
+using namespace bvb;
+
+void bvb_set_error(bvb_handle* h, int code, const char* fmt, ...) {
+  if (!h) return;
+  h->err_code = code;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(h->err_msg, sizeof(h->err_msg), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count, bool zero = false) {
+    if (count > n) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      n = 0;
+      cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+      if (e != cudaSuccess) return e;
+      n = count;
+      if (zero) return cudaMemset(p, 0, count * sizeof(T));
+    }
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// Device-resident state of one regression family (fixed T, n, M).
+struct PhiWorkspace {
+  PairGeom g;
+  int M = 0, r = 0, Nalloc = 0;
+  DevBuf<double> X, Y, A, W, WY, omega, V, PHI0, PHI, Z, logvar, lam, fac;
+  DevBuf<int2> lut, pairs;
+  DevBuf<int> colbase, status;
+  std::vector<int> h_status;
+  void release() {
+    X.release(); Y.release(); A.release(); W.release(); WY.release(); omega.release();
+    V.release(); PHI0.release(); PHI.release(); Z.release(); logvar.release(); lam.release();
+    fac.release(); lut.release(); pairs.release(); colbase.release(); status.release();
+  }
+};
+
+struct Scratch {
+  PhiWorkspace phi;
+  uint64_t call_counter = 0;
+};
+
+Scratch* scratch_of(bvb_handle* h) { return static_cast<Scratch*>(h->scratch); }
+
+__global__ void fill_normals_kernel(double* out, size_t n, uint64_t seed, uint32_t stream) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RngStream rng(seed, stream, (uint32_t)i, (uint32_t)(i >> 32));
+  out[i] = rng.normal();
+}
+
+int setup_geometry(bvb_handle* h, PhiWorkspace& ws, int T, int n, int M, int r) {
+  if (ws.g.T != T || ws.g.n != n) {
+    make_pair_geom(ws.g, T, n);
+    BVB_CUDA_TRY(ws.lut.ensure(ws.g.nArows));
+    BVB_CUDA_TRY(ws.pairs.ensure(ws.g.nArows));
+    BVB_CUDA_TRY(ws.colbase.ensure(ws.g.colbase.size()));
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.lut.p, ws.g.lut.data(), sizeof(int2) * ws.g.nArows, cudaMemcpyHostToDevice, h->stream));
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.pairs.p, ws.g.pairs.data(), sizeof(int2) * ws.g.nArows, cudaMemcpyHostToDevice, h->stream));
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.colbase.p, ws.g.colbase.data(), sizeof(int) * ws.g.colbase.size(), cudaMemcpyHostToDevice, h->stream));
+    BVB_CUDA_TRY(cudaStreamSynchronize(h->stream));  // host vectors may be rebuilt by the next call
+    BVB_CUDA_TRY(ws.A.ensure((size_t)ws.g.nArows * ws.g.Tp));
+    BVB_CUDA_TRY(ws.X.ensure((size_t)T * n));
+  }
+  const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
+  if (ws.M != M || ws.Nalloc != Nalloc || ws.W.n < (size_t)Nalloc * ws.g.Tp) {
+    ws.W.release();
+    ws.WY.release();
+    BVB_CUDA_TRY(ws.W.ensure((size_t)Nalloc * ws.g.Tp, true));
+    BVB_CUDA_TRY(ws.WY.ensure((size_t)Nalloc * ws.g.Tp, true));
+    ws.Nalloc = Nalloc;
+  }
+  ws.M = M;
+  ws.r = r;
+  BVB_CUDA_TRY(ws.omega.ensure((size_t)M * ws.g.ldo));
+  BVB_CUDA_TRY(ws.Y.ensure((size_t)T * M));
+  BVB_CUDA_TRY(ws.logvar.ensure((size_t)T * M));
+  BVB_CUDA_TRY(ws.V.ensure((size_t)n * M));
+  BVB_CUDA_TRY(ws.PHI0.ensure((size_t)n * M));
+  BVB_CUDA_TRY(ws.PHI.ensure((size_t)n * M));
+  BVB_CUDA_TRY(ws.Z.ensure((size_t)n * M));
+  BVB_CUDA_TRY(ws.status.ensure(M));
+  if (r > 0) {
+    BVB_CUDA_TRY(ws.lam.ensure((size_t)M * r));
+    BVB_CUDA_TRY(ws.fac.ensure((size_t)r * T));
+  }
+  ws.h_status.resize(M);
+  return BVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bvb_version(void) { return "bvb 0.1 (sm_100a)"; }
+
+int bvb_create(bvb_handle** out, int device, uint64_t seed) {
+  if (!out) return BVB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+    return BVB_ERR_CUDA;  // no CPU fallback: the caller must fail loudly
+  if (cudaSetDevice(device) != cudaSuccess) return BVB_ERR_CUDA;
+  bvb_handle* h = new (std::nothrow) bvb_handle();
+  if (!h) return BVB_ERR_CUDA;
+  h->device = device;
+  h->seed = seed;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return BVB_ERR_CUDA; }
+  h->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {  // kernels are sm_100a-only
+    delete h;
+    return BVB_ERR_UNSUPPORTED;
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BVB_ERR_CUDA; }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  h->scratch = new (std::nothrow) Scratch();
+  *out = h;
+  return BVB_OK;
+}
+
+void bvb_destroy(bvb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->scratch) {
+    scratch_of(h)->phi.release();
+    delete scratch_of(h);
+  }
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int bvb_last_error(const bvb_handle* h, int* step, int* sweep, int* equation, char* msg, int msg_len) {
+  if (!h) return BVB_ERR_ARG;
+  if (step) *step = h->err_step;
+  if (sweep) *sweep = h->err_sweep;
+  if (equation) *equation = h->err_eq;
+  if (msg && msg_len > 0) {
+    strncpy(msg, h->err_msg, msg_len - 1);
+    msg[msg_len - 1] = 0;
+  }
+  return h->err_code;
+}
+
+int bvb_last_timing(const bvb_handle* h, double* out4) {
+  if (!h || !out4) return 0;
+  for (int i = 0; i < 4; ++i) out4[i] = h->last_ms[i];
+  return h->last_launches;
+}
+
+int bvb_measure_fp64_peak(bvb_handle* h, double* out3) {
+  if (!h || !out3) return BVB_ERR_ARG;
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  BVB_CUDA_TRY(launch_measure_peak(out3, h->stream, h->num_sms));
+  return BVB_OK;
+}
+
+int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double* X,
+                        const double* Y, const double* logvar_idi, const double* V_prior,
+                        const double* PHI0, const double* facload, const double* fac,
+                        const double* z, const double* delta, int huge, double* PHI_out) {
+  if (!h) return BVB_ERR_ARG;
+  h->err_code = 0; h->err_step = 1; h->err_sweep = 0; h->err_eq = 0; h->err_msg[0] = 0;
+  if (T <= 0 || Kp <= 0 || M <= 0 || r < 0 || !X || !Y || !logvar_idi || !V_prior || !PHI0 || !PHI_out ||
+      (r > 0 && (!facload || !fac))) {
+    bvb_set_error(h, BVB_ERR_ARG, "bvb_phi_draw_factor: invalid argument");
+    return BVB_ERR_ARG;
+  }
+  if (huge) {
+    (void)delta;
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor: huge branch not built yet");
+    return BVB_ERR_UNSUPPORTED;
+  }
+  if (k2_smem_bytes(Kp) > 227 * 1024) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor: Kp=%d exceeds the in-SM panel of the standard path; use huge", Kp);
+    return BVB_ERR_UNSUPPORTED;
+  }
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  Scratch* sc = scratch_of(h);
+  PhiWorkspace& ws = sc->phi;
+  int rc = setup_geometry(h, ws, T, Kp, M, r);
+  if (rc != BVB_OK) return rc;
+  cudaStream_t s = h->stream;
+  const size_t szTM = sizeof(double) * (size_t)T * M, szKM = sizeof(double) * (size_t)Kp * M;
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.X.p, X, sizeof(double) * (size_t)T * Kp, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.Y.p, Y, szTM, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.logvar.p, logvar_idi, szTM, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.V.p, V_prior, szKM, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.PHI0.p, PHI0, szKM, cudaMemcpyHostToDevice, s));
+  if (r > 0) {
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.lam.p, facload, sizeof(double) * (size_t)M * r, cudaMemcpyHostToDevice, s));
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.fac.p, fac, sizeof(double) * (size_t)r * T, cudaMemcpyHostToDevice, s));
+  }
+  if (z) {
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.Z.p, z, szKM, cudaMemcpyHostToDevice, s));
+  } else {
+    const size_t nz = (size_t)Kp * M;
+    fill_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(ws.Z.p, nz, h->seed, (uint32_t)(0x5000u + sc->call_counter));
+  }
+  sc->call_counter++;
+
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  BVB_CUDA_TRY(launch_build_A(ws.A.p, ws.X.p, ws.pairs.p, T, ws.g.Tp, Kp, ws.g.nArows, 0, s));
+  BVB_CUDA_TRY(launch_prep_factor(ws.W.p, ws.WY.p, ws.Y.p, ws.logvar.p, ws.lam.p, ws.fac.p, T, ws.g.Tp, M, r, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[1], s));
+  K1Params k1{};
+  k1.A = ws.A.p; k1.W = ws.W.p; k1.WY = ws.WY.p; k1.lut = ws.lut.p; k1.V = ws.V.p; k1.PHI0 = ws.PHI0.p;
+  k1.omega = ws.omega.p; k1.Tp = ws.g.Tp; k1.nZtiles = ws.g.nZtiles; k1.ntiles = ws.g.nZtiles + ws.g.nXtiles;
+  k1.M = M; k1.n = Kp; k1.ldo = ws.g.ldo;
+  BVB_CUDA_TRY(launch_k1(k1, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[2], s));
+  K2Params k2{};
+  k2.omega = ws.omega.p; k2.colbase = ws.colbase.p; k2.z = ws.Z.p; k2.phi = ws.PHI.p; k2.status = ws.status.p;
+  k2.n = Kp; k2.M = M; k2.ldo = ws.g.ldo; k2.ldz = Kp; k2.ldphi = Kp;
+  BVB_CUDA_TRY(launch_k2(k2, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(PHI_out, ws.PHI.p, szKM, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.h_status.data(), ws.status.p, sizeof(int) * M, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->last_ms[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->last_ms[1] = ms;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->last_ms[2] = ms;
+  h->last_ms[3] = 0;
+  h->last_launches = 4 + (z ? 0 : 1);
+  for (int j = 0; j < M; ++j) {
+    if (ws.h_status[j] != 0) {
+      h->err_eq = j + 1;
+      if (ws.h_status[j] > 0)
+        bvb_set_error(h, BVB_ERR_NUMERIC, "univariate_regression_update() failed in %ith eqation: chol(): decomposition failed (pivot %d)", j + 1, ws.h_status[j]);
+      else
+        bvb_set_error(h, BVB_ERR_NUMERIC, "univariate_regression_update() failed in %ith eqation: non-finite draw", j + 1);
+      return BVB_ERR_NUMERIC;
+    }
+  }
+  return BVB_OK;
+}
+
+int bvb_phi_draw_cholesky(bvb_handle* h, int T, int Kp, int M, const double* PHI_in,
+                          const double* PHI0, const double* Y, const double* X, const double* U,
+                          const double* d_sqrt, const double* V_prior, const double* z,
+                          double* PHI_out) {
+  (void)T; (void)Kp; (void)M; (void)PHI_in; (void)PHI0; (void)Y; (void)X; (void)U; (void)d_sqrt;
+  (void)V_prior; (void)z; (void)PHI_out;
+  if (!h) return BVB_ERR_ARG;
+  bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_cholesky: not built yet");
+  return BVB_ERR_UNSUPPORTED;
+}
+
+int bvb_sample_u(bvb_handle* h, int T, int M, const double* resid, const double* V_i_U,
+                 const double* d_sqrt, const double* z, double* U_out) {
+  (void)T; (void)M; (void)resid; (void)V_i_U; (void)d_sqrt; (void)z; (void)U_out;
+  if (!h) return BVB_ERR_ARG;
+  bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_sample_u: not built yet");
+  return BVB_ERR_UNSUPPORTED;
+}
+
+int bvb_gig(bvb_handle* h, int n, const double* lambda, int len_lambda, const double* chi,
+            int len_chi, const double* psi, int len_psi, uint64_t stream, double* out) {
+  (void)n; (void)lambda; (void)len_lambda; (void)chi; (void)len_chi; (void)psi; (void)len_psi;
+  (void)stream; (void)out;
+  if (!h) return BVB_ERR_ARG;
+  bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gig: not built yet");
+  return BVB_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

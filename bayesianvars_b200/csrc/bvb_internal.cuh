@@ -1,0 +1,90 @@
+// Internal declarations shared by the libbvb.so translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bvb.h"
+#include "common.cuh"
+
+struct bvb_handle {
+  int device = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  int err_code = 0, err_step = 0, err_sweep = 0, err_eq = 0;
+  char err_msg[512] = {0};
+  double last_ms[4] = {0, 0, 0, 0};
+  int last_launches = 0;
+  cudaEvent_t ev[8] = {};
+  void* scratch = nullptr;  // owned by api.cu (PhiWorkspace cache)
+};
+
+void bvb_set_error(bvb_handle* h, int code, const char* fmt, ...);
+
+namespace bvb {
+
+// Geometry of one batched regression problem family (all equations share the
+// regressor matrix X; only weights / priors / right-hand sides differ).
+//
+// Packed "augmented" posterior system of one equation: columns c = 0..n-1 of the
+// lower triangle of Omega (n x n), each followed by the right-hand side entry
+// b[c] as row n.  Element (i, c), c <= i <= n, lives at colbase[c] + i.
+// colbase[c] is even, so rows with even index are 16-byte aligned.
+struct PairGeom {
+  int T = 0, Tp = 0;      // observations, padded to a multiple of K1_BK
+  int n = 0;              // regressors (Kp)
+  int P = 0;              // n(n+1)/2 pair rows
+  int nZtiles = 0;        // ceil(P / 64)
+  int nXtiles = 0;        // ceil(n / 64)   (rows of X^T for the rhs GEMM)
+  int nArows = 0;         // 64 * (nZtiles + nXtiles)
+  long ldo = 0;           // doubles per equation in the packed system (+slack)
+  std::vector<int> colbase;   // n entries
+  std::vector<int2> lut;      // nArows entries {dest offset | -1, coef index | -1}
+  std::vector<int2> pairs;    // nArows entries {a, b} (-1 for padding) for the Z builder
+};
+void make_pair_geom(PairGeom& g, int T, int n);
+
+constexpr int K1_BM = 64;
+constexpr int K1_BK = 20;
+constexpr int K1_STAGES = 3;
+constexpr int K1_THREADS = 128;
+constexpr int K1_NMAX = 104;  // equations per CTA column block (13 n8 tiles)
+
+struct K1Params {
+  const double* A;     // [nArows][Tp], K-major
+  const double* W;     // [Nalloc][Tp] weights w_j[t]
+  const double* WY;    // [Nalloc][Tp] w_j[t] * yhat_j[t]
+  const int2* lut;
+  const double* V;     // [n][M] prior variances
+  const double* PHI0;  // [n][M] prior means (may be null -> 0)
+  double* omega;       // [M][ldo]
+  int Tp, nZtiles, ntiles, M, n;
+  long ldo;
+};
+cudaError_t launch_k1(const K1Params& p, cudaStream_t s);
+
+struct K2Params {
+  double* omega;        // [M][ldo] in: packed augmented system; out: its Cholesky factor
+  const int* colbase;   // [n]
+  const double* z;      // [n][M] standard normals (ld = ldz)
+  double* phi;          // [n][M] out (ld = ldphi)
+  int* status;          // [M] 0 ok, c+1 = non-positive pivot at column c, -1 = non-finite
+  int n, M;
+  long ldo;
+  int ldz, ldphi;
+};
+cudaError_t launch_k2(const K2Params& p, cudaStream_t s);
+size_t k2_smem_bytes(int n);
+
+// prep kernels
+cudaError_t launch_build_A(double* A, const double* X, const int2* pairs, int T, int Tp, int n,
+                           int nArows, int nZrows, cudaStream_t s);
+cudaError_t launch_prep_factor(double* W, double* WY, const double* Y, const double* logvar,
+                               const double* facload, const double* fac, int T, int Tp, int M,
+                               int r, cudaStream_t s);
+cudaError_t launch_measure_peak(double* out3, cudaStream_t s, int num_sms);
+
+}  // namespace bvb

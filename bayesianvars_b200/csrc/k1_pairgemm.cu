@@ -1,0 +1,144 @@
+// K1 - batched weighted SYRK as ONE tall-skinny FP64 tensor-core GEMM.
+//
+// Replaces, for all equations at once, the reference's per-equation
+//   X_norm = X.each_col() % normalizer.col(j);          sample_coefficients.cpp:99
+//   Omega  = X_norm.t()*X_norm; Omega.diag() += 1/v;    sample_coefficients.cpp:55-56
+//   b      = X_norm.t()*y_norm + prior_mean/v;          sample_coefficients.cpp:61-64
+//
+// B200 design: every equation shares the regressor matrix X and differs only
+// in the diagonal weight w_j[t] = exp(-h_tj), so
+//   Omega_j[a,b] = sum_t (X[t,a] X[t,b]) * w_j[t]      ==   (Z W)[pair(a,b), j]
+// with Z[pair, t] = X[t,a] X[t,b] built ONCE per chain (X never changes inside a
+// Gibbs run).  The M symmetric rank-T updates become one dense GEMM with no
+// wasted upper-triangle flops, no per-equation rescaled copy of X, and the
+// weights as the (tiny, L2-resident) B operand.  The right-hand sides
+//   b_j = X' (w_j . yhat_j)  are extra row tiles of the same GEMM (A = X', B = WY).
+// The epilogue adds the prior terms (1/v on the diagonal, phi0/v on the rhs) and
+// scatters into the packed augmented layout K2 factorises in place.
+//
+// Tiling: CTA = 4 warps, 64 A-rows x (8*NT <= 104) equations, K chunks of 20
+// (3-stage cp.async ring, 160-byte rows -> conflict-free DMMA fragment loads:
+// row stride 20 doubles == 4 mod 16).  Each warp owns 16 rows x 8*NT columns as
+// 2 x NT m8n8k4 DMMA accumulators.  Two CTAs are resident per SM.
+#include "bvb_internal.cuh"
+
+namespace bvb {
+
+template <int NT>
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_pairgemm(const K1Params p) {
+  constexpr int NB = 8 * NT;                       // equations handled by this CTA
+  constexpr int A_STAGE = K1_BM * K1_BK;           // doubles
+  constexpr int B_STAGE = NB * K1_BK;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                               // [STAGES][64][20]
+  double* sB = smem + K1_STAGES * A_STAGE;         // [STAGES][NB][20]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * NB;
+  const bool ztile = tile < p.nZtiles;
+  const double* __restrict__ Ag = p.A + (size_t)tile * K1_BM * p.Tp;
+  const double* __restrict__ Bg = (ztile ? p.W : p.WY) + (size_t)n0 * p.Tp;
+  const int nk = p.Tp / K1_BK;
+
+  auto load_stage = [&](int stage, int kc) {
+    const double* a = Ag + kc * K1_BK;
+    const double* b = Bg + kc * K1_BK;
+    double* da = sA + stage * A_STAGE;
+    double* db = sB + stage * B_STAGE;
+    constexpr int PIECES = K1_BK / 2;              // 16-byte pieces per row
+    for (int i = tid; i < K1_BM * PIECES; i += K1_THREADS) {
+      int r = i / PIECES, c = i - r * PIECES;
+      cp_async16(da + r * K1_BK + 2 * c, a + (size_t)r * p.Tp + 2 * c);
+    }
+    for (int i = tid; i < NB * PIECES; i += K1_THREADS) {
+      int r = i / PIECES, c = i - r * PIECES;
+      cp_async16(db + r * K1_BK + 2 * c, b + (size_t)r * p.Tp + 2 * c);
+    }
+  };
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[m][nt][0] = acc[m][nt][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < K1_STAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int fr = lane >> 2, fk = lane & 3;         // fragment row / k index
+  for (int kc = 0; kc < nk; ++kc) {
+    cp_async_wait<K1_STAGES - 2>();
+    __syncthreads();
+    {
+      int nxt = kc + K1_STAGES - 1;
+      if (nxt < nk) load_stage(nxt % K1_STAGES, nxt);
+      cp_async_commit();
+    }
+    const double* a = sA + (kc % K1_STAGES) * A_STAGE + (warp * 16 + fr) * K1_BK + fk;
+    const double* b = sB + (kc % K1_STAGES) * B_STAGE + fr * K1_BK + fk;
+#pragma unroll
+    for (int ks = 0; ks < K1_BK / 4; ++ks) {
+      double a0 = a[4 * ks], a1 = a[8 * K1_BK + 4 * ks];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        double bv = b[nt * 8 * K1_BK + 4 * ks];
+        dmma884(acc[0][nt][0], acc[0][nt][1], a0, bv);
+        dmma884(acc[1][nt][0], acc[1][nt][1], a1, bv);
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // Epilogue: add prior terms, scatter into the packed augmented systems.
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int row = tile * K1_BM + warp * 16 + m * 8 + fr;
+    const int2 l = p.lut[row];
+    if (l.x < 0) continue;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = n0 + nt * 8 + 2 * fk + e;
+        if (j >= p.M) continue;
+        double v = acc[m][nt][e];
+        if (l.y >= 0) {
+          const double pv = p.V[(size_t)j * p.n + l.y];
+          if (ztile) v += 1.0 / pv;
+          else if (p.PHI0) v += p.PHI0[(size_t)j * p.n + l.y] / pv;
+        }
+        p.omega[(size_t)j * p.ldo + l.x] = v;
+      }
+    }
+  }
+}
+
+template <int NT>
+static cudaError_t launch_k1_nt(const K1Params& p, cudaStream_t s) {
+  const size_t smem = (size_t)K1_STAGES * (K1_BM + 8 * NT) * K1_BK * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(k1_pairgemm<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(p.ntiles, (p.M + 8 * NT - 1) / (8 * NT));
+  k1_pairgemm<NT><<<grid, K1_THREADS, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_k1(const K1Params& p, cudaStream_t s) {
+  const int m = p.M;
+  // Smallest column block that covers M in the fewest CTA columns.
+  const int blocks = (m + K1_NMAX - 1) / K1_NMAX;
+  const int per = (m + blocks - 1) / blocks;       // equations per CTA column
+  const int nt = (per + 7) / 8;
+  if (nt <= 1) return launch_k1_nt<1>(p, s);
+  if (nt <= 2) return launch_k1_nt<2>(p, s);
+  if (nt <= 4) return launch_k1_nt<4>(p, s);
+  if (nt <= 7) return launch_k1_nt<7>(p, s);
+  if (nt <= 10) return launch_k1_nt<10>(p, s);
+  return launch_k1_nt<13>(p, s);
+}
+
+}  // namespace bvb

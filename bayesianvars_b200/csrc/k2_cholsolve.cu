@@ -1,0 +1,306 @@
+// K2 - batched Cholesky factorisation + forward solve + N(0,1)-perturbed mean
+// draw, one CTA per equation.
+//
+// Replaces the reference's per-equation (sample_coefficients.cpp:58-70)
+//   R = chol(Omega,"upper"); Rinv = inv(trimatu(R));
+//   mean = Rinv*(Rinv.t()*b);  draw = mean + Rinv*z
+// by the algebraically identical   draw = L^-T (L^-1 b + z),  L = R'.
+//
+// Layout: the packed augmented system written by K1 (lower triangle of Omega by
+// columns, each column followed by its right-hand-side entry as row n), so the
+// forward solve L^-1 b falls out of the factorisation as the last row of L.
+//
+// Algorithm (left-looking, block size 32, in place, the factor stays L2-resident):
+//   for each 32-column block k:
+//     panel  = A[rows >= 32k, block k]                       (smem, cp.async)
+//     panel -= L[rows, 0:32k] * L[block rows, 0:32k]^T       (DMMA m8n8k4, 3-stage
+//                                                             cp.async ring over L)
+//     L_kk   = chol(panel diag 32x32), Linv = L_kk^-1        (one warp, registers)
+//     panel[sub rows] = panel[sub rows] * Linv^T             (DMMA, triangular skip)
+//     write the panel back; keep Linv for the back-solve
+//   back-solve  L^T phi = (L^-1 b) + z  block by block from the bottom, using the
+//   saved 32x32 inverses so no 32-step dependent chain is left in it.
+#include "bvb_internal.cuh"
+
+namespace bvb {
+
+constexpr int K2_NB = 32;
+constexpr int K2_BKC = 8;
+constexpr int K2_STAGES = 3;
+constexpr int K2_LS = 36;  // row stride of the Linv^T tile (== 4 mod 16)
+
+__host__ __device__ inline int k2_row_stride(int n) {
+  int rmax = (n + 1 > 33 ? n + 1 : 33) + 8;
+  return ((rmax + 15) / 16) * 16 + 4;
+}
+__host__ __device__ inline int k2_nblocks(int n) { return (n + K2_NB - 1) / K2_NB; }
+
+size_t k2_smem_bytes(int n) {
+  size_t rs = k2_row_stride(n);
+  size_t d = (size_t)K2_NB * rs + (size_t)K2_STAGES * K2_BKC * rs + (size_t)K2_NB * K2_LS +
+             (size_t)(k2_nblocks(n) * K2_NB + 32) + 64;
+  return d * sizeof(double);
+}
+
+template <int NWARPS, int MAXQ>
+__global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = p.n, n1 = n + 1;
+  const int RS = k2_row_stride(n);
+  const int nbk = k2_nblocks(n);
+  double* panel = smem;                                   // [32][RS]   panel[c][li]
+  double* stage = panel + K2_NB * RS;                     // [STAGES][BKC][RS]
+  double* linvT = stage + K2_STAGES * K2_BKC * RS;        // [32][36]   linvT[c'][c] = Linv[c][c']
+  double* ysol = linvT + K2_NB * K2_LS;                   // [nbk*32 + 32]
+  double* sblk = ysol + nbk * K2_NB + 32;                 // [32] + flags
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int eq = blockIdx.x;
+  double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
+  const int* __restrict__ colbase = p.colbase;
+  double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
+  int fail = 0;  // meaningful on warp 0 only
+
+  for (int k = 0; k < nbk; ++k) {
+    const int c0 = k * K2_NB;
+    const int w = min(K2_NB, n - c0);
+    const int kb_end = c0 + w;
+    const int nsub = n1 - kb_end;
+    const int R = K2_NB + nsub;
+    const bool full = (w == K2_NB);
+    // local row -> global row (or -1 for the virtual identity rows of a partial block)
+    auto grow = [&](int li) -> int { return li < K2_NB ? (li < w ? c0 + li : -1) : kb_end + li - K2_NB; };
+
+    // ---- A: panel load -------------------------------------------------------
+    for (int idx = tid; idx < K2_NB * R; idx += NWARPS * 32) {
+      const int c = idx / R, li = idx - c * R;
+      double* dst = panel + c * RS + li;
+      if (c < w) {
+        const int g = grow(li);
+        if (g >= c0 + c) cp_async8(dst, om + colbase[c0 + c] + g);
+        else *dst = 0.0;
+      } else {
+        *dst = (li == c) ? 1.0 : 0.0;
+      }
+    }
+    cp_async_commit();
+
+    // ---- B: left-looking update with the already-factorised columns -----------
+    const int nchunks = c0 / K2_BKC;
+    auto load_chunk = [&](int st, int ch) {
+      double* sbase = stage + st * (K2_BKC * RS);
+      if (full) {
+        const int npair = (R + 1) >> 1;
+        for (int idx = tid; idx < K2_BKC * npair; idx += NWARPS * 32) {
+          const int kc = idx / npair, pr = idx - kc * npair;
+          cp_async16(sbase + kc * RS + 2 * pr, om + colbase[ch * K2_BKC + kc] + c0 + 2 * pr);
+        }
+      } else {
+        for (int idx = tid; idx < K2_BKC * R; idx += NWARPS * 32) {
+          const int kc = idx / R, li = idx - kc * R;
+          const int g = grow(li);
+          if (g >= 0) cp_async8(sbase + kc * RS + li, om + colbase[ch * K2_BKC + kc] + g);
+          else sbase[kc * RS + li] = 0.0;
+        }
+      }
+    };
+
+    const int mtiles = (R + 7) >> 3;
+    double acc[MAXQ][4][2];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < K2_STAGES - 1; ++s) {
+      if (s < nchunks) load_chunk(s, s);
+      cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+      cp_async_wait<K2_STAGES - 2>();
+      __syncthreads();
+      {
+        const int nxt = ch + K2_STAGES - 1;
+        if (nxt < nchunks) load_chunk(nxt % K2_STAGES, nxt);
+        cp_async_commit();
+      }
+      const double* sb = stage + (ch % K2_STAGES) * (K2_BKC * RS);
+#pragma unroll
+      for (int ks = 0; ks < K2_BKC / 4; ++ks) {
+        const double* col = sb + (4 * ks + fk) * RS + fr;
+        double b[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[nt] = col[8 * nt];
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+          const int mt = warp + NWARPS * q;
+          if (mt < mtiles) {
+            const double a = col[8 * mt];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], a, b[nt]);
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (nchunks > 0) {
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q) {
+        const int mt = warp + NWARPS * q;
+        const int li = 8 * mt + fr;
+        if (mt < mtiles && li < R) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) panel[(8 * nt + 2 * fk + e) * RS + li] -= acc[q][nt][e];
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- C: factor the 32x32 diagonal block and invert it (warp 0) -------------
+    if (warp == 0) {
+      double a[K2_NB];
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) a[c] = (c <= lane) ? panel[c * RS + lane] : 0.0;
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) {
+        double dcc = __shfl_sync(0xffffffffu, a[c], c);
+        if (!(dcc > 0.0) || !isfinite(dcc)) {
+          if (fail == 0) fail = c0 + c + 1;
+          dcc = 1.0;
+        }
+        const double d = sqrt(dcc);
+        a[c] = (lane > c) ? a[c] / d : ((lane == c) ? d : 0.0);
+#pragma unroll
+        for (int c2 = c + 1; c2 < K2_NB; ++c2) {
+          const double l2 = __shfl_sync(0xffffffffu, a[c], c2);
+          a[c2] -= a[c] * l2;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) panel[c * RS + lane] = a[c];
+      __syncwarp();
+      // lane j solves L x = e_j  ->  column j of Linv
+      double x[K2_NB];
+#pragma unroll
+      for (int i = 0; i < K2_NB; ++i) {
+        double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int kk = 0; kk < i; ++kk) s -= panel[kk * RS + i] * x[kk];
+        x[i] = (i >= lane) ? s / panel[i * RS + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < K2_NB; ++i) {
+        linvT[lane * K2_LS + i] = x[i];            // linvT[c'=j][c=i] = Linv[i][j]
+        lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = x[i];  // ws[k][c'=i][c=j] = Linv[i][j]
+      }
+    }
+    __syncthreads();
+
+    // ---- D: sub-diagonal rows  X = A * Linv^T  (DMMA, skipping the zero triangle)
+    for (int mt = 4 + warp; mt < mtiles; mt += NWARPS) {
+      double t[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) t[nt][0] = t[nt][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < K2_NB / 4; ++ks) {
+        const double av = panel[(4 * ks + fk) * RS + 8 * mt + fr];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (4 * ks <= 8 * nt + 7) {
+            const double bv = linvT[(4 * ks + fk) * K2_LS + 8 * nt + fr];
+            dmma884(t[nt][0], t[nt][1], av, bv);
+          }
+        }
+      }
+      __syncwarp();
+      const int li = 8 * mt + fr;
+      if (li < R) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) panel[(8 * nt + 2 * fk + e) * RS + li] = t[nt][e];
+      }
+    }
+    __syncthreads();
+
+    // ---- E: write the factorised panel back; keep the forward-solved rhs --------
+    for (int idx = tid; idx < w * R; idx += NWARPS * 32) {
+      const int c = idx / R, li = idx - c * R;
+      const int g = grow(li);
+      if (g >= c0 + c) om[colbase[c0 + c] + g] = panel[c * RS + li];
+    }
+    if (tid < K2_NB) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;
+    __syncthreads();
+  }
+
+  // ---- back-solve  L^T phi = y + z ------------------------------------------------
+  for (int i = tid; i < n; i += NWARPS * 32) ysol[i] += p.z[(size_t)eq * p.ldz + i];
+  __syncthreads();
+  for (int k = nbk - 1; k >= 0; --k) {
+    const int c0 = k * K2_NB;
+    const int w = min(K2_NB, n - c0);
+    const int kb_end = c0 + w;
+    for (int c = warp; c < K2_NB; c += NWARPS) {
+      double s = 0.0;
+      if (c < w) {
+        const double* colp = om + colbase[c0 + c];
+        for (int i = kb_end + lane; i < n; i += 32) s += colp[i] * ysol[i];
+        s = warp_sum(s);
+      }
+      if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+      double xv = 0.0;
+#pragma unroll 8
+      for (int cp = 0; cp < K2_NB; ++cp) xv += wsk[cp * K2_NB + lane] * sblk[cp];
+      if (lane < w) ysol[c0 + lane] = xv;
+    }
+    __syncthreads();
+  }
+  bool bad = false;
+  for (int i = tid; i < n; i += NWARPS * 32) {
+    const double v = ysol[i];
+    p.phi[(size_t)eq * p.ldphi + i] = v;
+    bad |= !isfinite(v);
+  }
+  const int anybad = __syncthreads_or(bad ? 1 : 0);
+  if (tid == 0) p.status[eq] = fail ? fail : (anybad ? -1 : 0);
+}
+
+static double* g_linv_ws = nullptr;
+static size_t g_linv_ws_bytes = 0;
+
+cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
+  const int nbk = k2_nblocks(p.n);
+  const size_t need = (size_t)p.M * nbk * K2_NB * K2_NB * sizeof(double);
+  if (need > g_linv_ws_bytes) {
+    if (g_linv_ws) cudaFree(g_linv_ws);
+    cudaError_t e = cudaMalloc(&g_linv_ws, need);
+    if (e != cudaSuccess) { g_linv_ws = nullptr; g_linv_ws_bytes = 0; return e; }
+    g_linv_ws_bytes = need;
+  }
+  const size_t smem = k2_smem_bytes(p.n);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  // rows of the first updated panel decide how many m8 tiles a warp must hold
+  const int rmax = p.n + 1 - K2_NB;  // R of block k=1
+  cudaError_t e;
+  if (rmax <= 8 * 8 * 6) {
+    e = cudaFuncSetAttribute(k2_cholsolve<8, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k2_cholsolve<8, 6><<<p.M, 256, smem, s>>>(p, g_linv_ws);
+  } else {
+    e = cudaFuncSetAttribute(k2_cholsolve<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k2_cholsolve<16, 4><<<p.M, 512, smem, s>>>(p, g_linv_ws);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace bvb
