@@ -1,0 +1,107 @@
+"""GPU parity of sample_PHI_factor through the C ABI (host buffers), against the
+oracle on the same seeded inputs, against the committed golden fixtures, and -
+at BASELINE.json's full sizes - through size-independent properties.
+
+Tolerance: north_star asks 1e-9 relative per conditional draw in FP64; metric =
+max_i |x_i - xhat_i| / max_i |xhat_i| per equation."""
+import numpy as np
+import pytest
+
+from oracle import regression as orc
+from tools.synth import phi_draw_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def per_eq_relerr(a, b):
+    return (np.max(np.abs(a - b), axis=0) / np.maximum(np.max(np.abs(b), axis=0), 1e-300)).max()
+
+
+def run(handle, d, **kw):
+    return handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"],
+                                    z=d["z"], **kw)
+
+
+@pytest.mark.parametrize("M,p,T,r,prior", [
+    (2, 0, 30, 0, "flat"),     # lags = 0: intercept only (Kp = 1)
+    (3, 1, 40, 0, "flat"),
+    (10, 2, 235, 1, "dl"),     # config 1 shape
+    (14, 3, 100, 2, "dl"),     # reference smoke-grid shape (setup-all.R:3-5)
+    (7, 4, 20, 1, "dl"),       # T < Kp: precision is prior-dominated
+    (5, 13, 150, 1, "dl"),     # Kp = 66: 3 column blocks, last one partial (2 cols)
+    (16, 4, 120, 3, "dl"),     # Kp = 65
+    (50, 4, 300, 6, "dl"),     # config 2
+])
+def test_matches_oracle(handle, M, p, T, r, prior):
+    d = phi_draw_inputs(M, p, T, r, seed=100 + M + p, prior=prior)
+    ref = orc.sample_PHI_factor(d["PHI0"], d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"],
+                                d["facload"], d["fac"], False, d["z"])
+    out = run(handle, d)
+    assert per_eq_relerr(out, ref) < TOL
+
+
+def test_golden_fixtures(handle, request):
+    g = np.load(request.config.rootpath / "tests" / "golden" / "phi_factor.npz")
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert names
+    for name in names:
+        M, p, T, r = (int(g[f"{name}/{k}"]) for k in "MpTr")
+        d = phi_draw_inputs(M, p, T, r, seed=int(g[f"{name}/seed"]), prior=str(g[f"{name}/prior"]))
+        out = run(handle, d)
+        assert per_eq_relerr(out, g[f"{name}/PHI"]) < TOL, name
+
+
+def test_extreme_prior_dynamic_range(handle):
+    """DL/R2D2 drive 1/V_prior over ~1e-3..1e36."""
+    d = phi_draw_inputs(12, 3, 80, 1, seed=9)
+    rng = np.random.default_rng(9)
+    d["V"] = np.asfortranarray(10.0 ** rng.uniform(-36, 3, size=d["V"].shape))
+    ref = orc.sample_PHI_factor(d["PHI0"], d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"],
+                                d["facload"], d["fac"], False, d["z"])
+    out = run(handle, d)
+    assert per_eq_relerr(out, ref) < TOL
+
+
+def test_nonzero_prior_mean_and_device_rng(handle):
+    d = phi_draw_inputs(9, 2, 60, 2, seed=21)
+    d["PHI0"] = np.asfortranarray(np.random.default_rng(3).standard_normal(d["PHI0"].shape))
+    ref = orc.sample_PHI_factor(d["PHI0"], d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"],
+                                d["facload"], d["fac"], False, d["z"])
+    assert per_eq_relerr(run(handle, d), ref) < TOL
+    # z = NULL -> Philox normals on device: two calls differ, both finite
+    a = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"])
+    b = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"])
+    assert np.isfinite(a).all() and np.isfinite(b).all() and not np.allclose(a, b)
+
+
+def test_full_size_normal_equations(handle):
+    """Config 3 (M=100, p=4, T=500): with z = 0 the draw is the posterior mean and
+    must satisfy X'W(y - X phi) = (phi - phi0)/v for every equation; linearity
+    in z: draw(z) - draw(0) = L^-T z has covariance Omega^-1 => check
+    (draw(z)-draw(0))' Omega (draw(z)-draw(0)) = z'z."""
+    d = phi_draw_inputs(100, 4, 500, 1, seed=123)
+    z = d["z"].copy()
+    d["z"] = np.zeros_like(z, order="F")
+    mean = run(handle, d)
+    d["z"] = z
+    draw = run(handle, d)
+    Yh = d["Y"] - (d["facload"] @ d["fac"]).T
+    X = d["X"]
+    for j in range(0, 100, 7):
+        w = np.exp(-d["logvar"][:, j])
+        g = X.T @ (w * (Yh[:, j] - X @ mean[:, j])) - (mean[:, j] - d["PHI0"][:, j]) / d["V"][:, j]
+        scale = np.abs(X.T @ (w * Yh[:, j])).max() + np.abs(mean[:, j] / d["V"][:, j]).max()
+        assert np.abs(g).max() / scale < 1e-9
+        dl = draw[:, j] - mean[:, j]
+        q = dl @ ((X * w[:, None]).T @ (X @ dl)) + np.sum(dl * dl / d["V"][:, j])
+        assert abs(q - z[:, j] @ z[:, j]) / (z[:, j] @ z[:, j]) < 1e-8
+
+
+def test_cholesky_failure_is_reported(handle):
+    from bayesianvars_b200 import BvbError
+    d = phi_draw_inputs(4, 1, 30, 0, seed=5, prior="flat")
+    d["V"][1, 2] = -1e-30   # huge negative precision on one diagonal -> pivot <= 0
+    with pytest.raises(BvbError) as ei:
+        run(handle, d)
+    assert ei.value.code == 3 and ei.value.equation == 3 and "eqation" in str(ei.value)
