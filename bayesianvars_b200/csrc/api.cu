@@ -7,6 +7,9 @@
 
 using namespace bvb;
 
+void bvb_gibbs_release(bvb_handle* h);
+void bvb_comm_release(bvb_handle* h);
+
 void bvb_set_error(bvb_handle* h, int code, const char* fmt, ...) {
   if (!h) return;
   h->err_code = code;
@@ -22,7 +25,9 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
-  cudaError_t ensure(size_t count, bool zero = false) {
+  // `st` must be the stream the buffer is subsequently used on: a memset on the
+  // legacy default stream is not ordered with a cudaStreamNonBlocking stream.
+  cudaError_t ensure(size_t count, bool zero = false, cudaStream_t st = nullptr) {
     if (count > n) {
       if (p) cudaFree(p);
       p = nullptr;
@@ -30,7 +35,11 @@ struct DevBuf {
       cudaError_t e = cudaMalloc(&p, count * sizeof(T));
       if (e != cudaSuccess) return e;
       n = count;
-      if (zero) return cudaMemset(p, 0, count * sizeof(T));
+      if (zero) {
+        e = cudaMemsetAsync(p, 0, count * sizeof(T), st);
+        if (e != cudaSuccess) return e;
+        if (!st) return cudaDeviceSynchronize();
+      }
     }
     return cudaSuccess;
   }
@@ -87,8 +96,8 @@ int setup_geometry(bvb_handle* h, PhiWorkspace& ws, int T, int n, int M, int r) 
   if (ws.M != M || ws.Nalloc != Nalloc || ws.W.n < (size_t)Nalloc * ws.g.Tp) {
     ws.W.release();
     ws.WY.release();
-    BVB_CUDA_TRY(ws.W.ensure((size_t)Nalloc * ws.g.Tp, true));
-    BVB_CUDA_TRY(ws.WY.ensure((size_t)Nalloc * ws.g.Tp, true));
+    BVB_CUDA_TRY(ws.W.ensure((size_t)Nalloc * ws.g.Tp, true, h->stream));
+    BVB_CUDA_TRY(ws.WY.ensure((size_t)Nalloc * ws.g.Tp, true, h->stream));
     ws.Nalloc = Nalloc;
   }
   ws.M = M;
@@ -143,6 +152,8 @@ int bvb_create(bvb_handle** out, int device, uint64_t seed) {
 void bvb_destroy(bvb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  bvb_gibbs_release(h);
+  bvb_comm_release(h);
   if (h->scratch) {
     scratch_of(h)->phi.release();
     delete scratch_of(h);
@@ -231,6 +242,7 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
   k1.M = M; k1.n = Kp; k1.ldo = ws.g.ldo;
   BVB_CUDA_TRY(launch_k1(k1, s));
   BVB_CUDA_TRY(cudaEventRecord(h->ev[2], s));
+  BVB_CUDA_TRY(cudaMemsetAsync(ws.status.p, 0, sizeof(int) * M, s));
   K2Params k2{};
   k2.omega = ws.omega.p; k2.colbase = ws.colbase.p; k2.z = ws.Z.p; k2.phi = ws.PHI.p; k2.status = ws.status.p;
   k2.n = Kp; k2.M = M; k2.ldo = ws.g.ldo; k2.ldz = Kp; k2.ldphi = Kp;

@@ -20,6 +20,9 @@ struct bvb_handle {
   int last_launches = 0;
   cudaEvent_t ev[8] = {};
   void* scratch = nullptr;  // owned by api.cu (PhiWorkspace cache)
+  void* gibbs = nullptr;    // owned by gibbs.cu (bvb::Gibbs)
+  int rank = 0, world = 1;
+  void* comm = nullptr;     // ncclComm_t
 };
 
 void bvb_set_error(bvb_handle* h, int code, const char* fmt, ...);

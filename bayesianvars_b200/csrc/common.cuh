@@ -51,6 +51,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+__host__ __device__ inline double bvb_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // -------------------------------------------------------------- Philox -----
 // Philox4x32-10 (Salmon et al. 2011).  Counter-based: the 128-bit counter is
 // (c0..c3), the 64-bit key is the chain seed.  One call yields 4x32 random bits.

@@ -1,0 +1,46 @@
+// Device-side state of the Sigma_t block (factor SV or M univariate SVs).
+#pragma once
+#include "bvb_internal.cuh"
+#include "gig.cuh"
+#include "sv_math.cuh"
+
+namespace bvb {
+
+constexpr int FSV_RMAX = 16;  // max number of factors handled by the per-thread small systems
+
+struct FsvDev {
+  int M = 0, T = 0, r = 0;
+  // inputs
+  const double* resid = nullptr;    // T x M   (VAR residuals; orthogonalised residuals for cholesky)
+  // state
+  double* logvar = nullptr;         // T x (M+r)
+  double* logvar0 = nullptr;        // [M+r]
+  double* sv_para = nullptr;        // 3 x (M+r): mu, phi, sigma
+  double* facload = nullptr;        // M x r
+  double* fac = nullptr;            // r x T
+  double* tau2 = nullptr;           // M x r
+  double* lambda2 = nullptr;        // [M] rowwise | [r] columnwise
+  // scratch (time-major: index t*(M+r) + s)
+  double* ystar = nullptr;          // T x S
+  double* eps = nullptr;            // (T+1) x S
+  unsigned char* mixind = nullptr;  // T x S
+  double* scratch = nullptr;        // 3 (T+1) x S
+  double* eidi = nullptr;           // T x M idiosyncratic residuals (series-major)
+  int* status = nullptr;
+  // configuration
+  const int* hetero = nullptr;      // [M+r]
+  const int* restr = nullptr;       // M x r, 1 = unrestricted
+  const double* offset = nullptr;   // [M] sv offset
+  const double* priorsigma2 = nullptr;  // (M+r) x 2
+  const double* priorh0 = nullptr;      // [M+r]
+  const double* priorhomo = nullptr;    // M x 2
+  const double* shrink_a = nullptr; const double* shrink_c = nullptr; const double* shrink_d = nullptr;
+  double priormu[2] = {0, 10};
+  double priorphi[4] = {10, 3, 10, 3};
+  double facloadtol = 1e-14;
+  int ngprior = 1, columnwise = 0, interweaving = 4;
+};
+
+cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s);
+
+}  // namespace bvb

@@ -1,0 +1,722 @@
+// Gibbs sampler orchestration on the device: the loop body of bvar_cpp()
+// (src/bvar_cpp.cpp:498-845) as one CUDA graph per sweep, with every piece of
+// sampler state resident in HBM and stored draws staged through a device ring
+// and pinned host memory into the caller's (R-owned) arrays.
+//
+// One sweep, factor structure (bvar_cpp.cpp:519-647):
+//   prep (W = exp(-h), WY)  -> K1 pair-GEMM -> normals -> K2 Cholesky/solve/draw
+//   [-> NCCL allgather of the PHI columns when equations are sharded]
+//   -> tolerance clamp (:534-559) -> K3 hyper-parameters (:563-609)
+//   -> residuals Y - X PHI (:611) -> K8 factor-SV update (:617-647) -> store (:751-836)
+// The sweep counter lives in device memory so the captured graph is replayed
+// unchanged; all Philox streams are keyed by (purpose, element, sweep).
+#include "gibbs.cuh"
+
+#include <nccl.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+using namespace bvb;
+
+namespace bvb {
+
+constexpr uint32_t STREAM_PHI_Z = 0x10, STREAM_CLAMP = 0x11, STREAM_PHI_HYPER = 0x20;
+
+// ------------------------------------------------------------------ kernels
+__global__ void gibbs_normals_kernel(double* out, int n, int M, int ld, int j0, uint64_t seed, const uint32_t* sweep) {
+  // z[i, j] for the local equations j0..j0+M-1; stream element = global (i, j) so
+  // the draw does not depend on how equations are sharded
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * M) return;
+  const int j = (int)(idx / n), i = (int)(idx % n);
+  RngStream rng(seed, STREAM_PHI_Z, (uint32_t)((size_t)(j0 + j) * n + i), *sweep);
+  out[(size_t)j * ld + i] = rng.normal();
+}
+
+// PHI_diff = PHI - PHI0 on the K lag rows, pushed away from zero for DL / GT
+// (bvar_cpp.cpp:534-559); also the non-finite check of :529-531.
+__global__ void gibbs_clamp_kernel(double* PHI, const double* PHI0, double* coef, int K, int Kp, int M,
+                                   int do_clamp, double tol, uint64_t seed, const uint32_t* sweep, int* status) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Kp * M) return;
+  const int j = (int)(idx / Kp), k = (int)(idx % Kp);
+  double v = PHI[idx];
+  if (!isfinite(v)) atomicCAS(&status[0], 0, 100);
+  if (k >= K) return;
+  double dlt = v - PHI0[idx];
+  if (do_clamp) {
+    if (dlt == 0.0) {
+      RngStream rng(seed, STREAM_CLAMP, (uint32_t)idx, *sweep);
+      dlt = (rng.uniform() < 0.5) ? tol : -tol;   // R::rbinom(1, 0.5) == 0 -> +tol
+      PHI[idx] = PHI0[idx] + dlt;
+    } else if (dlt < tol && dlt > 0.0) {
+      dlt = tol;
+      PHI[idx] = PHI0[idx] + tol;
+    } else if (dlt > -tol && dlt < 0.0) {
+      dlt = -tol;
+      PHI[idx] = PHI0[idx] - tol;
+    }
+  }
+  coef[(size_t)j * K + k] = dlt;
+}
+
+__global__ void gibbs_scatter_V_kernel(double* Vprior, const double* V_i, int K, int Kp, int M) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)K * M) return;
+  const int j = (int)(idx / K), k = (int)(idx % K);
+  Vprior[(size_t)j * Kp + k] = V_i[idx];
+}
+
+// resid = Y - X PHI  (T x M); 32 x 32 output tile per CTA, K streamed through smem.
+__global__ void __launch_bounds__(256) gibbs_resid_kernel(double* __restrict__ resid, const double* __restrict__ Y,
+                                                          const double* __restrict__ X, const double* __restrict__ PHI,
+                                                          int T, int Kp, int M) {
+  __shared__ double sX[32][33];   // [k][t]
+  __shared__ double sP[32][33];   // [k][j]
+  const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7
+  double acc[4] = {0, 0, 0, 0};
+  for (int k0 = 0; k0 < Kp; k0 += 32) {
+    for (int kk = ty; kk < 32; kk += 8) {
+      const int k = k0 + kk;
+      sX[kk][tx] = (k < Kp && t0 + tx < T) ? X[(size_t)k * T + t0 + tx] : 0.0;
+    }
+    for (int jj = ty; jj < 32; jj += 8) {
+      const int k = k0 + tx;
+      sP[tx][jj] = (k < Kp && j0 + jj < M) ? PHI[(size_t)(j0 + jj) * Kp + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const double xv = sX[kk][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(xv, sP[kk][ty + 8 * q], acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int t = t0 + tx, j = j0 + ty + 8 * q;
+    if (t < T && j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - acc[q];
+  }
+}
+
+// Copy the current state into slot `slot` of the device ring if this sweep is stored.
+__global__ void gibbs_store_kernel(const GibbsStore st, const uint32_t* sweep, int* nstored) {
+  const int rep = (int)*sweep;
+  if (rep < st.burnin || ((rep + 1 - st.burnin) % st.thin) != 0) return;
+  const int slot = (((rep + 1 - st.burnin) / st.thin) - 1) - *st.first_slot;
+  if (slot < 0 || slot >= st.ring_slots) return;
+  double* dst = st.ring + (size_t)slot * st.slot_doubles;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < st.nseg; ++s) {
+    const GibbsSeg& sg = st.seg[s];
+    for (size_t i = tid; i < (size_t)sg.rows * sg.cols; i += nth) {
+      const size_t c = i / sg.rows, rr = i % sg.rows;
+      dst[sg.dst_off + i] = sg.src[c * sg.src_ld + sg.src_row0 + rr];
+    }
+  }
+  if (tid == 0) atomicMax(nstored, slot + 1);
+}
+
+__global__ void gibbs_advance_kernel(uint32_t* sweep) { *sweep += 1; }
+
+}  // namespace bvb
+
+// ------------------------------------------------------------------ host side
+namespace {
+
+#define GB_TRY(expr) BVB_CUDA_TRY(expr)
+
+int fail_arg(bvb_handle* h, const char* msg) {
+  bvb_set_error(h, BVB_ERR_ARG, "bvb_gibbs_init: %s", msg);
+  return BVB_ERR_ARG;
+}
+
+template <typename T>
+int upload(bvb_handle* h, GBuf<T>& b, const T* src, size_t n) {
+  if (n == 0) return BVB_OK;
+  GB_TRY(b.ensure(n));
+  if (src) GB_TRY(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return BVB_OK;
+}
+
+// Fill a HyperDev (+ its buffers) from the ABI description of one prior block.
+int setup_hyper(bvb_handle* h, GibbsHyper& H, int prior, int n, const std::vector<int>& grp, int G,
+                const std::vector<double>& gpar, const double* V_i_fixed, double tol, const double* a_vec,
+                const double* a_weight, const double* norm_consts, const double* c_vec, int grid_len, int hyper,
+                int dl_plus, int c_rel_a, int kernel_exp, double vs, const double* tau0, const double* tau1,
+                double s_a, double s_b, const double* p_init, const std::vector<double>& V_prep,
+                const std::vector<double>& loc1_init, const std::vector<double>& loc2_init,
+                const std::vector<double>& V_init, uint32_t stream_base) {
+  HyperDev& d = H.d;
+  d.prior = prior; d.n = n; d.G = G; d.nblocks = (n + HYP_THREADS - 1) / HYP_THREADS;
+  d.tol = tol; d.vs = vs; d.hyper = hyper; d.dl_plus = dl_plus; d.c_rel_a = c_rel_a; d.kernel_exp = kernel_exp;
+  d.s_a = s_a; d.s_b = s_b; d.grid_len = grid_len; d.stream_base = stream_base;
+  if (n == 0) return BVB_OK;
+  if (G > HYP_MAXG) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "more than %d coefficient groups", HYP_MAXG); return BVB_ERR_UNSUPPORTED; }
+  int rc;
+  if ((rc = upload(h, H.grp, grp.data(), n))) return rc;
+  if ((rc = upload(h, H.gpar, gpar.data(), (size_t)std::max(G, 1) * HYP_GP))) return rc;
+  GB_TRY(H.coef.ensure(n));
+  if ((rc = upload(h, H.V_i, V_init.data(), n))) return rc;
+  if ((rc = upload(h, H.loc1, loc1_init.data(), n))) return rc;
+  if ((rc = upload(h, H.loc2, loc2_init.data(), n))) return rc;
+  GB_TRY(H.partial.ensure((size_t)d.nblocks * std::max(G, 1) * HYP_NRED));
+  GB_TRY(H.gsum.ensure((size_t)std::max(G, 1) * HYP_NRED));
+  if (grid_len > 0) {
+    if ((rc = upload(h, H.a_vec, a_vec, grid_len))) return rc;
+    if ((rc = upload(h, H.a_weight, a_weight, grid_len))) return rc;
+    if ((rc = upload(h, H.norm_consts, norm_consts, grid_len))) return rc;
+    if ((rc = upload(h, H.c_vec, c_vec, grid_len))) return rc;
+  }
+  if (prior == BVB_PRIOR_SSVS) {
+    if ((rc = upload(h, H.tau0, tau0, n))) return rc;
+    if ((rc = upload(h, H.tau1, tau1, n))) return rc;
+  }
+  if (prior == BVB_PRIOR_HMP) if ((rc = upload(h, H.V_prep, V_prep.data(), n))) return rc;
+  (void)V_i_fixed; (void)p_init;
+  d.grp = H.grp.p; d.coef = H.coef.p; d.V_i = H.V_i.p; d.loc1 = H.loc1.p; d.loc2 = H.loc2.p; d.gpar = H.gpar.p;
+  d.partial = H.partial.p; d.gsum = H.gsum.p; d.a_vec = H.a_vec.p; d.a_weight = H.a_weight.p;
+  d.norm_consts = H.norm_consts.p; d.c_vec = H.c_vec.p; d.tau0 = H.tau0.p; d.tau1 = H.tau1.p; d.V_prep = H.V_prep.p;
+  return BVB_OK;
+}
+
+void add_seg(GibbsStore& st, const double* src, int rows, int cols, int src_ld, int src_row0, size_t& off) {
+  GibbsSeg& s = st.seg[st.nseg++];
+  s.src = src; s.rows = rows; s.cols = cols; s.src_ld = src_ld; s.src_row0 = src_row0; s.dst_off = off;
+  off += (size_t)rows * cols;
+}
+
+}  // namespace
+
+// One sweep's worth of launches on h->stream (captured into a graph by the caller).
+static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
+  cudaStream_t s = h->stream;
+  const int M = G.M, T = G.T, K = G.K, Kp = G.Kp;
+  const uint32_t* sw = G.sweep.p;
+  cudaEvent_t* ev = G.ev;
+  const bool timing = G.timing_pass;
+  auto mark = [&](int i) { if (timing) cudaEventRecord(ev[i], s); };
+  mark(0);
+  if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
+    // ---- 1) PHI | .  (factor structure: equations independent)
+    GB_TRY(launch_prep_factor(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p, G.fac.p, T, G.geom.Tp, M, G.r, s));
+    mark(1);
+    K1Params k1{};
+    k1.A = G.A.p; k1.W = G.W.p + (size_t)G.j0 * G.geom.Tp; k1.WY = G.WY.p + (size_t)G.j0 * G.geom.Tp; k1.lut = G.lut.p;
+    k1.V = G.Vprior.p + (size_t)G.j0 * Kp; k1.PHI0 = G.PHI0.p + (size_t)G.j0 * Kp; k1.omega = G.omega.p;
+    k1.Tp = G.geom.Tp; k1.nZtiles = G.geom.nZtiles; k1.ntiles = G.geom.nZtiles + G.geom.nXtiles;
+    k1.M = G.nloc; k1.n = Kp; k1.ldo = G.geom.ldo;
+    GB_TRY(launch_k1(k1, s));
+    mark(2);
+    {
+      const size_t nz = (size_t)Kp * G.nloc;
+      gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, G.nloc, Kp, G.j0, h->seed, sw);
+    }
+    K2Params k2{};
+    k2.omega = G.omega.p; k2.colbase = G.colbase.p; k2.z = G.Zn.p; k2.phi = G.PHI.p + (size_t)G.j0 * Kp;
+    k2.status = G.eqstatus.p + G.j0; k2.n = Kp; k2.M = G.nloc; k2.ldo = G.geom.ldo; k2.ldz = Kp; k2.ldphi = Kp;
+    GB_TRY(launch_k2(k2, s));
+    mark(3);
+    if (G.world > 1) {
+      // ranks own contiguous blocks of nloc_max columns (PHI is padded to world*nloc_max
+      // columns), so the gather is in place: sendbuff == recvbuff + rank*count
+      ncclResult_t nr = ncclAllGather(G.PHI.p + (size_t)G.rank * G.nloc_max * Kp, G.PHI.p, (size_t)G.nloc_max * Kp,
+                                      ncclDouble, (ncclComm_t)G.comm, s);
+      if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(nr)); return BVB_ERR_COMM; }
+    }
+    mark(4);
+    const size_t nphi = (size_t)Kp * M;
+    const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
+    gibbs_clamp_kernel<<<(unsigned)((nphi + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
+                                                                     G.PHI_tol, h->seed, sw, G.status.p);
+  }
+  // ---- 2) hyper-parameters of the prior on PHI
+  if (G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING) {
+    GB_TRY(launch_hyper_update(G.hphi.d, h->seed, sw, G.burnin, s));
+    const size_t nk = (size_t)K * M;
+    gibbs_scatter_V_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(G.Vprior.p, G.hphi.d.V_i, K, Kp, M);
+  }
+  mark(5);
+  // ---- resid = Y - X PHI
+  if (Kp > 0) {
+    dim3 grid((T + 31) / 32, (M + 31) / 32);
+    gibbs_resid_kernel<<<grid, 256, 0, s>>>(G.resid.p, G.Y.p, G.X.p, G.PHI.p, T, Kp, M);
+  }
+  mark(6);
+  // ---- 3) Sigma_t
+  GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));
+  mark(7);
+  // ---- store + advance
+  gibbs_store_kernel<<<64, 256, 0, s>>>(G.store, sw, G.nstored.p);
+  gibbs_advance_kernel<<<1, 1, 0, s>>>(G.sweep.p);
+  mark(8);
+  GB_TRY(cudaGetLastError());
+  return BVB_OK;
+}
+
+static void gibbs_free(bvb_handle* h) {
+  if (!h->gibbs) return;
+  Gibbs* G = static_cast<Gibbs*>(h->gibbs);
+  if (G->graph_exec) cudaGraphExecDestroy(G->graph_exec);
+  for (auto& e : G->ev) if (e) cudaEventDestroy(e);
+  if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
+  if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
+  for (int b = 0; b < 2; ++b) if (G->ev_pin[b]) cudaEventDestroy(G->ev_pin[b]);
+  for (int b = 0; b < 2; ++b) if (G->pinned[b]) cudaFreeHost(G->pinned[b]);
+  delete G;
+  h->gibbs = nullptr;
+}
+
+void bvb_gibbs_release(bvb_handle* h) { gibbs_free(h); }
+
+extern "C" {
+
+int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T, int K, int draws, int burnin,
+                   int thin, int tvp_keep_all, int intercept, const double* priorIntercept, const double* PHI0,
+                   const bvb_prior_phi* pp, const bvb_prior_sigma* ps, const bvb_startvals* sv, const int* i_vec,
+                   double PHI_tol, double L_tol, int huge, const bvb_draws* out) {
+  if (!h) return BVB_ERR_ARG;
+  h->err_code = 0; h->err_step = 0; h->err_sweep = 0; h->err_eq = 0; h->err_msg[0] = 0;
+  if (!Y || M <= 0 || T <= 0 || K < 0 || draws < 0 || burnin < 0 || thin < 1 || !pp || !ps || !sv || !out)
+    return fail_arg(h, "null or out-of-range argument");
+  const int Kp = K + (intercept ? 1 : 0);
+  if (Kp > 0 && (!X || !PHI0 || !sv->PHI)) return fail_arg(h, "X / PHI0 / startvals.PHI missing");
+  if (K > 0 && !i_vec) return fail_arg(h, "i_vec missing");
+  if (ps->type != BVB_SIGMA_FACTOR) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gibbs_init: cholesky structure runs through bvb_gibbs_init_cholesky (not built yet)");
+    return BVB_ERR_UNSUPPORTED;
+  }
+  if (huge) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gibbs_init: expert_huge path not built yet"); return BVB_ERR_UNSUPPORTED; }
+  const int r = ps->factor_factors;
+  if (r < 0 || r > FSV_RMAX) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "factor_factors=%d outside [0,%d]", r, FSV_RMAX); return BVB_ERR_UNSUPPORTED; }
+  if (Kp > 0 && k2_smem_bytes(Kp) > 227 * 1024) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "Kp=%d exceeds the in-SM panel of the standard path; use expert_huge", Kp);
+    return BVB_ERR_UNSUPPORTED;
+  }
+  GB_TRY(cudaSetDevice(h->device));
+  GB_TRY(cudaDeviceSynchronize());
+  gibbs_free(h);
+  gbuf_stream() = h->stream;
+  Gibbs* Gp = new (std::nothrow) Gibbs();
+  if (!Gp) return BVB_ERR_CUDA;
+  h->gibbs = Gp;
+  Gibbs& G = *Gp;
+  G.M = M; G.T = T; G.K = K; G.Kp = Kp; G.intercept = intercept ? 1 : 0; G.r = r; G.S = M + r;
+  G.draws = draws; G.burnin = burnin; G.thin = thin; G.tvp_all = tvp_keep_all ? 1 : 0;
+  G.nsave = draws / thin; G.PHI_tol = PHI_tol; G.L_tol = L_tol; G.out = *out;
+  G.rank = h->rank; G.world = h->world > 0 ? h->world : 1; G.comm = h->comm;
+  G.nloc_max = (M + G.world - 1) / G.world;
+  G.j0 = std::min(M, G.rank * G.nloc_max);
+  GB_TRY(G.first_slot.ensure(1, true));
+  G.nloc = std::max(0, std::min(M, G.j0 + G.nloc_max) - G.j0);
+  const int S = G.S;
+  int rc;
+  cudaStream_t s = h->stream;
+
+  // ---- data and PHI block
+  if ((rc = upload(h, G.Y, Y, (size_t)T * M))) return rc;
+  GB_TRY(G.resid.ensure((size_t)T * M));
+  GB_TRY(G.status.ensure(8, true));
+  GB_TRY(G.sweep.ensure(1, true));
+  GB_TRY(G.nstored.ensure(1, true));
+  GB_TRY(G.eqstatus.ensure(std::max(M, 1), true));
+  if (Kp > 0) {
+    if ((rc = upload(h, G.X, X, (size_t)T * Kp))) return rc;
+    if ((rc = upload(h, G.PHI0, PHI0, (size_t)Kp * M))) return rc;
+    GB_TRY(G.PHI.ensure((size_t)Kp * std::max(M, G.nloc_max * G.world)));
+    if ((rc = upload(h, G.PHI, sv->PHI, (size_t)Kp * M))) return rc;
+    make_pair_geom(G.geom, T, Kp);
+    if ((rc = upload(h, G.lut, G.geom.lut.data(), G.geom.nArows))) return rc;
+    if ((rc = upload(h, G.pairs, G.geom.pairs.data(), G.geom.nArows))) return rc;
+    if ((rc = upload(h, G.colbase, G.geom.colbase.data(), G.geom.colbase.size()))) return rc;
+    GB_TRY(G.A.ensure((size_t)G.geom.nArows * G.geom.Tp));
+    const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
+    GB_TRY(G.W.ensure((size_t)Nalloc * G.geom.Tp, true));
+    GB_TRY(G.WY.ensure((size_t)Nalloc * G.geom.Tp, true));
+    GB_TRY(G.omega.ensure((size_t)std::max(G.nloc, 1) * G.geom.ldo));
+    GB_TRY(G.Zn.ensure((size_t)Kp * std::max(G.nloc, 1)));
+    // the pair-product matrix Z is built ONCE per chain: X never changes
+    GB_TRY(launch_build_A(G.A.p, G.X.p, G.pairs.p, T, G.geom.Tp, Kp, G.geom.nArows, 0, s));
+  }
+
+  // ---- prior variances V_prior (Kp x M): V_i on the lag rows, priorIntercept on the last row
+  const int n = K * M;
+  std::vector<double> Vprior((size_t)std::max(Kp * M, 1), 1.0), V_init((size_t)std::max(n, 1), 1.0);
+  std::vector<double> loc1((size_t)std::max(n, 1), 0.0), loc2((size_t)std::max(n, 1), 1.0), V_prep_small;
+  std::vector<int> grp((size_t)std::max(n, 1), -1);
+  std::vector<double> gpar;
+  int Gn = 0;
+  const int prior = (K == 0) ? BVB_PRIOR_NOTHING : pp->prior;
+  if (K > 0) {
+    // i_vec_small = i_vec without intercept entries, same order as vec(PHI[0:K,])
+    std::vector<int> ivs((size_t)n);
+    for (int j = 0; j < M; ++j) for (int k = 0; k < K; ++k) ivs[(size_t)j * K + k] = i_vec[(size_t)j * Kp + k];
+    if (prior == BVB_PRIOR_HMP) {
+      Gn = 2;  // 0 = own-lag (i_vec_small > 0), 1 = cross-lag (< 0)   bvar_cpp.cpp:46-49
+      gpar.assign((size_t)Gn * HYP_GP, 0.0);
+      double cnt[2] = {0, 0};
+      V_prep_small.resize(n);
+      if (!pp->V_i_prep) return fail_arg(h, "HMP needs V_i_prep");
+      for (int j = 0; j < M; ++j) for (int k = 0; k < K; ++k) {
+        const size_t i = (size_t)j * K + k;
+        V_prep_small[i] = pp->V_i_prep[(size_t)j * Kp + k];   // V_i_prep(i_ocl)
+        grp[i] = ivs[i] > 0 ? 0 : (ivs[i] < 0 ? 1 : -1);
+        if (grp[i] >= 0) cnt[grp[i]] += 1;
+      }
+      const double lam_init[2] = {0.04, 0.0016};              // bvar_cpp.cpp:144-145
+      for (int g = 0; g < 2; ++g) {
+        gpar[g * HYP_GP + GP_A] = (g == 0 ? pp->lambda_1 : pp->lambda_2)[0];
+        gpar[g * HYP_GP + GP_B] = (g == 0 ? pp->lambda_1 : pp->lambda_2)[1];
+        gpar[g * HYP_GP + GP_AUX] = lam_init[g];
+        gpar[g * HYP_GP + GP_N] = cnt[g];
+      }
+      for (int i = 0; i < n; ++i) V_init[i] = (grp[i] >= 0 ? lam_init[grp[i]] : 1.0) * V_prep_small[i];
+    } else if (prior != BVB_PRIOR_NORMAL) {
+      Gn = pp->n_groups;
+      if (Gn <= 0 || !pp->groups) return fail_arg(h, "n_groups / groups missing");
+      gpar.assign((size_t)Gn * HYP_GP, 0.0);
+      for (int g = 0; g < Gn; ++g) {
+        double cnt = 0;
+        for (int i = 0; i < n; ++i) if (ivs[i] == pp->groups[g]) { grp[i] = g; cnt += 1; }
+        gpar[g * HYP_GP + GP_A] = pp->a ? pp->a[g] : 0.0;
+        gpar[g * HYP_GP + GP_B] = pp->b ? pp->b[g] : 0.0;
+        gpar[g * HYP_GP + GP_C] = pp->c ? pp->c[g] : 0.0;
+        gpar[g * HYP_GP + GP_XI] = 0.5;       // bvar_cpp.cpp:85
+        gpar[g * HYP_GP + GP_ZETA] = 10.0;    // :125
+        gpar[g * HYP_GP + GP_VARPI] = 1.0;    // :127
+        gpar[g * HYP_GP + GP_N] = cnt;
+      }
+    }
+    switch (prior) {
+      case BVB_PRIOR_NORMAL:
+        if (!pp->V_i) return fail_arg(h, "prior normal needs V_i");
+        for (int i = 0; i < n; ++i) V_init[i] = pp->V_i[i];
+        break;
+      case BVB_PRIOR_DL:  // lambda = 1/n, psi = 1, V = psi lambda^2  (:83-84,:105-107)
+        for (int i = 0; i < n; ++i) { loc1[i] = 1.0 / n; loc2[i] = 1.0; V_init[i] = loc1[i] * loc1[i]; }
+        break;
+      case BVB_PRIOR_GT:  // :113-119
+        for (int i = 0; i < n; ++i) { loc1[i] = 1.0 / n; loc2[i] = 1.0; V_init[i] = pp->GT_priorkernel ? 0.5 * loc1[i] : loc1[i]; }
+        break;
+      case BVB_PRIOR_HS:  // theta = 1/n, nu = 1, zeta = 10  (:123-129)
+        for (int i = 0; i < n; ++i) { loc1[i] = 1.0 / n; loc2[i] = 1.0; V_init[i] = loc1[i] * 10.0; }
+        break;
+      case BVB_PRIOR_SSVS:  // :131-145
+        if (!pp->SSVS_tau0 || !pp->SSVS_tau1 || !pp->SSVS_p) return fail_arg(h, "SSVS needs tau0/tau1/p");
+        for (int i = 0; i < n; ++i) {
+          loc1[i] = 0.0; loc2[i] = pp->SSVS_p[i];
+          V_init[i] = pp->SSVS_hyper ? pp->SSVS_tau1[i] * pp->SSVS_tau1[i] : pp->SSVS_tau0[i] * pp->SSVS_tau0[i];
+        }
+        break;
+      default: break;
+    }
+    for (int j = 0; j < M; ++j) for (int k = 0; k < K; ++k) Vprior[(size_t)j * Kp + k] = V_init[(size_t)j * K + k];
+  }
+  if (intercept) {
+    if (!priorIntercept) return fail_arg(h, "priorIntercept missing");
+    for (int j = 0; j < M; ++j) Vprior[(size_t)j * Kp + K] = priorIntercept[j];
+  }
+  if (Kp > 0) if ((rc = upload(h, G.Vprior, Vprior.data(), (size_t)Kp * M))) return rc;
+  if (gpar.size() < (size_t)std::max(Gn, 1) * HYP_GP) gpar.resize((size_t)std::max(Gn, 1) * HYP_GP, 0.0);
+  const int is_dl = prior == BVB_PRIOR_DL;
+  rc = setup_hyper(h, G.hphi, prior, n, grp, Gn, gpar, pp->V_i, pp->GL_tol, pp->a_vec, pp->a_weight, pp->norm_consts,
+                   pp->c_vec, (prior == BVB_PRIOR_DL || prior == BVB_PRIOR_GT) ? pp->grid_len : 0,
+                   is_dl ? pp->DL_hyper : (prior == BVB_PRIOR_GT ? pp->GT_hyper : (prior == BVB_PRIOR_SSVS ? pp->SSVS_hyper : 0)),
+                   pp->DL_plus, pp->c_rel_a, pp->GT_priorkernel, pp->GT_vs, pp->SSVS_tau0, pp->SSVS_tau1,
+                   pp->SSVS_s_a, pp->SSVS_s_b, pp->SSVS_p, V_prep_small, loc1, loc2, V_init, STREAM_PHI_HYPER);
+  if (rc) return rc;
+
+  // ---- Sigma_t block (factor SV)
+  FsvDev& F = G.fsv;
+  F.M = M; F.T = T; F.r = r;
+  if (!sv->sv_logvar || !sv->sv_para || !sv->sv_logvar0) return fail_arg(h, "sv start values missing");
+  if ((rc = upload(h, G.logvar, sv->sv_logvar, (size_t)T * S))) return rc;
+  if ((rc = upload(h, G.logvar0, sv->sv_logvar0, S))) return rc;
+  if ((rc = upload(h, G.sv_para, sv->sv_para, (size_t)3 * S))) return rc;
+  std::vector<int> restr((size_t)std::max(M * r, 1), 1);
+  std::vector<double> facload((size_t)std::max(M * r, 1), 0.0), tau2((size_t)std::max(M * r, 1), 1.0);
+  if (r > 0) {
+    if (!sv->facload || !sv->fac || !sv->tau2) return fail_arg(h, "factor start values missing");
+    for (size_t i = 0; i < (size_t)M * r; ++i) {
+      restr[i] = ps->factor_restrinv ? (ps->factor_restrinv[i] != 0) : 1;
+      facload[i] = restr[i] ? sv->facload[i] : 0.0;    // bvar_cpp.cpp:305-312
+      tau2[i] = restr[i] ? sv->tau2[i] : 0.0;
+    }
+    if ((rc = upload(h, G.fac, sv->fac, (size_t)r * T))) return rc;
+  }
+  if ((rc = upload(h, G.facload, facload.data(), (size_t)std::max(M * r, 1)))) return rc;
+  if ((rc = upload(h, G.tau2, tau2.data(), (size_t)std::max(M * r, 1)))) return rc;
+  if ((rc = upload(h, G.restr, restr.data(), (size_t)std::max(M * r, 1)))) return rc;
+  GB_TRY(G.lambda2.ensure(std::max(M, std::max(r, 1)), true));
+  std::vector<int> hetero(S, 1);
+  std::vector<double> offset(M, 0.0), ps2((size_t)2 * S, 0.5), ph0(S, -1.0), phomo((size_t)2 * M, 1.0);
+  for (int i = 0; i < S; ++i) {
+    if (ps->sv_heteroscedastic) hetero[i] = ps->sv_heteroscedastic[i] != 0;
+    if (ps->sv_priorsigma2) { ps2[i] = ps->sv_priorsigma2[i]; ps2[S + i] = ps->sv_priorsigma2[S + i]; }
+    if (ps->sv_priorh0) ph0[i] = ps->sv_priorh0[i];
+  }
+  if (ps->factor_priorhomoskedastic) for (int i = 0; i < 2 * M; ++i) phomo[i] = ps->factor_priorhomoskedastic[i];
+  if ((rc = upload(h, G.hetero, hetero.data(), S))) return rc;
+  if ((rc = upload(h, G.offset, offset.data(), M))) return rc;
+  if ((rc = upload(h, G.priorsigma2, ps2.data(), (size_t)2 * S))) return rc;
+  if ((rc = upload(h, G.priorh0, ph0.data(), S))) return rc;
+  if ((rc = upload(h, G.priorhomo, phomo.data(), (size_t)2 * M))) return rc;
+  const int units = ps->factor_columnwise ? r : M;
+  if (r > 0 && ps->factor_ngprior) {
+    if (!ps->factor_shrink_a || !ps->factor_shrink_c || !ps->factor_shrink_d) return fail_arg(h, "factor_shrinkagepriors missing");
+    if ((rc = upload(h, G.shrink_a, ps->factor_shrink_a, units))) return rc;
+    if ((rc = upload(h, G.shrink_c, ps->factor_shrink_c, units))) return rc;
+    if ((rc = upload(h, G.shrink_d, ps->factor_shrink_d, units))) return rc;
+  }
+  GB_TRY(G.ystar.ensure((size_t)T * S));
+  GB_TRY(G.eps.ensure((size_t)(T + 1) * S));
+  GB_TRY(G.mixind.ensure((size_t)T * S));
+  GB_TRY(G.svscratch.ensure((size_t)3 * (T + 1) * S));
+  GB_TRY(G.eidi.ensure((size_t)T * M));
+  F.resid = G.resid.p; F.logvar = G.logvar.p; F.logvar0 = G.logvar0.p; F.sv_para = G.sv_para.p;
+  F.facload = G.facload.p; F.fac = G.fac.p; F.tau2 = G.tau2.p; F.lambda2 = G.lambda2.p;
+  F.ystar = G.ystar.p; F.eps = G.eps.p; F.mixind = G.mixind.p; F.scratch = G.svscratch.p; F.eidi = G.eidi.p;
+  F.status = G.status.p + 1;
+  F.hetero = G.hetero.p; F.restr = G.restr.p; F.offset = G.offset.p; F.priorsigma2 = G.priorsigma2.p;
+  F.priorh0 = G.priorh0.p; F.priorhomo = G.priorhomo.p;
+  F.shrink_a = G.shrink_a.p; F.shrink_c = G.shrink_c.p; F.shrink_d = G.shrink_d.p;
+  F.priormu[0] = ps->sv_priormu[0]; F.priormu[1] = ps->sv_priormu[1];
+  for (int i = 0; i < 4; ++i) F.priorphi[i] = ps->sv_priorphi[i];
+  F.facloadtol = ps->factor_facloadtol; F.ngprior = ps->factor_ngprior; F.columnwise = ps->factor_columnwise;
+  F.interweaving = ps->factor_interweaving > 4 ? 4 : ps->factor_interweaving;
+  if (Kp == 0) GB_TRY(cudaMemcpyAsync(G.resid.p, G.Y.p, sizeof(double) * (size_t)T * M, cudaMemcpyDeviceToDevice, s));
+
+  // ---- stored-draw ring: one slot = everything bvar_cpp.cpp:751-836 copies per stored sweep
+  GibbsStore& st = G.store;
+  st.burnin = burnin; st.thin = thin; st.nseg = 0;
+  size_t off = 0;
+  G.off_PHI = off;      if (Kp > 0) add_seg(st, G.PHI.p, Kp, M, Kp, 0, off);
+  G.off_Vprior = off;   if (Kp > 0) add_seg(st, G.Vprior.p, Kp, M, Kp, 0, off);
+  const int lv_rows = G.tvp_all ? T : 1;
+  G.off_logvar = off;   add_seg(st, G.logvar.p, lv_rows, S, T, G.tvp_all ? 0 : T - 1, off);
+  G.off_svpara = off;   add_seg(st, G.sv_para.p, 3, S, 3, 0, off);
+  G.off_hyper = off; G.hyper_rows = 0;
+  if (prior == BVB_PRIOR_DL || prior == BVB_PRIOR_GT || prior == BVB_PRIOR_HS) {
+    // rows: a|zeta [G], xi|varpi [G], lambda|theta [n], psi|nu [n]   (bvar_cpp.cpp:758-779)
+    const int c0 = (prior == BVB_PRIOR_HS) ? GP_ZETA : GP_A, c1 = (prior == BVB_PRIOR_HS) ? GP_VARPI : GP_XI;
+    add_seg(st, G.hphi.d.gpar, 1, Gn, HYP_GP, c0, off);
+    add_seg(st, G.hphi.d.gpar, 1, Gn, HYP_GP, c1, off);
+    add_seg(st, G.hphi.d.loc1, n, 1, n, 0, off);
+    add_seg(st, G.hphi.d.loc2, n, 1, n, 0, off);
+    G.hyper_rows = 2 * Gn + 2 * n;
+  } else if (prior == BVB_PRIOR_SSVS) {
+    add_seg(st, G.hphi.d.loc1, n, 1, n, 0, off);
+    add_seg(st, G.hphi.d.loc2, n, 1, n, 0, off);
+    G.hyper_rows = 2 * n;
+  } else if (prior == BVB_PRIOR_HMP) {
+    add_seg(st, G.hphi.d.gpar, 1, 2, HYP_GP, GP_AUX, off);
+    G.hyper_rows = 2;
+  }
+  G.off_facload = off;  if (r > 0) add_seg(st, G.facload.p, M, r, M, 0, off);
+  const int fac_cols = G.tvp_all ? T : 1;
+  G.off_fac = off;      if (r > 0) add_seg(st, G.fac.p + (G.tvp_all ? 0 : (size_t)(T - 1) * r), r, fac_cols, r, 0, off);
+  st.slot_doubles = off;
+  // ring sized for one bvb_gibbs_run chunk (<= 256 sweeps) but bounded to 1 GiB
+  size_t slots = 256;
+  while (slots > 1 && slots * off * sizeof(double) > ((size_t)1 << 30)) slots /= 2;
+  st.ring_slots = (int)slots;
+  GB_TRY(G.ring.ensure(slots * off));
+  st.ring = G.ring.p;
+  st.first_slot = G.first_slot.p;
+  for (int b = 0; b < 2; ++b) GB_TRY(cudaMallocHost(&G.pinned[b], slots * off * sizeof(double)));
+  for (auto& e : G.ev) GB_TRY(cudaEventCreate(&e));
+  GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
+  GB_TRY(cudaEventCreate(&G.ev_chunk[1]));
+  for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_pin[b], cudaEventDisableTiming));
+  GB_TRY(cudaStreamSynchronize(s));
+  G.rep = 0;
+  G.ready = true;
+  return BVB_OK;
+}
+
+// Copy slots [first, first+count) of the pinned chunk into the caller's arrays.
+static void scatter_to_caller(Gibbs& G, const double* chunk, int first, int count) {
+  const size_t sd = G.store.slot_doubles;
+  const int M = G.M, Kp = G.Kp, S = G.S, T = G.T, r = G.r;
+  const int lv_rows = G.tvp_all ? T : 1, fac_cols = G.tvp_all ? T : 1;
+  for (int q = 0; q < count; ++q) {
+    const double* src = chunk + (size_t)q * sd;
+    const size_t d = (size_t)(first + q);
+    if (G.out.PHI && Kp > 0) memcpy(G.out.PHI + d * Kp * M, src + G.off_PHI, sizeof(double) * Kp * M);
+    if (G.out.V_prior && Kp > 0) memcpy(G.out.V_prior + d * Kp * M, src + G.off_Vprior, sizeof(double) * Kp * M);
+    if (G.out.logvar) memcpy(G.out.logvar + d * lv_rows * S, src + G.off_logvar, sizeof(double) * lv_rows * S);
+    if (G.out.sv_para) memcpy(G.out.sv_para + d * 3 * S, src + G.off_svpara, sizeof(double) * 3 * S);
+    if (G.out.phi_hyperparameter && G.hyper_rows > 0)
+      memcpy(G.out.phi_hyperparameter + d * G.hyper_rows, src + G.off_hyper, sizeof(double) * G.hyper_rows);
+    if (G.out.facload && r > 0) memcpy(G.out.facload + d * M * r, src + G.off_facload, sizeof(double) * M * r);
+    if (G.out.fac && r > 0) memcpy(G.out.fac + d * r * fac_cols, src + G.off_fac, sizeof(double) * r * fac_cols);
+  }
+}
+
+int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
+  if (!h || !h->gibbs) return BVB_ERR_ARG;
+  Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
+  if (!G.ready) return BVB_ERR_ARG;
+  GB_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int tot = G.draws + G.burnin;
+  int todo = std::min(max_sweeps, tot - G.rep);
+  if (todo < 0) todo = 0;
+  h->err_step = 0;
+  // capture one sweep into a graph on first use
+  if (!G.graph_exec && todo > 0) {
+    // timing pass (eager, with per-phase events) doubles as warm-up of nothing: it IS sweep 0
+    G.timing_pass = true;
+    int rc = enqueue_sweep(h, G);
+    G.timing_pass = false;
+    if (rc) return rc;
+    GB_TRY(cudaStreamSynchronize(s));
+    for (int i = 0; i < 8; ++i) { float ms = 0; cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]); G.phase_ms[i] = ms; }
+    G.rep += 1;
+    todo -= 1;
+    cudaGraph_t graph;
+    GB_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_sweep(h, G);
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc) return rc;
+    GB_TRY(ce);
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    G.launches_per_sweep = (int)nn;
+    GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  // Sub-chunks of <= 64 sweeps (and <= ring_slots stored draws).  The D2H copy of a
+  // sub-chunk's stored draws is queued behind its sweeps; the host scatters the
+  // PREVIOUS sub-chunk into the caller's arrays while the GPU runs the next one.
+  GB_TRY(cudaEventRecord(G.ev_chunk[0], s));
+  int ran = 0;
+  struct Pending { int buf, first, count; } pend = {-1, 0, 0};
+  auto flush = [&](Pending& pd) -> int {
+    if (pd.buf < 0) return BVB_OK;
+    GB_TRY(cudaEventSynchronize(G.ev_pin[pd.buf]));
+    if (G.rank == 0) scatter_to_caller(G, G.pinned[pd.buf], pd.first, pd.count);
+    pd.buf = -1;
+    return BVB_OK;
+  };
+  int flip = 0;
+  while (ran < todo) {
+    const int stored_before = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
+    int nsw = std::min(todo - ran, 64);
+    while (nsw > 1 && (std::max(0, G.rep + nsw - G.burnin) / G.thin) - stored_before > G.store.ring_slots) --nsw;
+    GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < nsw; ++i) GB_TRY(cudaGraphLaunch(G.graph_exec, s));
+    G.rep += nsw;
+    ran += nsw;
+    const int stored_after = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
+    const int cnt = stored_after - stored_before;
+    Pending cur = {-1, 0, 0};
+    if (cnt > 0) {
+      GB_TRY(cudaMemcpyAsync(G.pinned[flip], G.ring.p, sizeof(double) * (size_t)cnt * G.store.slot_doubles,
+                             cudaMemcpyDeviceToHost, s));
+      GB_TRY(cudaEventRecord(G.ev_pin[flip], s));
+      cur = {flip, stored_before, cnt};
+      flip ^= 1;
+    }
+    int rc = flush(pend);   // overlaps with the sweeps just queued
+    if (rc) return rc;
+    pend = cur;
+  }
+  {
+    int rc = flush(pend);
+    if (rc) return rc;
+  }
+  GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
+  GB_TRY(cudaStreamSynchronize(s));
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, G.ev_chunk[0], G.ev_chunk[1]);
+    G.last_chunk_ms = ms;
+    G.last_chunk_sweeps = ran;
+  }
+  // error status
+  int hst[8];
+  GB_TRY(cudaMemcpy(hst, G.status.p, sizeof(hst), cudaMemcpyDeviceToHost));
+  std::vector<int> eqs(G.M);
+  GB_TRY(cudaMemcpy(eqs.data(), G.eqstatus.p, sizeof(int) * G.M, cudaMemcpyDeviceToHost));
+  if (done) *done = G.rep;
+  for (int j = 0; j < G.M; ++j) {
+    if (eqs[j] != 0) {
+      h->err_step = 1; h->err_eq = j + 1; h->err_sweep = G.rep;
+      bvb_set_error(h, BVB_ERR_NUMERIC, "sample_PHI_factor() failed in run <= %i: univariate_regression_update() failed in %ith eqation: chol(): decomposition failed", G.rep, j + 1);
+      return BVB_ERR_NUMERIC;
+    }
+  }
+  if (hst[0] != 0) {
+    h->err_step = 1; h->err_sweep = G.rep;
+    bvb_set_error(h, BVB_ERR_NUMERIC, "non-finite PHI in rep <= %i.", G.rep);
+    return BVB_ERR_NUMERIC;
+  }
+  if (hst[1] != 0) {
+    h->err_step = 3; h->err_sweep = G.rep;
+    bvb_set_error(h, BVB_ERR_NUMERIC, "factorstochvol::update_fsv() failed in run <= %i: small system not positive definite (%s)", G.rep,
+                  hst[1] == 1 ? "loadings" : "factors");
+    return BVB_ERR_NUMERIC;
+  }
+  return BVB_OK;
+}
+
+int bvb_gibbs_timing(const bvb_handle* h, double* out10) {
+  if (!h || !h->gibbs || !out10) return 0;
+  const Gibbs& G = *static_cast<const Gibbs*>(h->gibbs);
+  out10[0] = G.last_chunk_ms;
+  out10[1] = G.launches_per_sweep;
+  for (int i = 0; i < 8; ++i) out10[2 + i] = G.phase_ms[i];
+  return G.last_chunk_sweeps;
+}
+
+int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar, double* sv_para, double* facload,
+                    double* fac, double* U) {
+  if (!h || !h->gibbs) return BVB_ERR_ARG;
+  Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
+  GB_TRY(cudaSetDevice(h->device));
+  GB_TRY(cudaStreamSynchronize(h->stream));
+  const size_t d = sizeof(double);
+  if (PHI && G.Kp) GB_TRY(cudaMemcpy(PHI, G.PHI.p, d * G.Kp * G.M, cudaMemcpyDeviceToHost));
+  if (V_prior && G.Kp) GB_TRY(cudaMemcpy(V_prior, G.Vprior.p, d * G.Kp * G.M, cudaMemcpyDeviceToHost));
+  if (logvar) GB_TRY(cudaMemcpy(logvar, G.logvar.p, d * G.T * G.S, cudaMemcpyDeviceToHost));
+  if (sv_para) GB_TRY(cudaMemcpy(sv_para, G.sv_para.p, d * 3 * G.S, cudaMemcpyDeviceToHost));
+  if (facload && G.r) GB_TRY(cudaMemcpy(facload, G.facload.p, d * G.M * G.r, cudaMemcpyDeviceToHost));
+  if (fac && G.r) GB_TRY(cudaMemcpy(fac, G.fac.p, d * G.r * G.T, cudaMemcpyDeviceToHost));
+  (void)U;
+  return BVB_OK;
+}
+
+}  // extern "C"
+void bvb_comm_release(bvb_handle* h) {
+  if (h && h->comm) { ncclCommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
+}
+extern "C" {
+int bvb_comm_unique_id(char* unique_id_128) {
+  if (!unique_id_128) return BVB_ERR_ARG;
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return BVB_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(unique_id_128, &id, 128);
+  return BVB_OK;
+}
+
+int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return BVB_ERR_ARG;
+  h->rank = rank; h->world = world;
+  if (world == 1) return BVB_OK;
+  if (!unique_id_128) return BVB_ERR_ARG;
+  GB_TRY(cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id_128, 128);
+  ncclComm_t comm;
+  ncclResult_t nr = ncclCommInitRank(&comm, world, id, rank);
+  if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclCommInitRank: %s", ncclGetErrorString(nr)); return BVB_ERR_COMM; }
+  h->comm = comm;
+  return BVB_OK;
+}
+
+}  // extern "C"

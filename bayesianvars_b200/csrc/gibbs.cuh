@@ -1,0 +1,97 @@
+// Sampler state of one Gibbs chain (device buffers + host bookkeeping).
+#pragma once
+#include "bvb_internal.cuh"
+#include "hyper.cuh"
+#include "fsv.cuh"
+
+namespace bvb {
+
+// Stream on which GBuf clears fresh allocations: it must be the stream the
+// uploads / kernels run on (a memset on the legacy default stream is NOT ordered
+// with a cudaStreamNonBlocking stream and could land after an upload).
+inline cudaStream_t& gbuf_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+
+template <typename T>
+struct GBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count, bool zero = false) {
+    if (count == 0) count = 1;
+    if (count > n) {
+      if (p) cudaFree(p);
+      p = nullptr; n = 0;
+      cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+      if (e != cudaSuccess) return e;
+      n = count;
+      zero = true;   // fresh allocations are always cleared (padding is relied upon)
+    }
+    if (zero) return cudaMemsetAsync(p, 0, n * sizeof(T), gbuf_stream());
+    return cudaSuccess;
+  }
+  ~GBuf() { if (p) cudaFree(p); }
+};
+
+struct GibbsHyper {
+  HyperDev d;
+  GBuf<int> grp;
+  GBuf<double> coef, V_i, loc1, loc2, gpar, partial, gsum, a_vec, a_weight, norm_consts, c_vec, tau0, tau1, V_prep;
+};
+
+struct GibbsSeg {
+  const double* src;
+  int rows, cols, src_ld, src_row0;
+  size_t dst_off;
+};
+struct GibbsStore {
+  GibbsSeg seg[16];
+  int nseg = 0;
+  double* ring = nullptr;
+  size_t slot_doubles = 0;
+  int ring_slots = 0;
+  const int* first_slot = nullptr;   // device: index of the stored draw that maps to ring slot 0
+  int burnin = 0, thin = 1;
+};
+
+struct Gibbs {
+  bool ready = false;
+  int M = 0, T = 0, K = 0, Kp = 0, intercept = 0, r = 0, S = 0;
+  int draws = 0, burnin = 0, thin = 1, nsave = 0, tvp_all = 0, rep = 0;
+  double PHI_tol = 0, L_tol = 0;
+  int rank = 0, world = 1, j0 = 0, nloc = 0, nloc_max = 0;
+  void* comm = nullptr;
+  PairGeom geom;
+  GBuf<double> X, Y, A, W, WY, omega, Vprior, PHI0, PHI, Zn, resid;
+  GBuf<int2> lut, pairs;
+  GBuf<int> colbase, status, eqstatus, nstored, first_slot;
+  GBuf<uint32_t> sweep;
+  GibbsHyper hphi;
+  // Sigma_t block
+  FsvDev fsv;
+  GBuf<double> logvar, logvar0, sv_para, facload, fac, tau2, lambda2, ystar, eps, svscratch, eidi;
+  GBuf<double> offset, priorsigma2, priorh0, priorhomo, shrink_a, shrink_c, shrink_d;
+  GBuf<unsigned char> mixind;
+  GBuf<int> hetero, restr;
+  // stored draws
+  GibbsStore store;
+  GBuf<double> ring;
+  double* pinned[2] = {nullptr, nullptr};
+  cudaEvent_t ev_pin[2] = {nullptr, nullptr};
+  bvb_draws out{};
+  size_t off_PHI = 0, off_Vprior = 0, off_logvar = 0, off_svpara = 0, off_hyper = 0, off_facload = 0, off_fac = 0;
+  int hyper_rows = 0;
+  // execution
+  cudaGraphExec_t graph_exec = nullptr;
+  bool timing_pass = false;
+  cudaEvent_t ev[9] = {};
+  cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
+  float phase_ms[8] = {0};
+  float last_chunk_ms = 0;
+  int last_chunk_sweeps = 0, launches_per_sweep = 0;
+};
+
+}  // namespace bvb
+
+void bvb_gibbs_release(bvb_handle* h);

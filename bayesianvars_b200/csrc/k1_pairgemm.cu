@@ -16,28 +16,38 @@
 // The epilogue adds the prior terms (1/v on the diagonal, phi0/v on the rhs) and
 // scatters into the packed augmented layout K2 factorises in place.
 //
-// Tiling: CTA = 4 warps, 64 A-rows x (8*NT <= 104) equations, K chunks of 20
-// (3-stage cp.async ring, 160-byte rows -> conflict-free DMMA fragment loads:
-// row stride 20 doubles == 4 mod 16).  Each warp owns 16 rows x 8*NT columns as
-// 2 x NT m8n8k4 DMMA accumulators.  Two CTAs are resident per SM.
+// Tiling: CTA = MW x 2 warps, 16*MW A-rows x (8*NT <= 104) equations, K chunks of
+// 20 (3-stage cp.async ring, 160-byte rows -> conflict-free DMMA fragment loads:
+// row stride 20 doubles == 4 mod 16).  Each warp owns 16 rows x half the columns
+// as 2 x ceil(NT/2) m8n8k4 DMMA accumulators, which keeps it under 128 registers
+// so 4 warps per scheduler are resident (the DMMA pipe needs that many to stay
+// fed: with 2 warps per scheduler ncu showed 58% pipe activity).
 #include "bvb_internal.cuh"
+#include <stdlib.h>
 
 namespace bvb {
 
-template <int NT>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_pairgemm(const K1Params p) {
+// NT = n8 tiles per CTA (split between two n-warps), MW = m-warps (16 rows each).
+template <int NT, int MW>
+__global__ void __launch_bounds__(MW * 64, (MW <= 2 ? 3 : 2)) k1_pairgemm(const K1Params p) {
+  constexpr int BM = 16 * MW;
+  constexpr int NTHREADS = MW * 64;
   constexpr int NB = 8 * NT;                       // equations handled by this CTA
-  constexpr int A_STAGE = K1_BM * K1_BK;           // doubles
+  constexpr int NTW = (NT + 1) / 2;                // n8 tiles per warp (second n-warp may own one less)
+  constexpr int A_STAGE = BM * K1_BK;              // doubles
   constexpr int B_STAGE = NB * K1_BK;
   extern __shared__ __align__(16) double smem[];
-  double* sA = smem;                               // [STAGES][64][20]
+  double* sA = smem;                               // [STAGES][BM][20]
   double* sB = smem + K1_STAGES * A_STAGE;         // [STAGES][NB][20]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int nt0 = wn * NTW;                        // first n-tile of this warp
+  const int ntc = wn == 0 ? NTW : NT - NTW;        // number of n-tiles of this warp
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * NB;
   const bool ztile = tile < p.nZtiles;
-  const double* __restrict__ Ag = p.A + (size_t)tile * K1_BM * p.Tp;
+  const double* __restrict__ Ag = p.A + (size_t)tile * BM * p.Tp;
   const double* __restrict__ Bg = (ztile ? p.W : p.WY) + (size_t)n0 * p.Tp;
   const int nk = p.Tp / K1_BK;
 
@@ -47,21 +57,21 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_pairgemm(const K1Params p) {
     double* da = sA + stage * A_STAGE;
     double* db = sB + stage * B_STAGE;
     constexpr int PIECES = K1_BK / 2;              // 16-byte pieces per row
-    for (int i = tid; i < K1_BM * PIECES; i += K1_THREADS) {
+    for (int i = tid; i < BM * PIECES; i += NTHREADS) {
       int r = i / PIECES, c = i - r * PIECES;
       cp_async16(da + r * K1_BK + 2 * c, a + (size_t)r * p.Tp + 2 * c);
     }
-    for (int i = tid; i < NB * PIECES; i += K1_THREADS) {
+    for (int i = tid; i < NB * PIECES; i += NTHREADS) {
       int r = i / PIECES, c = i - r * PIECES;
       cp_async16(db + r * K1_BK + 2 * c, b + (size_t)r * p.Tp + 2 * c);
     }
   };
 
-  double acc[2][NT][2];
+  double acc[2][NTW][2];
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) acc[m][nt][0] = acc[m][nt][1] = 0.0;
+    for (int nt = 0; nt < NTW; ++nt) acc[m][nt][0] = acc[m][nt][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < K1_STAGES - 1; ++s) {
@@ -78,16 +88,18 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_pairgemm(const K1Params p) {
       if (nxt < nk) load_stage(nxt % K1_STAGES, nxt);
       cp_async_commit();
     }
-    const double* a = sA + (kc % K1_STAGES) * A_STAGE + (warp * 16 + fr) * K1_BK + fk;
-    const double* b = sB + (kc % K1_STAGES) * B_STAGE + fr * K1_BK + fk;
+    const double* a = sA + (kc % K1_STAGES) * A_STAGE + (wm * 16 + fr) * K1_BK + fk;
+    const double* b = sB + (kc % K1_STAGES) * B_STAGE + (nt0 * 8 + fr) * K1_BK + fk;
 #pragma unroll
     for (int ks = 0; ks < K1_BK / 4; ++ks) {
       double a0 = a[4 * ks], a1 = a[8 * K1_BK + 4 * ks];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        double bv = b[nt * 8 * K1_BK + 4 * ks];
-        dmma884(acc[0][nt][0], acc[0][nt][1], a0, bv);
-        dmma884(acc[1][nt][0], acc[1][nt][1], a1, bv);
+      for (int nt = 0; nt < NTW; ++nt) {
+        if (nt < ntc) {
+          double bv = b[nt * 8 * K1_BK + 4 * ks];
+          dmma884(acc[0][nt][0], acc[0][nt][1], a0, bv);
+          dmma884(acc[1][nt][0], acc[1][nt][1], a1, bv);
+        }
       }
     }
   }
@@ -96,14 +108,15 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_pairgemm(const K1Params p) {
   // Epilogue: add prior terms, scatter into the packed augmented systems.
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
-    const int row = tile * K1_BM + warp * 16 + m * 8 + fr;
+    const int row = tile * BM + wm * 16 + m * 8 + fr;
     const int2 l = p.lut[row];
     if (l.x < 0) continue;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt >= ntc) continue;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = n0 + nt * 8 + 2 * fk + e;
+        const int j = n0 + (nt0 + nt) * 8 + 2 * fk + e;
         if (j >= p.M) continue;
         double v = acc[m][nt][e];
         if (l.y >= 0) {
@@ -117,14 +130,28 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_pairgemm(const K1Params p) {
   }
 }
 
+template <int NT, int MW>
+static cudaError_t launch_k1_cfg(const K1Params& p, cudaStream_t s) {
+  const size_t smem = (size_t)K1_STAGES * (16 * MW + 8 * NT) * K1_BK * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(k1_pairgemm<NT, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int rows = p.ntiles * K1_BM;               // geometry is laid out in 64-row tiles
+  dim3 grid(rows / (16 * MW), (p.M + 8 * NT - 1) / (8 * NT));
+  K1Params q = p;
+  q.nZtiles = p.nZtiles * (K1_BM / (16 * MW));
+  k1_pairgemm<NT, MW><<<grid, MW * 64, smem, s>>>(q);
+  return cudaGetLastError();
+}
+
 template <int NT>
 static cudaError_t launch_k1_nt(const K1Params& p, cudaStream_t s) {
-  const size_t smem = (size_t)K1_STAGES * (K1_BM + 8 * NT) * K1_BK * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(k1_pairgemm<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  dim3 grid(p.ntiles, (p.M + 8 * NT - 1) / (8 * NT));
-  k1_pairgemm<NT><<<grid, K1_THREADS, smem, s>>>(p);
-  return cudaGetLastError();
+  static int mw = 0;
+  if (mw == 0) {
+    const char* e = getenv("BVB_K1_MW");
+    mw = e ? atoi(e) : 4;
+    if (mw != 2 && mw != 4) mw = 4;
+  }
+  return mw == 2 ? launch_k1_cfg<NT, 2>(p, s) : launch_k1_cfg<NT, 4>(p, s);
 }
 
 cudaError_t launch_k1(const K1Params& p, cudaStream_t s) {

@@ -12,10 +12,11 @@
 //
 // Algorithm (left-looking, block size 32, in place, the factor stays L2-resident):
 //   for each 32-column block k:
-//     panel  = A[rows >= 32k, block k]                       (smem, cp.async)
-//     panel -= L[rows, 0:32k] * L[block rows, 0:32k]^T       (DMMA m8n8k4, 3-stage
-//                                                             cp.async ring over L)
-//     L_kk   = chol(panel diag 32x32), Linv = L_kk^-1        (one warp, registers)
+//     acc    = L[rows, 0:32k] * L[block rows, 0:32k]^T       (DMMA m8n8k4, 16 warps,
+//                                                             3-stage cp.async ring over L)
+//     panel  = A[rows >= 32k, block k] - acc                 (smem, aliases the ring)
+//     L_kk   = chol(panel diag 32x32), Linv = L_kk^-1        (one warp, registers,
+//                                                             rsqrt pivots, smem broadcast)
 //     panel[sub rows] = panel[sub rows] * Linv^T             (DMMA, triangular skip)
 //     write the panel back; keep Linv for the back-solve
 //   back-solve  L^T phi = (L^-1 b) + z  block by block from the bottom, using the
@@ -25,9 +26,11 @@
 namespace bvb {
 
 constexpr int K2_NB = 32;
-constexpr int K2_BKC = 8;
+constexpr int K2_BKC = 16;   // columns of L per pipeline stage (one per warp in the loader)
 constexpr int K2_STAGES = 3;
-constexpr int K2_LS = 36;  // row stride of the Linv^T tile (== 4 mod 16)
+constexpr int K2_LS = 36;    // row stride of the Linv^T tile (== 4 mod 16)
+constexpr int K2_NWARPS = 16;
+constexpr int K2_MAXQ = 4;   // m8 tiles per warp: 16 * 4 * 8 = 512 panel rows max
 
 __host__ __device__ inline int k2_row_stride(int n) {
   int rmax = (n + 1 > 33 ? n + 1 : 33) + 8;
@@ -35,32 +38,40 @@ __host__ __device__ inline int k2_row_stride(int n) {
 }
 __host__ __device__ inline int k2_nblocks(int n) { return (n + K2_NB - 1) / K2_NB; }
 
+// smem: [stage ring | panel (aliased)] [linvT] [ysol] [sblk] [colbuf 2x32] [rsbuf 32] [colbase ints]
 size_t k2_smem_bytes(int n) {
   size_t rs = k2_row_stride(n);
-  size_t d = (size_t)K2_NB * rs + (size_t)K2_STAGES * K2_BKC * rs + (size_t)K2_NB * K2_LS +
-             (size_t)(k2_nblocks(n) * K2_NB + 32) + 64;
+  size_t ring = (size_t)K2_STAGES * K2_BKC * rs, panel = (size_t)K2_NB * rs;
+  size_t d = (ring > panel ? ring : panel) + (size_t)K2_NB * K2_LS + (size_t)(k2_nblocks(n) * K2_NB + 32) +
+             32 + 64 + 32 + (size_t)(n + 3) / 2 + 8;
   return d * sizeof(double);
 }
 
-template <int NWARPS, int MAXQ>
-__global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws) {
+__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws) {
+  constexpr int NWARPS = K2_NWARPS, MAXQ = K2_MAXQ, NTHREADS = K2_NWARPS * 32;
   extern __shared__ __align__(16) double smem[];
   const int n = p.n, n1 = n + 1;
   const int RS = k2_row_stride(n);
   const int nbk = k2_nblocks(n);
-  double* panel = smem;                                   // [32][RS]   panel[c][li]
-  double* stage = panel + K2_NB * RS;                     // [STAGES][BKC][RS]
-  double* linvT = stage + K2_STAGES * K2_BKC * RS;        // [32][36]   linvT[c'][c] = Linv[c][c']
+  const size_t ring_d = (size_t)K2_STAGES * K2_BKC * RS, panel_d = (size_t)K2_NB * RS;
+  double* stage = smem;                                   // [STAGES][BKC][RS]
+  double* panel = smem;                                   // [32][RS]   panel[c][li]  (aliases the ring)
+  double* linvT = smem + (ring_d > panel_d ? ring_d : panel_d);  // [32][36] linvT[c'][c] = Linv[c][c']
   double* ysol = linvT + K2_NB * K2_LS;                   // [nbk*32 + 32]
-  double* sblk = ysol + nbk * K2_NB + 32;                 // [32] + flags
+  double* sblk = ysol + nbk * K2_NB + 32;                 // [32]
+  double* colbuf = sblk + 32;                             // [2][32]
+  double* rsbuf = colbuf + 64;                            // [32]
+  int* colb = reinterpret_cast<int*>(rsbuf + 32);         // [n]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int eq = blockIdx.x;
   double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
-  const int* __restrict__ colbase = p.colbase;
   double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
   int fail = 0;  // meaningful on warp 0 only
+
+  for (int i = tid; i < n; i += NTHREADS) colb[i] = p.colbase[i];
+  __syncthreads();
 
   for (int k = 0; k < nbk; ++k) {
     const int c0 = k * K2_NB;
@@ -69,44 +80,28 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
     const int nsub = n1 - kb_end;
     const int R = K2_NB + nsub;
     const bool full = (w == K2_NB);
+    const int mtiles = (R + 7) >> 3;
     // local row -> global row (or -1 for the virtual identity rows of a partial block)
     auto grow = [&](int li) -> int { return li < K2_NB ? (li < w ? c0 + li : -1) : kb_end + li - K2_NB; };
 
-    // ---- A: panel load -------------------------------------------------------
-    for (int idx = tid; idx < K2_NB * R; idx += NWARPS * 32) {
-      const int c = idx / R, li = idx - c * R;
-      double* dst = panel + c * RS + li;
-      if (c < w) {
-        const int g = grow(li);
-        if (g >= c0 + c) cp_async8(dst, om + colbase[c0 + c] + g);
-        else *dst = 0.0;
-      } else {
-        *dst = (li == c) ? 1.0 : 0.0;
-      }
-    }
-    cp_async_commit();
-
     // ---- B: left-looking update with the already-factorised columns -----------
+    // chunk = 16 columns of L, one column per warp in the loader (coalesced 16-byte cp.async)
     const int nchunks = c0 / K2_BKC;
     auto load_chunk = [&](int st, int ch) {
-      double* sbase = stage + st * (K2_BKC * RS);
+      double* sdst = stage + (size_t)st * (K2_BKC * RS) + warp * RS;
+      const double* src = om + colb[ch * K2_BKC + warp];
       if (full) {
         const int npair = (R + 1) >> 1;
-        for (int idx = tid; idx < K2_BKC * npair; idx += NWARPS * 32) {
-          const int kc = idx / npair, pr = idx - kc * npair;
-          cp_async16(sbase + kc * RS + 2 * pr, om + colbase[ch * K2_BKC + kc] + c0 + 2 * pr);
-        }
+        for (int pr = lane; pr < npair; pr += 32) cp_async16(sdst + 2 * pr, src + c0 + 2 * pr);
       } else {
-        for (int idx = tid; idx < K2_BKC * R; idx += NWARPS * 32) {
-          const int kc = idx / R, li = idx - kc * R;
+        for (int li = lane; li < R; li += 32) {
           const int g = grow(li);
-          if (g >= 0) cp_async8(sbase + kc * RS + li, om + colbase[ch * K2_BKC + kc] + g);
-          else sbase[kc * RS + li] = 0.0;
+          if (g >= 0) cp_async8(sdst + li, src + g);
+          else sdst[li] = 0.0;
         }
       }
     };
 
-    const int mtiles = (R + 7) >> 3;
     double acc[MAXQ][4][2];
 #pragma unroll
     for (int q = 0; q < MAXQ; ++q)
@@ -126,7 +121,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
         if (nxt < nchunks) load_chunk(nxt % K2_STAGES, nxt);
         cp_async_commit();
       }
-      const double* sb = stage + (ch % K2_STAGES) * (K2_BKC * RS);
+      const double* sb = stage + (size_t)(ch % K2_STAGES) * (K2_BKC * RS);
 #pragma unroll
       for (int ks = 0; ks < K2_BKC / 4; ++ks) {
         const double* col = sb + (4 * ks + fk) * RS + fr;
@@ -145,21 +140,38 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
       }
     }
     cp_async_wait<0>();
-    __syncthreads();
-    if (nchunks > 0) {
+    __syncthreads();   // ring is dead from here on; its memory becomes the panel
+
+    // ---- A: panel = A_orig - acc, straight from the accumulator fragments -------
 #pragma unroll
-      for (int q = 0; q < MAXQ; ++q) {
-        const int mt = warp + NWARPS * q;
-        const int li = 8 * mt + fr;
-        if (mt < mtiles && li < R) {
+    for (int q = 0; q < MAXQ; ++q) {
+      const int mt = warp + NWARPS * q;
+      const int li = 8 * mt + fr;
+      if (mt < mtiles && li < R) {
+        const int g = grow(li);
+        double orig[4][2];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) panel[(8 * nt + 2 * fk + e) * RS + li] -= acc[q][nt][e];
-        }
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * nt + 2 * fk + e;
+            double v;
+            if (c < w) v = (g >= c0 + c) ? om[colb[c0 + c] + g] : 0.0;
+            else v = (li == c) ? 1.0 : 0.0;
+            orig[nt][e] = v;
+          }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * nt + 2 * fk + e;
+            double v = orig[nt][e];
+            if (c < w && g >= c0 + c) v -= acc[q][nt][e];
+            panel[c * RS + li] = v;
+          }
       }
-      __syncthreads();
     }
+    __syncthreads();
 
     // ---- C: factor the 32x32 diagonal block and invert it (warp 0) -------------
     if (warp == 0) {
@@ -168,35 +180,37 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
       for (int c = 0; c < K2_NB; ++c) a[c] = (c <= lane) ? panel[c * RS + lane] : 0.0;
 #pragma unroll
       for (int c = 0; c < K2_NB; ++c) {
-        double dcc = __shfl_sync(0xffffffffu, a[c], c);
-        if (!(dcc > 0.0) || !isfinite(dcc)) {
+        double x = __shfl_sync(0xffffffffu, a[c], c);
+        if (!(x > 0.0) || !isfinite(x)) {
           if (fail == 0) fail = c0 + c + 1;
-          dcc = 1.0;
+          x = 1.0;
         }
-        const double d = sqrt(dcc);
-        a[c] = (lane > c) ? a[c] / d : ((lane == c) ? d : 0.0);
+        const double rs = rsqrt(x);
+        const double l = (lane >= c) ? a[c] * rs : 0.0;   // lane c: x * rsqrt(x) = sqrt(x)
+        a[c] = l;
+        double* cb = colbuf + (c & 1) * 32;
+        cb[lane] = l;
+        if (lane == c) rsbuf[c] = rs;
+        __syncwarp();
 #pragma unroll
-        for (int c2 = c + 1; c2 < K2_NB; ++c2) {
-          const double l2 = __shfl_sync(0xffffffffu, a[c], c2);
-          a[c2] -= a[c] * l2;
-        }
+        for (int c2 = c + 1; c2 < K2_NB; ++c2) a[c2] = fma(-l, cb[c2], a[c2]);
       }
 #pragma unroll
       for (int c = 0; c < K2_NB; ++c) panel[c * RS + lane] = a[c];
       __syncwarp();
-      // lane j solves L x = e_j  ->  column j of Linv
+      // lane j solves L x = e_j  ->  column j of Linv (reciprocal diagonal from rsbuf)
       double x[K2_NB];
 #pragma unroll
       for (int i = 0; i < K2_NB; ++i) {
         double s = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-        for (int kk = 0; kk < i; ++kk) s -= panel[kk * RS + i] * x[kk];
-        x[i] = (i >= lane) ? s / panel[i * RS + i] : 0.0;
+        for (int kk = 0; kk < i; ++kk) s = fma(-panel[kk * RS + i], x[kk], s);
+        x[i] = (i >= lane) ? s * rsbuf[i] : 0.0;
       }
 #pragma unroll
       for (int i = 0; i < K2_NB; ++i) {
-        linvT[lane * K2_LS + i] = x[i];            // linvT[c'=j][c=i] = Linv[i][j]
-        lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = x[i];  // ws[k][c'=i][c=j] = Linv[i][j]
+        linvT[lane * K2_LS + i] = x[i];                                        // linvT[c'=j][c=i] = Linv[i][j]
+        lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = x[i];            // ws[k][c'=i][c=j] = Linv[i][j]
       }
     }
     __syncthreads();
@@ -229,17 +243,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
     __syncthreads();
 
     // ---- E: write the factorised panel back; keep the forward-solved rhs --------
-    for (int idx = tid; idx < w * R; idx += NWARPS * 32) {
-      const int c = idx / R, li = idx - c * R;
-      const int g = grow(li);
-      if (g >= c0 + c) om[colbase[c0 + c] + g] = panel[c * RS + li];
+    for (int c = warp; c < w; c += NWARPS) {
+      double* dst = om + colb[c0 + c];
+      const double* src = panel + c * RS;
+      for (int li = lane; li < R; li += 32) {
+        const int g = grow(li);
+        if (g >= c0 + c) dst[g] = src[li];
+      }
     }
     if (tid < K2_NB) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;
     __syncthreads();
   }
 
   // ---- back-solve  L^T phi = y + z ------------------------------------------------
-  for (int i = tid; i < n; i += NWARPS * 32) ysol[i] += p.z[(size_t)eq * p.ldz + i];
+  for (int i = tid; i < n; i += NTHREADS) ysol[i] += p.z[(size_t)eq * p.ldz + i];
   __syncthreads();
   for (int k = nbk - 1; k >= 0; --k) {
     const int c0 = k * K2_NB;
@@ -248,8 +265,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
     for (int c = warp; c < K2_NB; c += NWARPS) {
       double s = 0.0;
       if (c < w) {
-        const double* colp = om + colbase[c0 + c];
-        for (int i = kb_end + lane; i < n; i += 32) s += colp[i] * ysol[i];
+        const double* colp = om + colb[c0 + c];
+        for (int i = kb_end + lane; i < n; i += 32) s = fma(colp[i], ysol[i], s);
         s = warp_sum(s);
       }
       if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
@@ -257,21 +274,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k2_cholsolve(const K2Params p,
     __syncthreads();
     if (warp == 0) {
       const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
-      double xv = 0.0;
-#pragma unroll 8
-      for (int cp = 0; cp < K2_NB; ++cp) xv += wsk[cp * K2_NB + lane] * sblk[cp];
-      if (lane < w) ysol[c0 + lane] = xv;
+      double xv0 = 0.0, xv1 = 0.0;
+#pragma unroll
+      for (int cp = 0; cp < K2_NB; cp += 2) {
+        xv0 = fma(wsk[cp * K2_NB + lane], sblk[cp], xv0);
+        xv1 = fma(wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
+      }
+      if (lane < w) ysol[c0 + lane] = xv0 + xv1;
     }
     __syncthreads();
   }
   bool bad = false;
-  for (int i = tid; i < n; i += NWARPS * 32) {
+  for (int i = tid; i < n; i += NTHREADS) {
     const double v = ysol[i];
     p.phi[(size_t)eq * p.ldphi + i] = v;
     bad |= !isfinite(v);
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
-  if (tid == 0) p.status[eq] = fail ? fail : (anybad ? -1 : 0);
+  // sticky: the first failure of an equation is kept until the host clears it
+  if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
 }
 
 static double* g_linv_ws = nullptr;
@@ -287,19 +308,10 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     g_linv_ws_bytes = need;
   }
   const size_t smem = k2_smem_bytes(p.n);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  // rows of the first updated panel decide how many m8 tiles a warp must hold
-  const int rmax = p.n + 1 - K2_NB;  // R of block k=1
-  cudaError_t e;
-  if (rmax <= 8 * 8 * 6) {
-    e = cudaFuncSetAttribute(k2_cholsolve<8, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k2_cholsolve<8, 6><<<p.M, 256, smem, s>>>(p, g_linv_ws);
-  } else {
-    e = cudaFuncSetAttribute(k2_cholsolve<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k2_cholsolve<16, 4><<<p.M, 512, smem, s>>>(p, g_linv_ws);
-  }
+  if (smem > 227 * 1024 || p.n + 1 > K2_NWARPS * K2_MAXQ * 8) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(k2_cholsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k2_cholsolve<<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws);
   return cudaGetLastError();
 }
 

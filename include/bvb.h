@@ -96,6 +96,148 @@ int bvb_gig(bvb_handle* h, int n, const double* lambda, int len_lambda,
             const double* chi, int len_chi, const double* psi, int len_psi,
             uint64_t stream, double* out);
 
+/* ---- a1/a6-a10/a12/a13: bvar_cpp() - the Gibbs sampler (src/bvar_cpp.cpp:10-857) ----
+ * The three structs mirror, key by key, the R lists bvar_cpp() receives
+ * (prior_phi_cpp: R/utility_functions.R:1585-1617, prior_sigma_cpp: :374-420,
+ * startvals: R/bvar_wrapper.R:352-385); the Rcpp shim fills them from the lists.
+ * Vectors are (pointer, implied length); n = K*M coefficients without intercepts,
+ * ordered as vec(PHI[0:K, ]) (column-major), n_U = M(M-1)/2 in trimatu_ind order. */
+#define BVB_PRIOR_NORMAL 0
+#define BVB_PRIOR_DL 1
+#define BVB_PRIOR_GT 2   /* R2D2: kernel exponential, vs 1/2;  NG: kernel normal, vs 1 */
+#define BVB_PRIOR_HS 3
+#define BVB_PRIOR_SSVS 4
+#define BVB_PRIOR_HMP 5
+#define BVB_PRIOR_NOTHING 6 /* lags = 0 (R/utility_functions.R:2001) */
+
+typedef struct bvb_prior_phi {
+  int prior;
+  const double* V_i;        /* [n]  prior "normal": fixed prior variances */
+  int n_groups;
+  const int* groups;        /* [n_groups] group ids as they appear in i_vec */
+  const double* a;          /* [n_groups] */
+  const double* b;          /* [n_groups] */
+  const double* c;          /* [n_groups] */
+  double GL_tol;
+  const double* a_vec;      /* [grid_len] */
+  const double* a_weight;   /* [grid_len] */
+  const double* norm_consts;/* [grid_len] */
+  const double* c_vec;      /* [grid_len] */
+  int grid_len;
+  int c_rel_a, DL_hyper, DL_plus, GT_hyper;
+  double GT_vs;
+  int GT_priorkernel;       /* 0 = "normal", 1 = "exponential" */
+  const double* SSVS_tau0;  /* [n] */
+  const double* SSVS_tau1;  /* [n] */
+  double SSVS_s_a, SSVS_s_b;
+  int SSVS_hyper;
+  const double* SSVS_p;     /* [n] */
+  const double* V_i_prep;   /* [n + M*intercept] (HMP) */
+  double lambda_1[2];       /* HMP shape, rate */
+  double lambda_2[2];
+} bvb_prior_phi;
+
+#define BVB_SIGMA_FACTOR 0
+#define BVB_SIGMA_CHOLESKY 1
+
+typedef struct bvb_prior_sigma {
+  int type;                      /* BVB_SIGMA_FACTOR | BVB_SIGMA_CHOLESKY */
+  /* cholesky_* keys: same meaning as bvb_prior_phi for the n_U free elements of U */
+  int cholesky_U_prior;
+  const double* cholesky_V_i;
+  double cholesky_a, cholesky_b, cholesky_c, cholesky_GL_tol;
+  const double* cholesky_a_vec; const double* cholesky_a_weight;
+  const double* cholesky_norm_consts; const double* cholesky_c_vec;
+  int cholesky_grid_len;
+  int cholesky_c_rel_a, cholesky_DL_hyper, cholesky_DL_plus, cholesky_GT_hyper;
+  double cholesky_GT_vs;
+  int cholesky_GT_priorkernel;
+  const double* cholesky_SSVS_tau0; const double* cholesky_SSVS_tau1;
+  double cholesky_SSVS_s_a, cholesky_SSVS_s_b;
+  int cholesky_SSVS_hyper;
+  const double* cholesky_SSVS_p;
+  double cholesky_lambda_3[2];
+  const double* cholesky_priorhomoscedastic; /* M x 2 */
+  const double* cholesky_sv_offset;          /* [M] */
+  /* factor_* keys */
+  int factor_factors;
+  const double* factor_shrink_a;  /* [M] rowwise | [r] columnwise */
+  const double* factor_shrink_c;
+  const double* factor_shrink_d;
+  int factor_ngprior, factor_columnwise;
+  double factor_facloadtol;
+  const int* factor_restrinv;     /* M x r, 1 = unrestricted */
+  const double* factor_priorhomoskedastic; /* M x 2 */
+  int factor_interweaving;
+  /* sv_* keys */
+  const int* sv_heteroscedastic;  /* [M (+ r)] */
+  double sv_priormu[2];           /* mean, sd */
+  double sv_priorphi[4];          /* idi a,b (, fac a,b) */
+  const double* sv_priorsigma2;   /* (M + r) x 2: shape, rate */
+  const double* sv_priorh0;       /* [M (+ r)]  <= 0: stationary */
+} bvb_prior_sigma;
+
+typedef struct bvb_startvals {
+  const double* PHI;         /* Kp x M */
+  const double* U;           /* M x M (cholesky) */
+  const double* sv_para;     /* 3 x (M + r) */
+  const double* sv_logvar;   /* T x (M + r) */
+  const double* sv_logvar0;  /* [M + r] */
+  const double* facload;     /* M x r */
+  const double* fac;         /* r x T */
+  const double* tau2;        /* M x r */
+} bvb_startvals;
+
+/* Caller-owned draw storage, laid out exactly like the arrays bvar_cpp() returns
+ * (src/bvar_cpp.cpp:409-482, :751-836); nsave = draws / thin.  NULL = not wanted. */
+typedef struct bvb_draws {
+  double* PHI;                /* Kp x M x nsave */
+  double* U;                  /* n_U x nsave */
+  double* logvar;             /* (T | 1) x (M + r) x nsave */
+  double* sv_para;            /* 3 x (M + r) x nsave */
+  double* phi_hyperparameter; /* size x nsave (rows as bvar_cpp.cpp:758-790) */
+  double* u_hyperparameter;
+  double* V_prior;            /* Kp x M x nsave */
+  double* facload;            /* M x r x nsave */
+  double* fac;                /* r x (T | 1) x nsave */
+} bvb_draws;
+
+/* Set up a chain on the handle's device.  Argument meaning = bvar_cpp()'s
+ * (src/bvar_cpp.cpp:10-30); tvp_keep_all: 1 = "all", 0 = "last".  i_vec is the
+ * vectorised indicator matrix ((K + intercept) * M ints; 0 = intercept).  Everything
+ * is copied to the device; the caller's inputs are never modified.
+ * Multi-GPU (factor structure): call bvb_comm_init first; equations are then
+ * sharded over the ranks, every rank passes identical arguments, and rank 0's
+ * bvb_draws receives the stored draws. */
+int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T, int K,
+                   int draws, int burnin, int thin, int tvp_keep_all, int intercept,
+                   const double* priorIntercept, const double* PHI0,
+                   const bvb_prior_phi* prior_phi, const bvb_prior_sigma* prior_sigma,
+                   const bvb_startvals* startvals, const int* i_vec,
+                   double PHI_tol, double L_tol, int huge, const bvb_draws* out);
+
+/* Run up to max_sweeps further sweeps (the shim calls this with 256 so it can
+ * poll R interrupts and print progress like bvar_cpp.cpp:501-503,838-843).
+ * *done receives the number of sweeps completed so far (== draws + burnin at the
+ * end).  Stored draws are written into the bvb_draws given to bvb_gibbs_init. */
+int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done);
+
+/* Device time of the sweeps run by the last bvb_gibbs_run call: out[0] total ms
+ * (CUDA events on the sampler stream), out[1] = kernels launched per sweep,
+ * out[2..9] = ms per sweep of {prep, K1, K2, hyper, resid, sv, store, comm}
+ * sampled on the last sweep.  Returns sweeps timed. */
+int bvb_gibbs_timing(const bvb_handle* h, double* out10);
+
+/* Copy the current sampler state back (for tests): any pointer may be NULL. */
+int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,
+                    double* sv_para, double* facload, double* fac, double* U);
+
+/* Multi-GPU plumbing: one process per GPU.  unique_id is the 128-byte
+ * ncclUniqueId produced by bvb_comm_unique_id on rank 0 and broadcast by the
+ * launcher (torch.distributed / MPI / a file). */
+int bvb_comm_unique_id(char* unique_id_128);
+int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128);
+
 /* ---- diagnostics -------------------------------------------------------------
  * Measured FP64 peaks on this device (own micro-kernels, register-resident):
  * out[0] = DMMA m8n8k4 TFLOP/s, out[1] = DFMA TFLOP/s, out[2] = SM clock MHz
