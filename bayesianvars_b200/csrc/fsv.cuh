@@ -20,11 +20,11 @@ struct FsvDev {
   double* fac = nullptr;            // r x T
   double* tau2 = nullptr;           // M x r
   double* lambda2 = nullptr;        // [M] rowwise | [r] columnwise
-  // scratch (time-major: index t*(M+r) + s)
-  double* ystar = nullptr;          // T x S
-  double* eps = nullptr;            // (T+1) x S
-  unsigned char* mixind = nullptr;  // T x S
-  double* scratch = nullptr;        // 3 (T+1) x S
+  // scratch (series-major)
+  double* ystar = nullptr;          // [S][T]
+  double* eps = nullptr;            // [S][T+1]
+  unsigned char* mixind = nullptr;  // [S][T]
+  double* scratch = nullptr;        // unused by the CTA-per-series kernel
   double* eidi = nullptr;           // T x M idiosyncratic residuals (series-major)
   int* status = nullptr;
   // configuration

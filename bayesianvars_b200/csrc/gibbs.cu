@@ -566,15 +566,12 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   int todo = std::min(max_sweeps, tot - G.rep);
   if (todo < 0) todo = 0;
   h->err_step = 0;
-  // capture one sweep into a graph on first use
+  // First sweep ever: eager (allocates lazily-sized workspaces, sets kernel
+  // attributes), then one sweep's launches are captured into a graph.
   if (!G.graph_exec && todo > 0) {
-    // timing pass (eager, with per-phase events) doubles as warm-up of nothing: it IS sweep 0
-    G.timing_pass = true;
     int rc = enqueue_sweep(h, G);
-    G.timing_pass = false;
     if (rc) return rc;
     GB_TRY(cudaStreamSynchronize(s));
-    for (int i = 0; i < 8; ++i) { float ms = 0; cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]); G.phase_ms[i] = ms; }
     G.rep += 1;
     todo -= 1;
     cudaGraph_t graph;
@@ -589,6 +586,10 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
     cudaGraphDestroy(graph);
   }
+  // Per-phase device times: the LAST sweep of every call with >= 8 sweeps is
+  // launched eagerly with CUDA events between the phases (warm caches).
+  const bool time_last = (todo >= 8);
+  if (time_last) todo -= 1;
   // Sub-chunks of <= 64 sweeps (and <= ring_slots stored draws).  The D2H copy of a
   // sub-chunk's stored draws is queued behind its sweeps; the host scatters the
   // PREVIOUS sub-chunk into the caller's arrays while the GPU runs the next one.
@@ -625,9 +626,32 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     if (rc) return rc;
     pend = cur;
   }
+  if (time_last) {
+    const int stored_before = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
+    GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
+    G.timing_pass = true;
+    int rc = enqueue_sweep(h, G);
+    G.timing_pass = false;
+    if (rc) return rc;
+    G.rep += 1;
+    ran += 1;
+    const int stored_after = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
+    if (stored_after > stored_before) {
+      rc = flush(pend);
+      if (rc) return rc;
+      GB_TRY(cudaMemcpyAsync(G.pinned[flip], G.ring.p, sizeof(double) * G.store.slot_doubles, cudaMemcpyDeviceToHost, s));
+      GB_TRY(cudaEventRecord(G.ev_pin[flip], s));
+      pend = {flip, stored_before, 1};
+      flip ^= 1;
+    }
+    G.timed = true;
+  }
   {
     int rc = flush(pend);
     if (rc) return rc;
+  }
+  if (time_last) {
+    for (int i = 0; i < 8; ++i) { float ms = 0; cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]); G.phase_ms[i] = ms; }
   }
   GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
   GB_TRY(cudaStreamSynchronize(s));

@@ -84,7 +84,7 @@ struct Gibbs {
   int hyper_rows = 0;
   // execution
   cudaGraphExec_t graph_exec = nullptr;
-  bool timing_pass = false;
+  bool timing_pass = false, timed = false;
   cudaEvent_t ev[9] = {};
   cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
   float phase_ms[8] = {0};

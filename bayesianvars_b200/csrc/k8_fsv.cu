@@ -14,7 +14,8 @@
 // Parity is unpinned (distributional only).
 //
 // Parallel shape: indicators + AWOL normals: one thread per (t, series);
-// h / (mu,phi,sigma): one thread per series (time-major scratch, coalesced);
+// h / (mu,phi,sigma): one CTA per series (shared-memory recursion on one thread,
+// sufficient statistics and element-wise parts on all 128);
 // loadings: one warp per row; factors: one thread per t.
 #include "fsv.cuh"
 
@@ -24,12 +25,13 @@ constexpr uint32_t STREAM_SV_ELEM = 0x100, STREAM_SV_SERIES = 0x101, STREAM_FSV_
                    STREAM_FSV_LOAD = 0x103, STREAM_FSV_IW = 0x104, STREAM_FSV_FAC = 0x105;
 
 // ystar, mixture indicators (from the current h) and the AWOL normals.
+// Series-major scratch: ystar / mixind [s*T + t], eps [s*(T+1) + t].
 __global__ void fsv_elem_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
   const uint32_t sweep = *sweep_p;
   const int S = d.M + d.r;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)(d.T + 1) * S) return;
-  const int s = (int)(idx % S), t = (int)(idx / S);  // time-major
+  const int s = (int)(idx / (d.T + 1)), t = (int)(idx % (d.T + 1));
   RngStream rng(seed, STREAM_SV_ELEM, (uint32_t)idx, sweep);
   d.eps[idx] = rng.normal();
   if (t >= d.T) return;
@@ -43,36 +45,127 @@ __global__ void fsv_elem_kernel(const FsvDev d, uint64_t seed, const uint32_t* s
     const double f = d.fac[(size_t)t * d.r + (s - d.M)];
     ys = log(f * f);
   }
-  d.ystar[idx] = ys;
-  d.mixind[idx] = (unsigned char)sv_draw_indicator(ys - d.logvar[(size_t)s * d.T + t], rng.uniform());
+  d.ystar[(size_t)s * d.T + t] = ys;
+  d.mixind[(size_t)s * d.T + t] = (unsigned char)sv_draw_indicator(ys - d.logvar[(size_t)s * d.T + t], rng.uniform());
 }
 
-__global__ void fsv_series_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+constexpr int SV_THREADS = 128;
+
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double* sh /* [N][SV_THREADS/32] */) {
+  // fixed-order (deterministic) block reduction of N values; result broadcast to all threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v[i] = warp_sum(v[i]);
+    if (lane == 0) sh[i * (SV_THREADS / 32) + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < SV_THREADS / 32; ++w) t += sh[i * (SV_THREADS / 32) + w];
+    v[i] = t;
+  }
+  __syncthreads();
+}
+
+// One CTA per series: the element-wise parts and the sufficient statistics use
+// all threads, only the (T+1)-step tridiagonal recursion and the scalar
+// parameter draws run on thread 0, out of shared memory.
+__global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double red[8 * (SV_THREADS / 32)];
+  __shared__ double bc[4];
   const uint32_t sweep = *sweep_p;
-  const int S = d.M + d.r;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
+  const int S = d.M + d.r, T = d.T, tid = threadIdx.x;
+  const int s = blockIdx.x;
+  double* h = d.logvar + (size_t)s * T;
+  if (!d.hetero[s]) {
+    if (s < d.M) {
+      // homoskedastic idiosyncratic variance: inverse gamma (factorstochvol; bvar_cpp.cpp:728-732 analogue)
+      double ss[1] = {0.0};
+      for (int t = tid; t < T; t += SV_THREADS) { const double e = d.eidi[(size_t)s * T + t]; ss[0] += e * e; }
+      block_sum<1>(ss, red);
+      if (tid == 0) {
+        RngStream rng(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+        bc[0] = log((d.priorhomo[d.M + s] + 0.5 * ss[0]) / rng.gamma(d.priorhomo[s] + 0.5 * T));
+      }
+      __syncthreads();
+      for (int t = tid; t < T; t += SV_THREADS) h[t] = bc[0];
+    }  // homoskedastic factors keep h == 0
+    return;
+  }
+  double* od = sm;                 // [T+1]
+  double* c = od + (T + 1);        // [T+1]
+  double* lo = c + (T + 1);        // [T+1]
+  double* hh = lo + (T + 1);       // [T+1]  hh[0] = h0
+  double* ep = hh + (T + 1);       // [T+1]
+  double* ys = ep + (T + 1);       // [T]
+  unsigned char* rr = reinterpret_cast<unsigned char*>(ys + T);  // [T]
+  SvPrior pr;
+  pr.mu_mean = d.priormu[0]; pr.mu_sd = d.priormu[1];
+  pr.phi_a = d.priorphi[s < d.M ? 0 : 2]; pr.phi_b = d.priorphi[s < d.M ? 1 : 3];
+  pr.s2_shape = d.priorsigma2[s]; pr.s2_rate = d.priorsigma2[S + s];
+  pr.h0_var = d.priorh0[s];
+  pr.mu_const = (s >= d.M) ? 1 : 0;
+  double mu = pr.mu_const ? 0.0 : d.sv_para[3 * s + 0], phi = d.sv_para[3 * s + 1], sigma = d.sv_para[3 * s + 2];
+  for (int t = tid; t < T; t += SV_THREADS) {
+    ys[t] = d.ystar[(size_t)s * T + t];
+    rr[t] = d.mixind[(size_t)s * T + t];
+  }
+  for (int t = tid; t <= T; t += SV_THREADS) ep[t] = d.eps[(size_t)s * (T + 1) + t];
+  __syncthreads();
+  // (a) tridiagonal system, AWOL draw
+  {
+    const double s2inv = 1.0 / (sigma * sigma);
+    const double B0inv = (pr.h0_var <= 0.0) ? (1.0 - phi * phi) : 1.0 / pr.h0_var;
+    for (int t = tid; t <= T; t += SV_THREADS)
+      sv_system_row(t, T, t > 0 ? ys[t - 1] : 0.0, t > 0 ? rr[t - 1] : 0, mu, phi, s2inv, B0inv, od[t], c[t]);
+    __syncthreads();
+    if (tid == 0) sv_awol(T, -phi * s2inv, od, c, lo, ep, hh);
+    __syncthreads();
+  }
+  // (b) centered draw
   RngStream rng(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
-  double* h = d.logvar + (size_t)s * d.T;
-  if (d.hetero[s]) {
-    SvPrior pr;
-    pr.mu_mean = d.priormu[0]; pr.mu_sd = d.priormu[1];
-    pr.phi_a = d.priorphi[s < d.M ? 0 : 2]; pr.phi_b = d.priorphi[s < d.M ? 1 : 3];
-    pr.s2_shape = d.priorsigma2[s]; pr.s2_rate = d.priorsigma2[S + s];
-    pr.h0_var = d.priorh0[s];
-    pr.mu_const = (s >= d.M) ? 1 : 0;
-    double mu = d.sv_para[3 * s + 0], phi = d.sv_para[3 * s + 1], sigma = d.sv_para[3 * s + 2], h0 = d.logvar0[s];
-    sv_update_series(rng, d.T, d.ystar + s, h, h0, mu, phi, sigma, d.mixind + s, d.eps + s, pr, d.scratch + s, S);
-    d.sv_para[3 * s + 0] = mu; d.sv_para[3 * s + 1] = phi; d.sv_para[3 * s + 2] = sigma;
-    d.logvar0[s] = h0;
-  } else if (s < d.M) {
-    // homoskedastic idiosyncratic variance: inverse gamma (factorstochvol; bvar_cpp.cpp:728-732 analogue)
-    double ss = 0.0;
-    for (int t = 0; t < d.T; ++t) { const double e = d.eidi[(size_t)s * d.T + t]; ss += e * e; }
-    const double v = (d.priorhomo[d.M + s] + 0.5 * ss) / rng.gamma(d.priorhomo[s] + 0.5 * d.T);
-    const double lv = log(v);
-    for (int t = 0; t < d.T; ++t) h[t] = lv;
-  }  // homoskedastic factors keep h == 0
+  {
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int t = 1 + tid; t <= T; t += SV_THREADS) {
+      const double a = hh[t - 1], b = hh[t];
+      v[0] += a; v[1] += b; v[2] += a * b; v[3] += a * a; v[4] += b * b;
+    }
+    block_sum<5>(v, red);
+    if (tid == 0) {
+      SvCSums cs = {v[0], v[1], v[2], v[3], v[4]};
+      sv_draw_centered(rng, T, cs, hh[0], mu, phi, sigma, pr);
+      bc[0] = mu; bc[1] = phi; bc[2] = sigma;
+    }
+    __syncthreads();
+    mu = bc[0]; phi = bc[1]; sigma = bc[2];
+  }
+  // (b') non-centered draw (ASIS) and transformation back
+  {
+    const double mu_c = mu, sg_c = sigma;
+    SvNSums ns = {0, 0, 0, 0, 0, 0, 0};
+    for (int t = 1 + tid; t <= T; t += SV_THREADS)
+      sv_nc_accumulate(ns, (hh[t] - mu_c) / sg_c, (hh[t - 1] - mu_c) / sg_c, ys[t - 1], rr[t - 1]);
+    double v[7] = {ns.p00, ns.p01, ns.p11, ns.l0, ns.l1, ns.n_prev2, ns.n_cross};
+    block_sum<7>(v, red);
+    if (tid == 0) {
+      SvNSums tot = {v[0], v[1], v[2], v[3], v[4], v[5], v[6]};
+      double mu_n, sg_n;
+      sv_draw_noncentered(rng, tot, (hh[0] - mu_c) / sg_c, mu_n, sg_n, phi, pr);
+      bc[0] = mu_n; bc[1] = sg_n; bc[2] = phi;
+    }
+    __syncthreads();
+    const double mu_n = bc[0], sg_n = bc[1];
+    for (int t = 1 + tid; t <= T; t += SV_THREADS) h[t - 1] = mu_n + sg_n * ((hh[t] - mu_c) / sg_c);
+    if (tid == 0) {
+      d.logvar0[s] = mu_n + sg_n * ((hh[0] - mu_c) / sg_c);
+      d.sv_para[3 * s + 0] = mu_n; d.sv_para[3 * s + 1] = bc[2]; d.sv_para[3 * s + 2] = fabs(sg_n);
+    }
+  }
 }
 
 // Normal-gamma prior on the loadings: lambda2 then tau2 (Kastner 2019, eq. 6-7).
@@ -282,7 +375,11 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
   const int S = d.M + d.r;
   const size_t nel = (size_t)(d.T + 1) * S;
   fsv_elem_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(d, seed, sweep);
-  fsv_series_kernel<<<(S + 31) / 32, 32, 0, s>>>(d, seed, sweep);
+  {
+    const size_t smem = (size_t)(6 * (d.T + 1)) * sizeof(double) + (size_t)d.T + 16;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fsv_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fsv_series_kernel<<<S, SV_THREADS, smem, s>>>(d, seed, sweep);
+  }
   if (d.r > 0) {
     if (d.ngprior) {
       const int units = d.columnwise ? d.r : d.M;
