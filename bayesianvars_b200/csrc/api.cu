@@ -1,6 +1,7 @@
 // C ABI of libbvb.so (see include/bvb.h).  Host orchestration only: every
 // number a caller sees is produced by the sm_100a kernels; there is no CPU path.
 #include "bvb_internal.cuh"
+#include "gig.cuh"
 
 #include <string.h>
 #include <new>
@@ -77,6 +78,16 @@ __global__ void fill_normals_kernel(double* out, size_t n, uint64_t seed, uint32
   if (i >= n) return;
   RngStream rng(seed, stream, (uint32_t)i, (uint32_t)(i >> 32));
   out[i] = rng.normal();
+}
+
+// out[i + n*j] = GIG(lambda[j % ll], chi[j % lc], psi[j % lp])   (gig_vec.cpp:20-43)
+__global__ void gig_vec_kernel(double* out, int n, int m, const double* lambda, int ll, const double* chi, int lc,
+                               const double* psi, int lp, uint64_t seed, uint64_t stream) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * m) return;
+  const int j = (int)(idx / n);
+  RngStream rng(seed, 0x6000u + (uint32_t)(stream & 0xfffu), (uint32_t)idx, (uint32_t)(stream >> 12));
+  out[idx] = gig_draw(rng, lambda[j % ll], chi[j % lc], psi[j % lp]);
 }
 
 int setup_geometry(bvb_handle* h, PhiWorkspace& ws, int T, int n, int M, int r) {
@@ -291,11 +302,43 @@ int bvb_sample_u(bvb_handle* h, int T, int M, const double* resid, const double*
 
 int bvb_gig(bvb_handle* h, int n, const double* lambda, int len_lambda, const double* chi,
             int len_chi, const double* psi, int len_psi, uint64_t stream, double* out) {
-  (void)n; (void)lambda; (void)len_lambda; (void)chi; (void)len_chi; (void)psi; (void)len_psi;
-  (void)stream; (void)out;
   if (!h) return BVB_ERR_ARG;
-  bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gig: not built yet");
-  return BVB_ERR_UNSUPPORTED;
+  h->err_code = 0; h->err_step = 2; h->err_msg[0] = 0;
+  if (n < 0 || len_lambda <= 0 || len_chi <= 0 || len_psi <= 0 || !lambda || !chi || !psi || (n > 0 && !out)) {
+    bvb_set_error(h, BVB_ERR_ARG, "bvb_gig: invalid argument");
+    return BVB_ERR_ARG;
+  }
+  const int m = len_lambda > len_chi ? (len_lambda > len_psi ? len_lambda : len_psi) : (len_chi > len_psi ? len_chi : len_psi);
+  const size_t tot = (size_t)n * m;
+  if (tot == 0) return BVB_OK;
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  DevBuf<double> dl, dc, dp, dout;
+  cudaStream_t s = h->stream;
+  auto fin = [&](int rc) { dl.release(); dc.release(); dp.release(); dout.release(); return rc; };
+  if (dl.ensure(len_lambda) || dc.ensure(len_chi) || dp.ensure(len_psi) || dout.ensure(tot)) {
+    bvb_set_error(h, BVB_ERR_CUDA, "bvb_gig: allocation failed");
+    return fin(BVB_ERR_CUDA);
+  }
+  cudaMemcpyAsync(dl.p, lambda, sizeof(double) * len_lambda, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dc.p, chi, sizeof(double) * len_chi, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dp.p, psi, sizeof(double) * len_psi, cudaMemcpyHostToDevice, s);
+  gig_vec_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(dout.p, n, m, dl.p, len_lambda, dc.p, len_chi, dp.p, len_psi, h->seed, stream);
+  cudaMemcpyAsync(out, dout.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    bvb_set_error(h, BVB_ERR_CUDA, "bvb_gig: %s", cudaGetErrorString(e));
+    return fin(BVB_ERR_CUDA);
+  }
+  for (size_t i = 0; i < tot; ++i) {
+    if (out[i] != out[i]) {  // NaN <=> invalid parameters (the reference raises an R error)
+      const size_t j = i / (size_t)n;
+      bvb_set_error(h, BVB_ERR_ARG, "invalid parameters for GIG distribution: lambda=%g, chi=%g, psi=%g",
+                    lambda[j % len_lambda], chi[j % len_chi], psi[j % len_psi]);
+      return fin(BVB_ERR_ARG);
+    }
+  }
+  return fin(BVB_OK);
 }
 
 }  // extern "C"

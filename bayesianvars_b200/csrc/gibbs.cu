@@ -232,6 +232,8 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
     gibbs_clamp_kernel<<<(unsigned)((nphi + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
                                                                      G.PHI_tol, h->seed, sw, G.status.p);
+  } else {
+    mark(1); mark(2); mark(3); mark(4);
   }
   // ---- 2) hyper-parameters of the prior on PHI
   if (G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING) {
@@ -651,7 +653,11 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     if (rc) return rc;
   }
   if (time_last) {
-    for (int i = 0; i < 8; ++i) { float ms = 0; cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]); G.phase_ms[i] = ms; }
+    for (int i = 0; i < 8; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]) != cudaSuccess) { ms = 0; cudaGetLastError(); }
+      G.phase_ms[i] = ms;
+    }
   }
   GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
   GB_TRY(cudaStreamSynchronize(s));
