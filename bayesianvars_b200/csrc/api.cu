@@ -4,6 +4,7 @@
 #include "gig.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 using namespace bvb;
@@ -257,8 +258,21 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
   K2Params k2{};
   k2.omega = ws.omega.p; k2.colbase = ws.colbase.p; k2.z = ws.Z.p; k2.phi = ws.PHI.p; k2.status = ws.status.p;
   k2.n = Kp; k2.M = M; k2.ldo = ws.g.ldo; k2.ldz = Kp; k2.ldphi = Kp;
+  static long long* d_prof = nullptr;
+  if (getenv("BVB_K2_DEBUG")) k2.debug_mode = atoi(getenv("BVB_K2_DEBUG"));
+  if (getenv("BVB_K2_PROF")) {
+    if (!d_prof) cudaMalloc(&d_prof, 8 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), s);
+    k2.prof = d_prof;
+  }
   BVB_CUDA_TRY(launch_k2(k2, s));
   BVB_CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  if (k2.prof) {
+    long long hp[8];
+    cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "K2 phase cycles (CTA 0): gemm=%lld fill=%lld factor=%lld invert=%lld trsm=%lld writeback=%lld backsolve=%lld\n", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+  }
   BVB_CUDA_TRY(cudaMemcpyAsync(PHI_out, ws.PHI.p, szKM, cudaMemcpyDeviceToHost, s));
   BVB_CUDA_TRY(cudaMemcpyAsync(ws.h_status.data(), ws.status.p, sizeof(int) * M, cudaMemcpyDeviceToHost, s));
   BVB_CUDA_TRY(cudaStreamSynchronize(s));

@@ -78,6 +78,8 @@ struct K2Params {
   int n, M;
   long ldo;
   int ldz, ldphi;
+  long long* prof = nullptr;  // optional [8] phase cycle counters (debug)
+  int debug_mode = 0;         // 1: skip the DMMA of the update loop, 2: skip its loads (timing experiments only)
 };
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s);
 size_t k2_smem_bytes(int n);

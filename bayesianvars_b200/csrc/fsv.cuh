@@ -26,6 +26,7 @@ struct FsvDev {
   unsigned char* mixind = nullptr;  // [S][T]
   double* scratch = nullptr;        // unused by the CTA-per-series kernel
   double* eidi = nullptr;           // T x M idiosyncratic residuals (series-major)
+  double* wexp = nullptr;           // T x M exp(-h) of the idiosyncratic series (refreshed by the series kernel)
   int* status = nullptr;
   // configuration
   const int* hetero = nullptr;      // [M+r]

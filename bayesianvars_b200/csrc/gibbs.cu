@@ -68,37 +68,44 @@ __global__ void gibbs_scatter_V_kernel(double* Vprior, const double* V_i, int K,
   Vprior[(size_t)j * Kp + k] = V_i[idx];
 }
 
-// resid = Y - X PHI  (T x M); 32 x 32 output tile per CTA, K streamed through smem.
-__global__ void __launch_bounds__(256) gibbs_resid_kernel(double* __restrict__ resid, const double* __restrict__ Y,
+// resid = Y - X PHI  (T x M, bvar_cpp.cpp:611).  One warp per 8 x 8 output tile:
+// DMMA m8n8k4 with both operands read straight from L2 (X 1.6 MB and PHI 0.3 MB
+// stay resident); A[m][k] = X[t0+m, k], B[k][n] = PHI[k, j0+n].
+__global__ void __launch_bounds__(128) gibbs_resid_kernel(double* __restrict__ resid, const double* __restrict__ Y,
                                                           const double* __restrict__ X, const double* __restrict__ PHI,
                                                           int T, int Kp, int M) {
-  __shared__ double sX[32][33];   // [k][t]
-  __shared__ double sP[32][33];   // [k][j]
-  const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7
-  double acc[4] = {0, 0, 0, 0};
-  for (int k0 = 0; k0 < Kp; k0 += 32) {
-    for (int kk = ty; kk < 32; kk += 8) {
-      const int k = k0 + kk;
-      sX[kk][tx] = (k < Kp && t0 + tx < T) ? X[(size_t)k * T + t0 + tx] : 0.0;
-    }
-    for (int jj = ty; jj < 32; jj += 8) {
-      const int k = k0 + tx;
-      sP[tx][jj] = (k < Kp && j0 + jj < M) ? PHI[(size_t)(j0 + jj) * Kp + k] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk) {
-      const double xv = sX[kk][tx];
+  const int lane = threadIdx.x & 31;
+  const int ntj = (M + 7) / 8;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= ((T + 7) / 8) * ntj) return;
+  const int t0 = (tile / ntj) * 8, j0 = (tile % ntj) * 8;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int tr = min(t0 + fr, T - 1), jc = min(j0 + fr, M - 1);
+  const double* xa = X + tr;
+  const double* pb = PHI + (size_t)jc * Kp;
+  double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+  int k = 0;
+  for (; k + 32 <= Kp; k += 32) {   // 8 k4-steps per trip: 16 independent L2 loads in flight per lane
+    double av[8], bv[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fma(xv, sP[kk][ty + 8 * q], acc[q]);
+    for (int q = 0; q < 8; ++q) { av[q] = xa[(size_t)(k + 4 * q + fk) * T]; bv[q] = pb[k + 4 * q + fk]; }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      dmma884(c0, c1, av[q], bv[q]);
+      dmma884(d0, d1, av[q + 1], bv[q + 1]);
     }
-    __syncthreads();
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int t = t0 + tx, j = j0 + ty + 8 * q;
-    if (t < T && j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - acc[q];
+  for (; k < Kp; k += 4) {
+    const int kk = k + fk;
+    const double a0 = kk < Kp ? xa[(size_t)kk * T] : 0.0;
+    const double b0 = kk < Kp ? pb[kk] : 0.0;
+    dmma884(c0, c1, a0, b0);
+  }
+  c0 += d0; c1 += d1;
+  const int t = t0 + fr, j = j0 + 2 * fk;
+  if (t < T) {
+    if (j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - c0;
+    if (j + 1 < M) resid[(size_t)(j + 1) * T + t] = Y[(size_t)(j + 1) * T + t] - c1;
   }
 }
 
@@ -244,8 +251,8 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   mark(5);
   // ---- resid = Y - X PHI
   if (Kp > 0) {
-    dim3 grid((T + 31) / 32, (M + 31) / 32);
-    gibbs_resid_kernel<<<grid, 256, 0, s>>>(G.resid.p, G.Y.p, G.X.p, G.PHI.p, T, Kp, M);
+    const int tiles = ((T + 7) / 8) * ((M + 7) / 8);
+    gibbs_resid_kernel<<<(tiles + 3) / 4, 128, 0, s>>>(G.resid.p, G.Y.p, G.X.p, G.PHI.p, T, Kp, M);
   }
   mark(6);
   // ---- 3) Sigma_t
@@ -478,9 +485,10 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   GB_TRY(G.mixind.ensure((size_t)T * S));
   GB_TRY(G.svscratch.ensure((size_t)3 * (T + 1) * S));
   GB_TRY(G.eidi.ensure((size_t)T * M));
+  GB_TRY(G.wexp.ensure((size_t)T * M));
   F.resid = G.resid.p; F.logvar = G.logvar.p; F.logvar0 = G.logvar0.p; F.sv_para = G.sv_para.p;
   F.facload = G.facload.p; F.fac = G.fac.p; F.tau2 = G.tau2.p; F.lambda2 = G.lambda2.p;
-  F.ystar = G.ystar.p; F.eps = G.eps.p; F.mixind = G.mixind.p; F.scratch = G.svscratch.p; F.eidi = G.eidi.p;
+  F.ystar = G.ystar.p; F.eps = G.eps.p; F.mixind = G.mixind.p; F.scratch = G.svscratch.p; F.eidi = G.eidi.p; F.wexp = G.wexp.p;
   F.status = G.status.p + 1;
   F.hetero = G.hetero.p; F.restr = G.restr.p; F.offset = G.offset.p; F.priorsigma2 = G.priorsigma2.p;
   F.priorh0 = G.priorh0.p; F.priorhomo = G.priorhomo.p;

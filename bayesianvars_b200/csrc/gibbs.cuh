@@ -70,7 +70,7 @@ struct Gibbs {
   GibbsHyper hphi;
   // Sigma_t block
   FsvDev fsv;
-  GBuf<double> logvar, logvar0, sv_para, facload, fac, tau2, lambda2, ystar, eps, svscratch, eidi;
+  GBuf<double> logvar, logvar0, sv_para, facload, fac, tau2, lambda2, ystar, eps, svscratch, eidi, wexp;
   GBuf<double> offset, priorsigma2, priorh0, priorhomo, shrink_a, shrink_c, shrink_d;
   GBuf<unsigned char> mixind;
   GBuf<int> hetero, restr;

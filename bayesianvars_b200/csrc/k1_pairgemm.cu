@@ -27,6 +27,23 @@
 
 namespace bvb {
 
+// DMMA work of one pipeline stage for a warp that owns NTC n8 tiles.  NTC is a
+// template parameter (not a runtime predicate): ptxas if-converts `if (nt < ntc)`
+// into predicated DMMAs, and a predicated-off DMMA still occupies the tensor pipe.
+template <int NTC, int NTW>
+__device__ __forceinline__ void k1_stage_mma(double (&acc)[2][NTW][2], const double* a, const double* b) {
+#pragma unroll
+  for (int ks = 0; ks < K1_BK / 4; ++ks) {
+    const double a0 = a[4 * ks], a1 = a[8 * K1_BK + 4 * ks];
+#pragma unroll
+    for (int nt = 0; nt < NTC; ++nt) {
+      const double bv = b[nt * 8 * K1_BK + 4 * ks];
+      dmma884(acc[0][nt][0], acc[0][nt][1], a0, bv);
+      dmma884(acc[1][nt][0], acc[1][nt][1], a1, bv);
+    }
+  }
+}
+
 // NT = n8 tiles per CTA (split between two n-warps), MW = m-warps (16 rows each).
 template <int NT, int MW>
 __global__ void __launch_bounds__(MW * 64, (MW <= 2 ? 3 : 2)) k1_pairgemm(const K1Params p) {
@@ -90,18 +107,8 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 2 ? 3 : 2)) k1_pairgemm(const 
     }
     const double* a = sA + (kc % K1_STAGES) * A_STAGE + (wm * 16 + fr) * K1_BK + fk;
     const double* b = sB + (kc % K1_STAGES) * B_STAGE + (nt0 * 8 + fr) * K1_BK + fk;
-#pragma unroll
-    for (int ks = 0; ks < K1_BK / 4; ++ks) {
-      double a0 = a[4 * ks], a1 = a[8 * K1_BK + 4 * ks];
-#pragma unroll
-      for (int nt = 0; nt < NTW; ++nt) {
-        if (nt < ntc) {
-          double bv = b[nt * 8 * K1_BK + 4 * ks];
-          dmma884(acc[0][nt][0], acc[0][nt][1], a0, bv);
-          dmma884(acc[1][nt][0], acc[1][nt][1], a1, bv);
-        }
-      }
-    }
+    if (wn == 0) k1_stage_mma<NTW, NTW>(acc, a, b);
+    else if (NT - NTW > 0) k1_stage_mma<(NT - NTW > 0 ? NT - NTW : 1), NTW>(acc, a, b);
   }
   cp_async_wait<0>();
 

@@ -47,6 +47,31 @@ size_t k2_smem_bytes(int n) {
   return d * sizeof(double);
 }
 
+
+// DMMA work of one pipeline stage for a warp that owns NQ m8 tiles (mt = warp +
+// NWARPS*q).  NQ is a template parameter on purpose: a runtime `if (mt < mtiles)`
+// is if-converted by ptxas into PREDICATED DMMAs, and a predicated-off DMMA
+// still occupies the tensor pipe for its full 16 cycles (measured: the loop ran
+// at MAXQ tiles' cost for every warp, 4x the useful work).
+template <int NQ>
+__device__ __forceinline__ void k2_stage_mma(double (&acc)[K2_MAXQ][4][2], const double* sb, int RS, int warp, int fr, int fk) {
+#pragma unroll
+  for (int ks = 0; ks < K2_BKC / 4; ++ks) {
+    const double* col = sb + (4 * ks + fk) * RS + fr;
+    double b[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = col[8 * nt];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double a = col[8 * (warp + K2_NWARPS * q)];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], a, b[nt]);
+    }
+  }
+}
+template <>
+__device__ __forceinline__ void k2_stage_mma<0>(double (&)[K2_MAXQ][4][2], const double*, int, int, int, int) {}
+
 __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws) {
   constexpr int NWARPS = K2_NWARPS, MAXQ = K2_MAXQ, NTHREADS = K2_NWARPS * 32;
   extern __shared__ __align__(16) double smem[];
@@ -69,6 +94,11 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
   double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
   double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
   int fail = 0;  // meaningful on warp 0 only
+  // optional phase profile (cycles, CTA 0 / thread 0): gemm, fill, factor, invert, trsm, writeback, backsolve
+  long long tprev = 0;
+  const bool prof = (p.prof != nullptr) && eq == 0 && tid == 0;
+  if (prof) tprev = clock64();
+#define K2_TICK(slot) do { if (prof) { const long long tn = clock64(); p.prof[slot] += tn - tprev; tprev = tn; } } while (0)
 
   for (int i = tid; i < n; i += NTHREADS) colb[i] = p.colbase[i];
   __syncthreads();
@@ -102,6 +132,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       }
     };
 
+    const int nq = (mtiles > warp) ? (mtiles - warp + NWARPS - 1) / NWARPS : 0;
     double acc[MAXQ][4][2];
 #pragma unroll
     for (int q = 0; q < MAXQ; ++q)
@@ -118,29 +149,22 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       __syncthreads();
       {
         const int nxt = ch + K2_STAGES - 1;
-        if (nxt < nchunks) load_chunk(nxt % K2_STAGES, nxt);
+        if (nxt < nchunks && p.debug_mode != 2) load_chunk(nxt % K2_STAGES, nxt);
         cp_async_commit();
       }
       const double* sb = stage + (size_t)(ch % K2_STAGES) * (K2_BKC * RS);
-#pragma unroll
-      for (int ks = 0; ks < K2_BKC / 4; ++ks) {
-        const double* col = sb + (4 * ks + fk) * RS + fr;
-        double b[4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) b[nt] = col[8 * nt];
-#pragma unroll
-        for (int q = 0; q < MAXQ; ++q) {
-          const int mt = warp + NWARPS * q;
-          if (mt < mtiles) {
-            const double a = col[8 * mt];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], a, b[nt]);
-          }
-        }
+      if (p.debug_mode == 1) continue;
+      switch (nq) {   // warp-uniform: number of m8 tiles this warp owns in this block column
+        case 1: k2_stage_mma<1>(acc, sb, RS, warp, fr, fk); break;
+        case 2: k2_stage_mma<2>(acc, sb, RS, warp, fr, fk); break;
+        case 3: k2_stage_mma<3>(acc, sb, RS, warp, fr, fk); break;
+        case 4: k2_stage_mma<4>(acc, sb, RS, warp, fr, fk); break;
+        default: break;
       }
     }
     cp_async_wait<0>();
     __syncthreads();   // ring is dead from here on; its memory becomes the panel
+    K2_TICK(0);
 
     // ---- A: panel = A_orig - acc, straight from the accumulator fragments -------
 #pragma unroll
@@ -172,48 +196,62 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       }
     }
     __syncthreads();
+    K2_TICK(1);
 
     // ---- C: factor the 32x32 diagonal block and invert it (warp 0) -------------
+    // Lane i holds row i.  Right-looking, software-pipelined: as soon as column c
+    // is scaled, column c+1 is brought up to date and the NEXT pivot's
+    // shuffle + rsqrt chain is started before the remaining (independent) rank-1
+    // updates are issued, so the 32-pivot dependent chain is ~(shfl + rsqrt + mul + fma).
     if (warp == 0) {
       double a[K2_NB];
 #pragma unroll
       for (int c = 0; c < K2_NB; ++c) a[c] = (c <= lane) ? panel[c * RS + lane] : 0.0;
+      double x = __shfl_sync(0xffffffffu, a[0], 0);
+      if (!(x > 0.0) || !isfinite(x)) { if (fail == 0) fail = c0 + 1; x = 1.0; }
+      double rs = rsqrt(x);
 #pragma unroll
       for (int c = 0; c < K2_NB; ++c) {
-        double x = __shfl_sync(0xffffffffu, a[c], c);
-        if (!(x > 0.0) || !isfinite(x)) {
-          if (fail == 0) fail = c0 + c + 1;
-          x = 1.0;
-        }
-        const double rs = rsqrt(x);
         const double l = (lane >= c) ? a[c] * rs : 0.0;   // lane c: x * rsqrt(x) = sqrt(x)
         a[c] = l;
         double* cb = colbuf + (c & 1) * 32;
         cb[lane] = l;
         if (lane == c) rsbuf[c] = rs;
         __syncwarp();
+        if (c + 1 < K2_NB) {
+          a[c + 1] = fma(-l, cb[c + 1], a[c + 1]);
+          x = __shfl_sync(0xffffffffu, a[c + 1], c + 1);
+          if (!(x > 0.0) || !isfinite(x)) { if (fail == 0) fail = c0 + c + 2; x = 1.0; }
+          rs = rsqrt(x);
+        }
 #pragma unroll
-        for (int c2 = c + 1; c2 < K2_NB; ++c2) a[c2] = fma(-l, cb[c2], a[c2]);
+        for (int c2 = c + 2; c2 < K2_NB; ++c2) a[c2] = fma(-l, cb[c2], a[c2]);
       }
 #pragma unroll
       for (int c = 0; c < K2_NB; ++c) panel[c * RS + lane] = a[c];
       __syncwarp();
-      // lane j solves L x = e_j  ->  column j of Linv (reciprocal diagonal from rsbuf)
-      double x[K2_NB];
+      K2_TICK(2);
+      // lane j solves L x = e_j -> column j of Linv.  Right-looking substitution: once
+      // x[k] is known all later partial sums are updated (independent FMAs), so the
+      // dependent chain is one fma + one mul per row.
+      double sacc[K2_NB];
 #pragma unroll
-      for (int i = 0; i < K2_NB; ++i) {
-        double s = (i == lane) ? 1.0 : 0.0;
+      for (int i = 0; i < K2_NB; ++i) sacc[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-        for (int kk = 0; kk < i; ++kk) s = fma(-panel[kk * RS + i], x[kk], s);
-        x[i] = (i >= lane) ? s * rsbuf[i] : 0.0;
+      for (int kk = 0; kk < K2_NB; ++kk) {
+        const double xk = (kk >= lane) ? sacc[kk] * rsbuf[kk] : 0.0;
+        sacc[kk] = xk;
+#pragma unroll
+        for (int i = kk + 1; i < K2_NB; ++i) sacc[i] = fma(-panel[kk * RS + i], xk, sacc[i]);
       }
 #pragma unroll
       for (int i = 0; i < K2_NB; ++i) {
-        linvT[lane * K2_LS + i] = x[i];                                        // linvT[c'=j][c=i] = Linv[i][j]
-        lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = x[i];            // ws[k][c'=i][c=j] = Linv[i][j]
+        linvT[lane * K2_LS + i] = sacc[i];                                        // linvT[c'=j][c=i] = Linv[i][j]
+        lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = sacc[i];            // ws[k][c'=i][c=j] = Linv[i][j]
       }
     }
     __syncthreads();
+    K2_TICK(3);
 
     // ---- D: sub-diagonal rows  X = A * Linv^T  (DMMA, skipping the zero triangle)
     for (int mt = 4 + warp; mt < mtiles; mt += NWARPS) {
@@ -241,6 +279,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       }
     }
     __syncthreads();
+    K2_TICK(4);
 
     // ---- E: write the factorised panel back; keep the forward-solved rhs --------
     for (int c = warp; c < w; c += NWARPS) {
@@ -253,6 +292,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     }
     if (tid < K2_NB) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;
     __syncthreads();
+    K2_TICK(5);
   }
 
   // ---- back-solve  L^T phi = y + z ------------------------------------------------
@@ -291,6 +331,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     bad |= !isfinite(v);
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
+  K2_TICK(6);
   // sticky: the first failure of an equation is kept until the host clears it
   if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
 }

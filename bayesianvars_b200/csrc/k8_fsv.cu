@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
         bc[0] = log((d.priorhomo[d.M + s] + 0.5 * ss[0]) / rng.gamma(d.priorhomo[s] + 0.5 * T));
       }
       __syncthreads();
-      for (int t = tid; t < T; t += SV_THREADS) h[t] = bc[0];
+      for (int t = tid; t < T; t += SV_THREADS) { h[t] = bc[0]; d.wexp[(size_t)s * T + t] = exp(-bc[0]); }
     }  // homoskedastic factors keep h == 0
     return;
   }
@@ -160,7 +160,11 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
     }
     __syncthreads();
     const double mu_n = bc[0], sg_n = bc[1];
-    for (int t = 1 + tid; t <= T; t += SV_THREADS) h[t - 1] = mu_n + sg_n * ((hh[t] - mu_c) / sg_c);
+    for (int t = 1 + tid; t <= T; t += SV_THREADS) {
+      const double hv = mu_n + sg_n * ((hh[t] - mu_c) / sg_c);
+      h[t - 1] = hv;
+      if (s < d.M) d.wexp[(size_t)s * T + t - 1] = exp(-hv);
+    }
     if (tid == 0) {
       d.logvar0[s] = mu_n + sg_n * ((hh[0] - mu_c) / sg_c);
       d.sv_para[3 * s + 0] = mu_n; d.sv_para[3 * s + 1] = bc[2]; d.sv_para[3 * s + 2] = fabs(sg_n);
@@ -238,9 +242,9 @@ __global__ void __launch_bounds__(128) fsv_loadings_kernel(const FsvDev d, uint6
   double A[FSV_RMAX * FSV_RMAX], b[FSV_RMAX];
   for (int p = 0; p < ri; ++p) { b[p] = 0.0; for (int q = 0; q <= p; ++q) A[p * FSV_RMAX + q] = 0.0; }
   const double* y = d.resid + (size_t)i * d.T;
-  const double* h = d.logvar + (size_t)i * d.T;
+  const double* wx = d.wexp + (size_t)i * d.T;
   for (int t = lane; t < d.T; t += 32) {
-    const double w = exp(-h[t]);
+    const double w = wx[t];
     const double* f = d.fac + (size_t)t * d.r;
     for (int p = 0; p < ri; ++p) {
       const double fw = f[idx[p]] * w;
@@ -276,10 +280,18 @@ __global__ void fsv_interweave_kernel(const FsvDev d, uint64_t seed, const uint3
   int lead = j;
   if (largest) {
     double best = -1.0;
-    for (int i = 0; i < d.M; ++i) {
+    int bi = 0x7fffffff;
+    for (int i = lane; i < d.M; i += 32) {
       const double a = fabs(d.facload[(size_t)j * d.M + i]);
-      if (d.restr[(size_t)j * d.M + i] && a > best) { best = a; lead = i; }
+      if (d.restr[(size_t)j * d.M + i] && a > best) { best = a; bi = i; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // max |loading|, ties -> smallest row (as a serial scan would pick)
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi != 0x7fffffff) lead = bi;
   }
   const double Lold = d.facload[(size_t)j * d.M + lead];
   if (!(fabs(Lold) > 0.0)) return;
@@ -349,20 +361,50 @@ __global__ void fsv_interweave_kernel(const FsvDev d, uint64_t seed, const uint3
 }
 
 // Factors: T independent r-variate regressions with M observations each.
-__global__ void fsv_factors_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+// Block = 32 time points x 8 slices of the M rows; slice sums are reduced through
+// shared memory and slice 0 solves the r x r system.
+constexpr int FAC_SLICES = 8;
+__global__ void __launch_bounds__(32 * FAC_SLICES) fsv_factors_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+  extern __shared__ double fsm[];   // [FAC_SLICES][nred][32]
   const uint32_t sweep = *sweep_p;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= d.T) return;
+  const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + tx;
   const int r = d.r;
+  const int nred = r * (r + 1) / 2 + r;
   double A[FSV_RMAX * FSV_RMAX], b[FSV_RMAX];
   for (int p = 0; p < r; ++p) { b[p] = 0.0; for (int q = 0; q <= p; ++q) A[p * FSV_RMAX + q] = 0.0; }
-  for (int i = 0; i < d.M; ++i) {
-    const double w = exp(-d.logvar[(size_t)i * d.T + t]);
-    const double y = d.resid[(size_t)i * d.T + t];
+  if (t < d.T) {
+    for (int i = sl; i < d.M; i += FAC_SLICES) {
+      const double w = d.wexp[(size_t)i * d.T + t];
+      const double y = d.resid[(size_t)i * d.T + t];
+      for (int p = 0; p < r; ++p) {
+        const double lw = d.facload[(size_t)p * d.M + i] * w;
+        b[p] += lw * y;
+        for (int q = 0; q <= p; ++q) A[p * FSV_RMAX + q] += lw * d.facload[(size_t)q * d.M + i];
+      }
+    }
+  }
+  {
+    int k = 0;
     for (int p = 0; p < r; ++p) {
-      const double lw = d.facload[(size_t)p * d.M + i] * w;
-      b[p] += lw * y;
-      for (int q = 0; q <= p; ++q) A[p * FSV_RMAX + q] += lw * d.facload[(size_t)q * d.M + i];
+      for (int q = 0; q <= p; ++q) fsm[((size_t)sl * nred + k++) * 32 + tx] = A[p * FSV_RMAX + q];
+    }
+    for (int p = 0; p < r; ++p) fsm[((size_t)sl * nred + k++) * 32 + tx] = b[p];
+  }
+  __syncthreads();
+  if (sl != 0 || t >= d.T) return;
+  {
+    int k = 0;
+    for (int p = 0; p < r; ++p)
+      for (int q = 0; q <= p; ++q, ++k) {
+        double v = 0.0;
+        for (int z = 0; z < FAC_SLICES; ++z) v += fsm[((size_t)z * nred + k) * 32 + tx];
+        A[p * FSV_RMAX + q] = v;
+      }
+    for (int p = 0; p < r; ++p, ++k) {
+      double v = 0.0;
+      for (int z = 0; z < FAC_SLICES; ++z) v += fsm[((size_t)z * nred + k) * 32 + tx];
+      b[p] = v;
     }
   }
   for (int p = 0; p < r; ++p) A[p * FSV_RMAX + p] += exp(-d.logvar[(size_t)(d.M + p) * d.T + t]);
@@ -387,7 +429,11 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
     }
     fsv_loadings_kernel<<<(d.M + 3) / 4, 128, 0, s>>>(d, seed, sweep);
     if (d.interweaving != 0) fsv_interweave_kernel<<<d.r, 32, 0, s>>>(d, seed, sweep);
-    fsv_factors_kernel<<<(d.T + 63) / 64, 64, 0, s>>>(d, seed, sweep);
+    {
+      const size_t fsmem = (size_t)FAC_SLICES * (d.r * (d.r + 1) / 2 + d.r) * 32 * sizeof(double);
+      if (fsmem > 48 * 1024) cudaFuncSetAttribute(fsv_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      fsv_factors_kernel<<<(d.T + 31) / 32, 32 * FAC_SLICES, fsmem, s>>>(d, seed, sweep);
+    }
   }
   return cudaGetLastError();
 }

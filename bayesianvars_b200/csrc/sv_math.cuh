@@ -99,11 +99,16 @@ __host__ __device__ inline void sv_system_row(int t, int T, double ystar_tm1, in
 // overwritten (1/L_diag, forward-solved rhs, L_offdiag).
 __host__ __device__ inline void sv_awol(int T, double off, double* od, double* c, double* lo, const double* eps,
                                         double* hh) {
+  // The recursion is a (T+1)-step dependent chain; operands of step t+1 are
+  // loaded before step t's chain is consumed so memory latency stays off it.
   double lprev = 0.0, aprev = 0.0;
+  double od_n = od[0], c_n = c[0];
   for (int t = 0; t <= T; ++t) {
-    const double d = od[t] - lprev * lprev;   // L_diag^2
+    const double od_t = od_n, c_t = c_n;
+    if (t < T) { od_n = od[t + 1]; c_n = c[t + 1]; }
+    const double d = od_t - lprev * lprev;    // L_diag^2
     const double ri = bvb_rsqrt(d);
-    const double at = (c[t] - lprev * aprev) * ri;
+    const double at = (c_t - lprev * aprev) * ri;
     od[t] = ri;
     c[t] = at;
     lprev = off * ri;                         // L_offdiag[t]
@@ -111,8 +116,11 @@ __host__ __device__ inline void sv_awol(int T, double off, double* od, double* c
     aprev = at;
   }
   double hnext = 0.0;
+  double num_n = c[T] + eps[T], lo_n = 0.0, ri_n = od[T];
   for (int t = T; t >= 0; --t) {
-    const double ht = (c[t] + eps[t] - ((t < T) ? lo[t] * hnext : 0.0)) * od[t];
+    const double num = num_n, lot = lo_n, rit = ri_n;
+    if (t > 0) { num_n = c[t - 1] + eps[t - 1]; lo_n = lo[t - 1]; ri_n = od[t - 1]; }
+    const double ht = (num - lot * hnext) * rit;
     hh[t] = ht;
     hnext = ht;
   }
