@@ -2,10 +2,12 @@
 // number a caller sees is produced by the sm_100a kernels; there is no CPU path.
 #include "bvb_internal.cuh"
 #include "gig.cuh"
+#include "chol.cuh"
 
 #include <string.h>
 #include <stdlib.h>
 #include <new>
+#include <algorithm>
 
 using namespace bvb;
 
@@ -67,8 +69,25 @@ struct PhiWorkspace {
   }
 };
 
+// Scratch of the cholesky-structure entry points (bvb_phi_draw_cholesky, bvb_sample_u).
+struct CholWorkspace {
+  PairGeom g;          // geometry of the PHI systems (T, Kp)
+  PairGeom gu;         // geometry of the U systems (T, M-1)
+  DevBuf<double> X, Y, PHI0, V, U, dsq, Zn, PHI, A, W, WYzero, omega, d2inv, resid, XPHI, Q, rvec, bvec;
+  DevBuf<double> Au, Wu, WYu, omegau, Vu, Zu, phiu, ViU, zflat;
+  DevBuf<int2> lut, pairs, lutu, pairsu;
+  DevBuf<int> colbase, colbaseu, status;
+  void release() {
+    for (DevBuf<double>* b : {&X, &Y, &PHI0, &V, &U, &dsq, &Zn, &PHI, &A, &W, &WYzero, &omega, &d2inv, &resid, &XPHI, &Q,
+                              &rvec, &bvec, &Au, &Wu, &WYu, &omegau, &Vu, &Zu, &phiu, &ViU, &zflat}) b->release();
+    lut.release(); pairs.release(); lutu.release(); pairsu.release();
+    colbase.release(); colbaseu.release(); status.release();
+  }
+};
+
 struct Scratch {
   PhiWorkspace phi;
+  CholWorkspace chol;
   uint64_t call_counter = 0;
 };
 
@@ -168,6 +187,7 @@ void bvb_destroy(bvb_handle* h) {
   bvb_comm_release(h);
   if (h->scratch) {
     scratch_of(h)->phi.release();
+    scratch_of(h)->chol.release();
     delete scratch_of(h);
   }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -299,19 +319,144 @@ int bvb_phi_draw_cholesky(bvb_handle* h, int T, int Kp, int M, const double* PHI
                           const double* PHI0, const double* Y, const double* X, const double* U,
                           const double* d_sqrt, const double* V_prior, const double* z,
                           double* PHI_out) {
-  (void)T; (void)Kp; (void)M; (void)PHI_in; (void)PHI0; (void)Y; (void)X; (void)U; (void)d_sqrt;
-  (void)V_prior; (void)z; (void)PHI_out;
   if (!h) return BVB_ERR_ARG;
-  bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_cholesky: not built yet");
-  return BVB_ERR_UNSUPPORTED;
+  h->err_code = 0; h->err_step = 1; h->err_sweep = 0; h->err_eq = 0; h->err_msg[0] = 0;
+  if (T <= 0 || Kp <= 0 || M <= 0 || !PHI_in || !PHI0 || !Y || !X || !U || !d_sqrt || !V_prior || !PHI_out) {
+    bvb_set_error(h, BVB_ERR_ARG, "bvb_phi_draw_cholesky: invalid argument");
+    return BVB_ERR_ARG;
+  }
+  if (k2_smem_bytes(Kp) > 227 * 1024) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_cholesky: Kp=%d exceeds the in-SM panel", Kp);
+    return BVB_ERR_UNSUPPORTED;
+  }
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  Scratch* sc = scratch_of(h);
+  CholWorkspace& ws = sc->chol;
+  cudaStream_t s = h->stream;
+  make_pair_geom(ws.g, T, Kp);
+  const size_t tm = (size_t)T * M, km = (size_t)Kp * M;
+  const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
+  BVB_CUDA_TRY(ws.lut.ensure(ws.g.nArows)); BVB_CUDA_TRY(ws.pairs.ensure(ws.g.nArows));
+  BVB_CUDA_TRY(ws.colbase.ensure(ws.g.colbase.size()));
+  BVB_CUDA_TRY(ws.A.ensure((size_t)ws.g.nArows * ws.g.Tp));
+  ws.W.release(); ws.WYzero.release();
+  BVB_CUDA_TRY(ws.W.ensure((size_t)Nalloc * ws.g.Tp, true, s));
+  BVB_CUDA_TRY(ws.WYzero.ensure((size_t)Nalloc * ws.g.Tp, true, s));
+  BVB_CUDA_TRY(ws.omega.ensure((size_t)M * ws.g.ldo));
+  BVB_CUDA_TRY(ws.X.ensure((size_t)T * Kp)); BVB_CUDA_TRY(ws.Y.ensure(tm)); BVB_CUDA_TRY(ws.PHI0.ensure(km));
+  BVB_CUDA_TRY(ws.V.ensure(km)); BVB_CUDA_TRY(ws.U.ensure((size_t)M * M)); BVB_CUDA_TRY(ws.dsq.ensure(tm));
+  BVB_CUDA_TRY(ws.Zn.ensure(km)); BVB_CUDA_TRY(ws.PHI.ensure(km)); BVB_CUDA_TRY(ws.d2inv.ensure(tm));
+  BVB_CUDA_TRY(ws.resid.ensure(tm)); BVB_CUDA_TRY(ws.XPHI.ensure(tm)); BVB_CUDA_TRY(ws.Q.ensure(tm));
+  BVB_CUDA_TRY(ws.rvec.ensure(T)); BVB_CUDA_TRY(ws.bvec.ensure(Kp)); BVB_CUDA_TRY(ws.status.ensure(M));
+  const size_t d = sizeof(double);
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.lut.p, ws.g.lut.data(), sizeof(int2) * ws.g.nArows, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.pairs.p, ws.g.pairs.data(), sizeof(int2) * ws.g.nArows, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.colbase.p, ws.g.colbase.data(), sizeof(int) * ws.g.colbase.size(), cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.X.p, X, d * T * Kp, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.Y.p, Y, d * tm, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.PHI0.p, PHI0, d * km, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.V.p, V_prior, d * km, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.U.p, U, d * M * M, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.dsq.p, d_sqrt, d * tm, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.PHI.p, PHI_in, d * km, cudaMemcpyHostToDevice, s));
+  if (z) {
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.Zn.p, z, d * km, cudaMemcpyHostToDevice, s));
+  } else {
+    fill_normals_kernel<<<(unsigned)((km + 255) / 256), 256, 0, s>>>(ws.Zn.p, km, h->seed, (uint32_t)(0x5800u + sc->call_counter));
+  }
+  sc->call_counter++;
+  BVB_CUDA_TRY(cudaMemsetAsync(ws.status.p, 0, sizeof(int) * M, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  BVB_CUDA_TRY(launch_build_A(ws.A.p, ws.X.p, ws.pairs.p, T, ws.g.Tp, Kp, ws.g.nArows, 0, s));
+  CholPhiCtx c;
+  c.T = T; c.Tp = ws.g.Tp; c.Kp = Kp; c.M = M;
+  c.X = ws.X.p; c.Y = ws.Y.p; c.PHI0 = ws.PHI0.p; c.V = ws.V.p; c.U = ws.U.p; c.dsq = ws.dsq.p; c.Zn = ws.Zn.p; c.PHI = ws.PHI.p;
+  c.A = ws.A.p; c.lut = ws.lut.p; c.colbase = ws.colbase.p; c.nZtiles = ws.g.nZtiles; c.ntiles = ws.g.nZtiles + ws.g.nXtiles;
+  c.ldo = ws.g.ldo; c.W = ws.W.p; c.WYzero = ws.WYzero.p; c.omega = ws.omega.p; c.d2inv = ws.d2inv.p; c.resid = ws.resid.p;
+  c.XPHI = ws.XPHI.p; c.Q = ws.Q.p; c.rvec = ws.rvec.p; c.bvec = ws.bvec.p; c.status = ws.status.p;
+  BVB_CUDA_TRY(launch_chol_phi(c, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[1], s));
+  std::vector<int> st(M);
+  BVB_CUDA_TRY(cudaMemcpyAsync(PHI_out, ws.PHI.p, d * km, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(st.data(), ws.status.p, sizeof(int) * M, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->last_ms[0] = 0; h->last_ms[1] = 0; h->last_ms[2] = 0; h->last_ms[3] = ms;
+  h->last_launches = 8 + 3 * M;
+  for (int j = 0; j < M; ++j)
+    if (st[j] != 0) {
+      h->err_eq = j + 1;
+      bvb_set_error(h, BVB_ERR_NUMERIC, "univariate_regression_update() failed in %ith eqation:\nchol(): decomposition failed", j + 1);
+      return BVB_ERR_NUMERIC;
+    }
+  return BVB_OK;
 }
 
 int bvb_sample_u(bvb_handle* h, int T, int M, const double* resid, const double* V_i_U,
                  const double* d_sqrt, const double* z, double* U_out) {
-  (void)T; (void)M; (void)resid; (void)V_i_U; (void)d_sqrt; (void)z; (void)U_out;
   if (!h) return BVB_ERR_ARG;
-  bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_sample_u: not built yet");
-  return BVB_ERR_UNSUPPORTED;
+  h->err_code = 0; h->err_step = 3; h->err_sweep = 0; h->err_eq = 0; h->err_msg[0] = 0;
+  if (T <= 0 || M <= 0 || !resid || !d_sqrt || !U_out || (M > 1 && !V_i_U)) {
+    bvb_set_error(h, BVB_ERR_ARG, "bvb_sample_u: invalid argument");
+    return BVB_ERR_ARG;
+  }
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  Scratch* sc = scratch_of(h);
+  CholWorkspace& ws = sc->chol;
+  cudaStream_t s = h->stream;
+  const int nu = M > 1 ? M - 1 : 1, ne = M - 1;
+  const size_t tm = (size_t)T * M, nU = (size_t)M * (M - 1) / 2, d = sizeof(double);
+  make_pair_geom(ws.gu, T, nu);
+  if (k2_smem_bytes(nu) > 227 * 1024) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_sample_u: M=%d exceeds the in-SM panel", M);
+    return BVB_ERR_UNSUPPORTED;
+  }
+  const int Nalloc = ((std::max(ne, 1) + 7) / 8) * 8 + K1_NMAX;
+  BVB_CUDA_TRY(ws.lutu.ensure(ws.gu.nArows)); BVB_CUDA_TRY(ws.pairsu.ensure(ws.gu.nArows));
+  BVB_CUDA_TRY(ws.colbaseu.ensure(ws.gu.colbase.size()));
+  BVB_CUDA_TRY(ws.Au.ensure((size_t)ws.gu.nArows * ws.gu.Tp));
+  ws.Wu.release(); ws.WYu.release();
+  BVB_CUDA_TRY(ws.Wu.ensure((size_t)Nalloc * ws.gu.Tp, true, s));
+  BVB_CUDA_TRY(ws.WYu.ensure((size_t)Nalloc * ws.gu.Tp, true, s));
+  BVB_CUDA_TRY(ws.omegau.ensure((size_t)std::max(ne, 1) * ws.gu.ldo));
+  BVB_CUDA_TRY(ws.Vu.ensure((size_t)std::max(ne, 1) * nu)); BVB_CUDA_TRY(ws.Zu.ensure((size_t)std::max(ne, 1) * nu));
+  BVB_CUDA_TRY(ws.phiu.ensure((size_t)std::max(ne, 1) * nu));
+  BVB_CUDA_TRY(ws.ViU.ensure(std::max<size_t>(nU, 1))); BVB_CUDA_TRY(ws.zflat.ensure(std::max<size_t>(nU, 1)));
+  BVB_CUDA_TRY(ws.resid.ensure(tm)); BVB_CUDA_TRY(ws.dsq.ensure(tm)); BVB_CUDA_TRY(ws.U.ensure((size_t)M * M));
+  BVB_CUDA_TRY(ws.status.ensure(M));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.lutu.p, ws.gu.lut.data(), sizeof(int2) * ws.gu.nArows, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.pairsu.p, ws.gu.pairs.data(), sizeof(int2) * ws.gu.nArows, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.colbaseu.p, ws.gu.colbase.data(), sizeof(int) * ws.gu.colbase.size(), cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.resid.p, resid, d * tm, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.dsq.p, d_sqrt, d * tm, cudaMemcpyHostToDevice, s));
+  if (nU > 0) {
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.ViU.p, V_i_U, d * nU, cudaMemcpyHostToDevice, s));
+    if (z) {
+      BVB_CUDA_TRY(cudaMemcpyAsync(ws.zflat.p, z, d * nU, cudaMemcpyHostToDevice, s));
+    } else {
+      fill_normals_kernel<<<(unsigned)((nU + 255) / 256), 256, 0, s>>>(ws.zflat.p, nU, h->seed, (uint32_t)(0x5c00u + sc->call_counter));
+    }
+  }
+  sc->call_counter++;
+  BVB_CUDA_TRY(cudaMemsetAsync(ws.status.p, 0, sizeof(int) * M, s));
+  CholUCtx c;
+  c.T = T; c.Tp = ws.gu.Tp; c.M = M; c.nu = nu; c.resid = ws.resid.p; c.dsq = ws.dsq.p; c.V_i_U = ws.ViU.p; c.zflat = ws.zflat.p;
+  c.U = ws.U.p; c.A = ws.Au.p; c.lut = ws.lutu.p; c.pairs = ws.pairsu.p; c.colbase = ws.colbaseu.p;
+  c.nZtiles = ws.gu.nZtiles; c.ntiles = ws.gu.nZtiles + ws.gu.nXtiles; c.nArows = ws.gu.nArows; c.ldo = ws.gu.ldo;
+  c.W = ws.Wu.p; c.WY = ws.WYu.p; c.omega = ws.omegau.p; c.Vu = ws.Vu.p; c.Zu = ws.Zu.p; c.phi = ws.phiu.p; c.status = ws.status.p;
+  BVB_CUDA_TRY(launch_sample_u(c, s));
+  std::vector<int> st(M, 0);
+  BVB_CUDA_TRY(cudaMemcpyAsync(U_out, ws.U.p, d * M * M, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(st.data(), ws.status.p, sizeof(int) * M, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaStreamSynchronize(s));
+  for (int e = 0; e < ne; ++e)
+    if (st[e] != 0) {
+      h->err_eq = e + 2;
+      bvb_set_error(h, BVB_ERR_NUMERIC, "univariate_regression_update() failed in equation %i: chol(): decomposition failed", e + 2);
+      return BVB_ERR_NUMERIC;
+    }
+  return BVB_OK;
 }
 
 int bvb_gig(bvb_handle* h, int n, const double* lambda, int len_lambda, const double* chi,

@@ -11,6 +11,7 @@
 // The sweep counter lives in device memory so the captured graph is replayed
 // unchanged; all Philox streams are keyed by (purpose, element, sweep).
 #include "gibbs.cuh"
+#include "chol.cuh"
 
 #include <nccl.h>
 #include <string.h>
@@ -107,6 +108,13 @@ __global__ void __launch_bounds__(128) gibbs_resid_kernel(double* __restrict__ r
     if (j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - c0;
     if (j + 1 < M) resid[(size_t)(j + 1) * T + t] = Y[(size_t)(j + 1) * T + t] - c1;
   }
+}
+
+cudaError_t launch_resid(double* resid, const double* Y, const double* X, const double* PHI, int T, int Kp, int M,
+                         cudaStream_t s) {
+  const int tiles = ((T + 7) / 8) * ((M + 7) / 8);
+  gibbs_resid_kernel<<<(tiles + 3) / 4, 128, 0, s>>>(resid, Y, X, PHI, T, Kp, M);
+  return cudaGetLastError();
 }
 
 // Copy the current state into slot `slot` of the device ring if this sweep is stored.

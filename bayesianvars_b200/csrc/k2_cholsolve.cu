@@ -295,6 +295,10 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     K2_TICK(5);
   }
 
+  if (p.mode == 1) {   // factor only: the caller solves later (triangular algorithm)
+    if (tid == 0 && fail) atomicCAS(&p.status[eq], 0, fail);
+    return;
+  }
   // ---- back-solve  L^T phi = y + z ------------------------------------------------
   for (int i = tid; i < n; i += NTHREADS) ysol[i] += p.z[(size_t)eq * p.ldz + i];
   __syncthreads();
@@ -336,6 +340,95 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
   if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
 }
 
+
+// Solve-only companion (triangular algorithm, sample_coefficients.cpp:118-146): the
+// systems were factorised in batch (mode 1); equation `eq`'s right-hand side only
+// becomes known once the previous equations have been drawn.  One CTA:
+//   forward   y_blk = Linv_kk (b_blk - L[blk, 0:c0] y_{0:c0})
+//   backward  phi   = L^-T (y + z)            (same block scheme as above)
+__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_solve_kernel(const K2Params p, const double* __restrict__ linv_ws,
+                                                                     const double* __restrict__ bvec, int eq0) {
+  constexpr int NWARPS = K2_NWARPS, NTHREADS = K2_NWARPS * 32;
+  extern __shared__ __align__(16) double smem[];
+  const int n = p.n;
+  const int nbk = k2_nblocks(n);
+  double* ysol = smem;                       // [nbk*32 + 32]
+  double* part = ysol + nbk * K2_NB + 32;    // [NWARPS][32]
+  double* sblk = part + NWARPS * K2_NB;      // [32]
+  int* colb = reinterpret_cast<int*>(sblk + 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int eq = eq0 + blockIdx.x;
+  const double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
+  const double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
+  const double* __restrict__ b = bvec + (size_t)blockIdx.x * n;
+  for (int i = tid; i < n; i += NTHREADS) colb[i] = p.colbase[i];
+  for (int i = tid; i < nbk * K2_NB + 32; i += NTHREADS) ysol[i] = 0.0;
+  __syncthreads();
+  // ---- forward
+  for (int k = 0; k < nbk; ++k) {
+    const int c0 = k * K2_NB;
+    const int w = min(K2_NB, n - c0);
+    // lanes = the 32 rows of the block, warps split the c0 previous columns
+    double s = 0.0;
+    if (lane < w) {
+      for (int c = warp; c < c0; c += NWARPS) s = fma(om[colb[c] + c0 + lane], ysol[c], s);
+    }
+    part[warp * K2_NB + lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < NWARPS; ++ww) t += part[ww * K2_NB + lane];
+      sblk[lane] = (lane < w) ? b[c0 + lane] - t : 0.0;
+      __syncwarp();
+      // y[c] = sum_{c' <= c} Linv[c][c'] s[c'],  ws[c][c'] = Linv[c][c'] -> lane = c'?  use lane = c:
+      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+      double yv = 0.0;
+#pragma unroll 8
+      for (int cp = 0; cp < K2_NB; ++cp) yv = fma(wsk[lane * K2_NB + cp], sblk[cp], yv);
+      if (lane < w) ysol[c0 + lane] = yv;
+    }
+    __syncthreads();
+  }
+  // ---- backward
+  for (int i = tid; i < n; i += NTHREADS) ysol[i] += p.z[(size_t)blockIdx.x * p.ldz + i];
+  __syncthreads();
+  for (int k = nbk - 1; k >= 0; --k) {
+    const int c0 = k * K2_NB;
+    const int w = min(K2_NB, n - c0);
+    const int kb_end = c0 + w;
+    for (int c = warp; c < K2_NB; c += NWARPS) {
+      double s = 0.0;
+      if (c < w) {
+        const double* colp = om + colb[c0 + c];
+        for (int i = kb_end + lane; i < n; i += 32) s = fma(colp[i], ysol[i], s);
+        s = warp_sum(s);
+      }
+      if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+      double xv0 = 0.0, xv1 = 0.0;
+#pragma unroll
+      for (int cp = 0; cp < K2_NB; cp += 2) {
+        xv0 = fma(wsk[cp * K2_NB + lane], sblk[cp], xv0);
+        xv1 = fma(wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
+      }
+      if (lane < w) ysol[c0 + lane] = xv0 + xv1;
+    }
+    __syncthreads();
+  }
+  bool bad = false;
+  for (int i = tid; i < n; i += NTHREADS) {
+    const double v = ysol[i];
+    p.phi[(size_t)blockIdx.x * p.ldphi + i] = v;
+    bad |= !isfinite(v);
+  }
+  const int anybad = __syncthreads_or(bad ? 1 : 0);
+  if (tid == 0 && anybad) atomicCAS(&p.status[eq], 0, -1);
+}
+
 static double* g_linv_ws = nullptr;
 static size_t g_linv_ws_bytes = 0;
 
@@ -353,6 +446,20 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(k2_cholsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k2_cholsolve<<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws);
+  return cudaGetLastError();
+}
+
+// Solve `count` already-factorised equations eq0..eq0+count-1 (p.omega / status are
+// the batch arrays; p.z, p.phi and bvec are indexed from the first solved equation).
+cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s) {
+  if (!g_linv_ws) return cudaErrorInvalidValue;
+  const int nbk = k2_nblocks(p.n);
+  const size_t smem = ((size_t)(nbk * K2_NB + 32) + K2_NWARPS * K2_NB + 32) * sizeof(double) + (size_t)(p.n + 4) * sizeof(int);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k2_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k2_solve_kernel<<<count, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws, bvec, eq0);
   return cudaGetLastError();
 }
 
