@@ -269,7 +269,50 @@ def specify_prior_sigma(M, type="factor", factor_factors=1, factor_restrict="non
             factor_priorhomoskedastic = np.tile([1.1, 0.055], (M, 1))
         cpp["factor_priorhomoskedastic"] = np.asfortranarray(np.asarray(factor_priorhomoskedastic, float))
     elif type == "cholesky":
-        raise NotImplementedError("cholesky structure: host mirror lands with bvb_gibbs_init's cholesky branch")
+        n_U = (M * M - M) // 2
+        cpp["factor_factors"] = 0
+        het = bool(cholesky_heteroscedastic)
+        cpp["sv_heteroscedastic"] = np.full(M, int(het), np.int32)
+        cpp["sv_priormu"] = np.asarray(cholesky_priormu, float)
+        cpp["sv_priorphi"] = np.asarray(cholesky_priorphi, float)
+        ps2 = np.asarray(cholesky_priorsigma2, float)
+        cpp["sv_priorsigma2"] = np.asfortranarray(np.tile(ps2, (M, 1)) if ps2.ndim == 1 else ps2)
+        cpp["sv_priorh0"] = np.full(M, -1.0) if isinstance(cholesky_priorh0, str) else np.resize(np.asarray(cholesky_priorh0, float) ** 2, M)
+        cpp["cholesky_sv_offset"] = np.resize(np.asarray(expert_sv_offset, float), M)
+        ph = np.array([0.01, 0.01]) if cholesky_priorhomoscedastic is None else np.asarray(cholesky_priorhomoscedastic, float)
+        cpp["cholesky_priorhomoscedastic"] = np.asfortranarray(np.tile(ph, (M, 1)) if ph.ndim == 1 else ph)
+        up = cholesky_U_prior
+        cpp.update(cholesky_U_prior=up, cholesky_V_i=np.zeros(max(n_U, 1)), cholesky_a=0.0, cholesky_b=0.0, cholesky_c=0.0,
+                   cholesky_GL_tol=0.0, cholesky_a_vec=np.zeros(0), cholesky_a_weight=np.zeros(0),
+                   cholesky_norm_consts=np.zeros(0), cholesky_c_vec=np.zeros(0), cholesky_c_rel_a=False,
+                   cholesky_DL_hyper=False, cholesky_DL_plus=False, cholesky_GT_hyper=False, cholesky_GT_vs=1.0,
+                   cholesky_GT_priorkernel="normal", cholesky_SSVS_tau0=np.zeros(max(n_U, 1)),
+                   cholesky_SSVS_tau1=np.zeros(max(n_U, 1)), cholesky_SSVS_s_a=1.0, cholesky_SSVS_s_b=1.0,
+                   cholesky_SSVS_hyper=False, cholesky_SSVS_p=np.zeros(max(n_U, 1)),
+                   cholesky_lambda_3=np.asarray(cholesky_HMP_lambda3, float))
+        if up == "DL":
+            cpp["cholesky_GL_tol"] = cholesky_DL_tol
+            cpp["cholesky_a"] = 1.0 / max(n_U, 1) if cholesky_DL_a == "1/n" else float(cholesky_DL_a)
+        elif up == "R2D2":
+            cpp.update(cholesky_U_prior="GT", cholesky_a=float(cholesky_R2D2_a), cholesky_b=float(cholesky_R2D2_b),
+                       cholesky_c=0.5 * float(cholesky_R2D2_a), cholesky_c_rel_a=True, cholesky_GT_vs=0.5,
+                       cholesky_GT_priorkernel="exponential", cholesky_GL_tol=cholesky_R2D2_tol)
+        elif up == "NG":
+            cpp.update(cholesky_U_prior="GT", cholesky_a=float(cholesky_NG_a), cholesky_b=float(cholesky_NG_b),
+                       cholesky_c=float(cholesky_NG_c), cholesky_GT_vs=1.0, cholesky_GT_priorkernel="normal",
+                       cholesky_GL_tol=cholesky_NG_tol)
+        elif up == "SSVS":
+            if np.size(cholesky_SSVS_p) == 2:
+                cpp["cholesky_SSVS_s_a"], cpp["cholesky_SSVS_s_b"] = (float(x) for x in cholesky_SSVS_p)
+                cpp["cholesky_SSVS_hyper"] = True
+                cholesky_SSVS_p = 0.5
+            cpp["cholesky_SSVS_tau0"] = np.full(max(n_U, 1), float(cholesky_SSVS_c0))
+            cpp["cholesky_SSVS_tau1"] = np.full(max(n_U, 1), float(cholesky_SSVS_c1))
+            cpp["cholesky_SSVS_p"] = np.full(max(n_U, 1), float(cholesky_SSVS_p))
+        elif up == "normal":
+            cpp["cholesky_V_i"] = np.resize(np.asarray(cholesky_normal_sds, float) ** 2, max(n_U, 1))
+        elif up not in ("HS", "HMP"):
+            raise ValueError("Argument 'cholesky_U_prior' must be one of 'DL', 'R2D2', 'NG', 'HS', 'SSVS', 'HMP' or 'normal'.")
     else:
         raise ValueError("type must be 'factor' or 'cholesky'")
     return dict(prior_sigma_cpp=cpp, general_settings=gs)
@@ -321,6 +364,20 @@ def prepare(data, lags, prior_intercept, prior_phi, prior_sigma, startvals=None,
             sv["PHI"] = V_post @ (P0 @ PHI0 + X.T @ Y)
         else:
             sv["PHI"] = np.zeros((0, M))
+    if pcpp["type"] == "cholesky":
+        if "U" not in sv:
+            # R/bvar_wrapper.R:310-319: Sigma_flat from the flat conjugate posterior, U = L_flat
+            P0 = np.eye(Kp) / 1e3 if Kp else np.zeros((0, 0))
+            PHI_flat = np.linalg.inv(P0 + X.T @ X) @ (P0 @ PHI0 + X.T @ Y) if Kp else np.zeros((0, M))
+            E = Y - X @ PHI_flat if Kp else Y
+            S_post = np.eye(M) + E.T @ E + ((PHI_flat - PHI0).T @ P0 @ (PHI_flat - PHI0) if Kp else 0.0)
+            Sigma_flat = S_post / (M + 2 + Tobs - M - 1)
+            Uc = np.linalg.cholesky(Sigma_flat).T            # R's chol(): upper
+            L_inv = Uc / np.sqrt(np.diag(Uc) ** 2)[:, None]   # U / sqrt(D) divides row-wise (column recycling)
+            sv["U"] = np.linalg.solve(L_inv, np.eye(M))       # backsolve(L_inv, diag(M))
+        sv.setdefault("sv_para", np.asfortranarray(np.vstack([np.full(M, -10.0), np.full(M, 0.9), np.full(M, 0.2)])))
+        sv.setdefault("sv_logvar0", np.full(M, -10.0))
+        sv.setdefault("sv_logvar", np.full((Tobs, M), -10.0, order="F"))
     if pcpp["type"] == "factor":
         r = pcpp["factor_factors"]
         S = M + r
@@ -406,6 +463,31 @@ def marshal_prior_sigma(cpp, keep):
         s.sv_priorh0 = keep.d(cpp["sv_priorh0"])
     else:
         s.type = 1
+        s.factor_factors = 0
+        s.cholesky_U_prior = PRIOR_CODES[cpp["cholesky_U_prior"]]
+        s.cholesky_V_i = keep.d(cpp["cholesky_V_i"])
+        for k in ("a", "b", "c", "GL_tol", "GT_vs", "SSVS_s_a", "SSVS_s_b"):
+            setattr(s, "cholesky_" + k, float(cpp["cholesky_" + k]))
+        s.cholesky_grid_len = int(np.size(cpp["cholesky_a_vec"]))
+        if s.cholesky_grid_len:
+            for k in ("a_vec", "a_weight", "norm_consts"):
+                setattr(s, "cholesky_" + k, keep.d(cpp["cholesky_" + k]))
+            cv = cpp["cholesky_c_vec"]
+            s.cholesky_c_vec = keep.d(cv if np.size(cv) == s.cholesky_grid_len else np.zeros(s.cholesky_grid_len))
+        for k in ("c_rel_a", "DL_hyper", "DL_plus", "GT_hyper", "SSVS_hyper"):
+            setattr(s, "cholesky_" + k, int(bool(cpp["cholesky_" + k])))
+        s.cholesky_GT_priorkernel = 1 if cpp["cholesky_GT_priorkernel"] == "exponential" else 0
+        s.cholesky_SSVS_tau0, s.cholesky_SSVS_tau1 = keep.d(cpp["cholesky_SSVS_tau0"]), keep.d(cpp["cholesky_SSVS_tau1"])
+        s.cholesky_SSVS_p = keep.d(cpp["cholesky_SSVS_p"])
+        s.cholesky_lambda_3 = (C.c_double * 2)(*cpp["cholesky_lambda_3"])
+        s.cholesky_priorhomoscedastic = keep.d(cpp["cholesky_priorhomoscedastic"])
+        s.cholesky_sv_offset = keep.d(cpp["cholesky_sv_offset"])
+        s.sv_heteroscedastic = keep.i(cpp["sv_heteroscedastic"])
+        s.sv_priormu = (C.c_double * 2)(*cpp["sv_priormu"])
+        pphi = np.asarray(cpp["sv_priorphi"], float)
+        s.sv_priorphi = (C.c_double * 4)(*np.resize(pphi, 4))
+        s.sv_priorsigma2 = keep.d(cpp["sv_priorsigma2"])
+        s.sv_priorh0 = keep.d(cpp["sv_priorh0"])
     return s
 
 
@@ -422,6 +504,10 @@ class Sampler:
         pcpp, scpp = prior_phi["prior_phi_cpp"], prior_sigma["prior_sigma_cpp"]
         r = scpp.get("factor_factors", 0)
         S = M + r
+        chol = scpp["type"] == "cholesky"
+        n_U = (M * M - M) // 2 if chol else 0
+        up = scpp.get("cholesky_U_prior", "normal")
+        uh_rows = {"DL": 2 + 2 * n_U, "GT": 2 + 2 * n_U, "HS": 2 + 2 * n_U, "SSVS": 2 * n_U, "HMP": 1}.get(up, 0) if chol and n_U else 0
         self.nsave = draws // thin
         self.draws, self.burnin, self.thin = draws, burnin, thin
         n = K * M
@@ -434,15 +520,15 @@ class Sampler:
             logvar=np.zeros((tv, S, ns), order="F"), sv_para=np.zeros((3, S, ns), order="F"),
             phi_hyperparameter=np.zeros((hyper_rows, ns), order="F"),
             facload=np.zeros((M, r, ns), order="F"), fac=np.zeros((r, tv, ns), order="F"),
-            U=np.zeros((0, 0)), u_hyperparameter=np.zeros((0, 0)))
+            U=np.zeros((n_U, ns if chol else 0), order="F"), u_hyperparameter=np.zeros((uh_rows, ns if uh_rows else 0), order="F"))
         d = Draws()
-        for k in ("PHI", "V_prior", "logvar", "sv_para", "phi_hyperparameter", "facload", "fac"):
+        for k in ("PHI", "V_prior", "logvar", "sv_para", "phi_hyperparameter", "facload", "fac", "U", "u_hyperparameter"):
             if self.out[k].size:
                 setattr(d, k, self.out[k].ctypes.data_as(_dp))
         self._draws = d
         sv = prep["startvals"]
         st = StartVals()
-        for k in ("PHI", "sv_para", "sv_logvar", "sv_logvar0", "facload", "fac", "tau2"):
+        for k in ("PHI", "U", "sv_para", "sv_logvar", "sv_logvar0", "facload", "fac", "tau2"):
             if k in sv and np.size(sv[k]):
                 setattr(st, k, self.keep.d(sv[k]))
         pp = marshal_prior_phi(pcpp, self.keep)
@@ -478,9 +564,10 @@ class Sampler:
         r = S - M
         st = dict(PHI=np.zeros((Kp, M), order="F"), V_prior=np.zeros((Kp, M), order="F"),
                   logvar=np.zeros((T, S), order="F"), sv_para=np.zeros((3, S), order="F"),
-                  facload=np.zeros((M, r), order="F"), fac=np.zeros((r, T), order="F"))
+                  facload=np.zeros((M, r), order="F"), fac=np.zeros((r, T), order="F"), U=np.zeros((M, M), order="F"))
         rc = self.lib.bvb_gibbs_state(self.h._h, *(fptr(st[k]) if st[k].size else None
-                                                   for k in ("PHI", "V_prior", "logvar", "sv_para", "facload", "fac")), None)
+                                                   for k in ("PHI", "V_prior", "logvar", "sv_para", "facload", "fac")),
+                                      fptr(st["U"]) if self.out["U"].size else None)
         self.h._check(rc)
         return st
 

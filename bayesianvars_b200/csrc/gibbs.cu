@@ -22,7 +22,7 @@ using namespace bvb;
 
 namespace bvb {
 
-constexpr uint32_t STREAM_PHI_Z = 0x10, STREAM_CLAMP = 0x11, STREAM_PHI_HYPER = 0x20;
+constexpr uint32_t STREAM_PHI_Z = 0x10, STREAM_CLAMP = 0x11, STREAM_U_Z = 0x13, STREAM_PHI_HYPER = 0x20, STREAM_U_HYPER = 0x30;
 
 // ------------------------------------------------------------------ kernels
 __global__ void gibbs_normals_kernel(double* out, int n, int M, int ld, int j0, uint64_t seed, const uint32_t* sweep) {
@@ -137,6 +137,49 @@ __global__ void gibbs_store_kernel(const GibbsStore st, const uint32_t* sweep, i
 
 __global__ void gibbs_advance_kernel(uint32_t* sweep) { *sweep += 1; }
 
+// Cholesky structure: push |U_ij| (i < j) away from zero for DL / GT priors
+// (bvar_cpp.cpp:667-685) and gather u = U(trimatu_ind) (:688) - column-major upper
+// triangle, element (i, j) at j(j-1)/2 + i.
+__global__ void chol_clamp_u_kernel(double* U, double* uvec, int M, int do_clamp, double tol, uint64_t seed,
+                                    const uint32_t* sweep) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * M) return;
+  const int j = (int)(idx / M), i = (int)(idx % M);
+  if (i >= j) return;
+  double v = U[idx];
+  if (do_clamp) {
+    if (v == 0.0) {
+      RngStream rng(seed, STREAM_CLAMP + 1, (uint32_t)idx, *sweep);
+      v = (rng.uniform() < 0.5) ? tol : -tol;
+    } else if (v < tol && v > 0.0) v = tol;
+    else if (v > -tol && v < 0.0) v = -tol;
+    U[idx] = v;
+  }
+  uvec[(size_t)j * (j - 1) / 2 + i] = v;
+}
+
+// str_resid = resid U (bvar_cpp.cpp:725)
+__global__ void chol_strres_kernel(double* out, const double* resid, const double* U, int T, int M) {
+  const int i = blockIdx.x;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    double q = 0.0;
+    for (int m = 0; m <= i; ++m) q = fma(resid[(size_t)m * T + t], U[(size_t)i * M + m], q);
+    out[(size_t)i * T + t] = q;
+  }
+}
+
+__global__ void chol_dsq_kernel(double* dsq, const double* logvar, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dsq[i] = exp(0.5 * logvar[i]);
+}
+
+__global__ void gibbs_flat_normals_kernel(double* out, size_t n, uint64_t seed, uint32_t stream, const uint32_t* sweep) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RngStream rng(seed, stream, (uint32_t)i, *sweep);
+  out[i] = rng.normal();
+}
+
 }  // namespace bvb
 
 // ------------------------------------------------------------------ host side
@@ -215,7 +258,17 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   const bool timing = G.timing_pass;
   auto mark = [&](int i) { if (timing) cudaEventRecord(ev[i], s); };
   mark(0);
-  if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
+  if (K > 0 && G.sigma_type == BVB_SIGMA_CHOLESKY) {
+    // ---- 1) PHI | .  (cholesky structure: corrected triangular algorithm, bvar_cpp.cpp:510)
+    const size_t nz = (size_t)Kp * M;
+    gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, M, Kp, 0, h->seed, sw);
+    mark(1);
+    GB_TRY(launch_chol_phi(G.cphi, s));
+    mark(2); mark(3); mark(4);
+    const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
+    gibbs_clamp_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
+                                                                   G.PHI_tol, h->seed, sw, G.status.p);
+  } else if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
     // ---- 1) PHI | .  (factor structure: equations independent)
     GB_TRY(launch_prep_factor(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p, G.fac.p, T, G.geom.Tp, M, G.r, s));
     mark(1);
@@ -264,7 +317,22 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   }
   mark(6);
   // ---- 3) Sigma_t
-  GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));
+  if (G.sigma_type == BVB_SIGMA_CHOLESKY) {
+    const int M2 = M * M;
+    if (G.nU > 0) {
+      gibbs_flat_normals_kernel<<<(G.nU + 255) / 256, 256, 0, s>>>(G.zflat.p, (size_t)G.nU, h->seed, STREAM_U_Z, sw);
+      GB_TRY(launch_sample_u(G.cu, s));                                                       // bvar_cpp.cpp:659
+      const int clampU = (G.hU.d.prior == BVB_PRIOR_DL || G.hU.d.prior == BVB_PRIOR_GT) ? 1 : 0;
+      chol_clamp_u_kernel<<<(M2 + 255) / 256, 256, 0, s>>>(G.U.p, G.hU.d.coef, M, clampU, G.L_tol, h->seed, sw);   // :667-688
+      GB_TRY(launch_hyper_update(G.hU.d, h->seed, sw, G.burnin, s));                          // :689-721
+    }
+    chol_strres_kernel<<<M, 256, 0, s>>>(G.strres.p, G.resid.p, G.U.p, T, M);                 // :725
+    GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));                                         // :727-746
+    const size_t tm = (size_t)T * M;
+    chol_dsq_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(G.dsq.p, G.logvar.p, tm);
+  } else {
+    GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));
+  }
   mark(7);
   // ---- store + advance
   gibbs_store_kernel<<<64, 256, 0, s>>>(G.store, sw, G.nstored.p);
@@ -302,12 +370,13 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   const int Kp = K + (intercept ? 1 : 0);
   if (Kp > 0 && (!X || !PHI0 || !sv->PHI)) return fail_arg(h, "X / PHI0 / startvals.PHI missing");
   if (K > 0 && !i_vec) return fail_arg(h, "i_vec missing");
-  if (ps->type != BVB_SIGMA_FACTOR) {
-    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gibbs_init: cholesky structure runs through bvb_gibbs_init_cholesky (not built yet)");
+  const bool chol = ps->type == BVB_SIGMA_CHOLESKY;
+  if (chol && h->world > 1) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "cholesky structure does not shard (Gauss-Seidel over equations): run one chain per GPU");
     return BVB_ERR_UNSUPPORTED;
   }
   if (huge) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gibbs_init: expert_huge path not built yet"); return BVB_ERR_UNSUPPORTED; }
-  const int r = ps->factor_factors;
+  const int r = chol ? 0 : ps->factor_factors;
   if (r < 0 || r > FSV_RMAX) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "factor_factors=%d outside [0,%d]", r, FSV_RMAX); return BVB_ERR_UNSUPPORTED; }
   if (Kp > 0 && k2_smem_bytes(Kp) > 227 * 1024) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "Kp=%d exceeds the in-SM panel of the standard path; use expert_huge", Kp);
@@ -324,6 +393,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   G.M = M; G.T = T; G.K = K; G.Kp = Kp; G.intercept = intercept ? 1 : 0; G.r = r; G.S = M + r;
   G.draws = draws; G.burnin = burnin; G.thin = thin; G.tvp_all = tvp_keep_all ? 1 : 0;
   G.nsave = draws / thin; G.PHI_tol = PHI_tol; G.L_tol = L_tol; G.out = *out;
+  G.sigma_type = ps->type;
   G.rank = h->rank; G.world = h->world > 0 ? h->world : 1; G.comm = h->comm;
   G.nloc_max = (M + G.world - 1) / G.world;
   G.j0 = std::min(M, G.rank * G.nloc_max);
@@ -475,7 +545,9 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     if (ps->sv_priorsigma2) { ps2[i] = ps->sv_priorsigma2[i]; ps2[S + i] = ps->sv_priorsigma2[S + i]; }
     if (ps->sv_priorh0) ph0[i] = ps->sv_priorh0[i];
   }
-  if (ps->factor_priorhomoskedastic) for (int i = 0; i < 2 * M; ++i) phomo[i] = ps->factor_priorhomoskedastic[i];
+  if (!chol && ps->factor_priorhomoskedastic) for (int i = 0; i < 2 * M; ++i) phomo[i] = ps->factor_priorhomoskedastic[i];
+  if (chol && ps->cholesky_priorhomoscedastic) for (int i = 0; i < 2 * M; ++i) phomo[i] = ps->cholesky_priorhomoscedastic[i];
+  if (chol && ps->cholesky_sv_offset) for (int i = 0; i < M; ++i) offset[i] = ps->cholesky_sv_offset[i];
   if ((rc = upload(h, G.hetero, hetero.data(), S))) return rc;
   if ((rc = upload(h, G.offset, offset.data(), M))) return rc;
   if ((rc = upload(h, G.priorsigma2, ps2.data(), (size_t)2 * S))) return rc;
@@ -502,10 +574,95 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   F.priorh0 = G.priorh0.p; F.priorhomo = G.priorhomo.p;
   F.shrink_a = G.shrink_a.p; F.shrink_c = G.shrink_c.p; F.shrink_d = G.shrink_d.p;
   F.priormu[0] = ps->sv_priormu[0]; F.priormu[1] = ps->sv_priormu[1];
-  for (int i = 0; i < 4; ++i) F.priorphi[i] = ps->sv_priorphi[i];
+  for (int i = 0; i < 4; ++i) F.priorphi[i] = ps->sv_priorphi[chol ? i % 2 : i];
   F.facloadtol = ps->factor_facloadtol; F.ngprior = ps->factor_ngprior; F.columnwise = ps->factor_columnwise;
   F.interweaving = ps->factor_interweaving > 4 ? 4 : ps->factor_interweaving;
   if (Kp == 0) GB_TRY(cudaMemcpyAsync(G.resid.p, G.Y.p, sizeof(double) * (size_t)T * M, cudaMemcpyDeviceToDevice, s));
+
+  // ---- cholesky structure: U, its prior block, and the contexts of the two sequential draws
+  int priorU = BVB_PRIOR_NORMAL;
+  const int nU = M * (M - 1) / 2;
+  G.nU = chol ? nU : 0;
+  if (chol) {
+    if (!sv->U) return fail_arg(h, "startvals.U missing");
+    const size_t tm = (size_t)T * M;
+    if ((rc = upload(h, G.U, sv->U, (size_t)M * M))) return rc;
+    GB_TRY(G.dsq.ensure(tm)); GB_TRY(G.d2inv.ensure(tm)); GB_TRY(G.XPHI.ensure(tm)); GB_TRY(G.Q.ensure(tm));
+    GB_TRY(G.strres.ensure(tm)); GB_TRY(G.rvec.ensure(T)); GB_TRY(G.bvec.ensure(std::max(Kp, 1)));
+    GB_TRY(G.zflat.ensure(std::max(nU, 1))); GB_TRY(G.ustatus.ensure(M, true));
+    chol_dsq_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(G.dsq.p, G.logvar.p, tm);   // bvar_cpp.cpp:404
+    F.resid = G.strres.p;   // the SV kernels see the orthogonalised residuals
+    if (Kp > 0) {
+      const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
+      GB_TRY(G.WYzero.ensure((size_t)Nalloc * G.geom.Tp, true));
+      CholPhiCtx& c = G.cphi;
+      c.T = T; c.Tp = G.geom.Tp; c.Kp = Kp; c.M = M; c.X = G.X.p; c.Y = G.Y.p; c.PHI0 = G.PHI0.p; c.V = G.Vprior.p;
+      c.U = G.U.p; c.dsq = G.dsq.p; c.Zn = G.Zn.p; c.PHI = G.PHI.p; c.A = G.A.p; c.lut = G.lut.p; c.colbase = G.colbase.p;
+      c.nZtiles = G.geom.nZtiles; c.ntiles = G.geom.nZtiles + G.geom.nXtiles; c.ldo = G.geom.ldo; c.W = G.W.p;
+      c.WYzero = G.WYzero.p; c.omega = G.omega.p; c.d2inv = G.d2inv.p; c.resid = G.resid.p; c.XPHI = G.XPHI.p; c.Q = G.Q.p;
+      c.rvec = G.rvec.p; c.bvec = G.bvec.p; c.status = G.eqstatus.p;
+    }
+    // prior on the free elements of U (bvar_cpp.cpp:166-245)
+    priorU = ps->cholesky_U_prior;
+    std::vector<double> l1((size_t)std::max(nU, 1), 0.0), l2((size_t)std::max(nU, 1), 1.0), Vi((size_t)std::max(nU, 1), 1.0), Vprep;
+    std::vector<int> grpU((size_t)std::max(nU, 1), 0);
+    std::vector<double> gp(HYP_GP, 0.0);
+    gp[GP_A] = ps->cholesky_a; gp[GP_B] = ps->cholesky_b; gp[GP_C] = ps->cholesky_c; gp[GP_XI] = 0.5;
+    gp[GP_ZETA] = 10.0; gp[GP_VARPI] = 1.0; gp[GP_N] = nU;
+    switch (priorU) {
+      case BVB_PRIOR_NORMAL:
+        if (nU > 0 && !ps->cholesky_V_i) return fail_arg(h, "cholesky_V_i missing");
+        for (int i = 0; i < nU; ++i) Vi[i] = ps->cholesky_V_i[i];
+        break;
+      case BVB_PRIOR_DL:   // V_i_U = psi_U % lambda_U (:214)
+        for (int i = 0; i < nU; ++i) { l1[i] = 1.0 / nU; l2[i] = 1.0; Vi[i] = l1[i]; }
+        break;
+      case BVB_PRIOR_GT:
+        for (int i = 0; i < nU; ++i) { l1[i] = 1.0 / nU; l2[i] = 1.0; Vi[i] = ps->cholesky_GT_priorkernel ? 0.5 * l1[i] : l1[i]; }
+        break;
+      case BVB_PRIOR_HS:
+        for (int i = 0; i < nU; ++i) { l1[i] = 1.0 / nU; l2[i] = 1.0; Vi[i] = l1[i] * 10.0; }
+        break;
+      case BVB_PRIOR_SSVS:
+        if (nU > 0 && (!ps->cholesky_SSVS_tau0 || !ps->cholesky_SSVS_tau1 || !ps->cholesky_SSVS_p)) return fail_arg(h, "cholesky SSVS keys missing");
+        for (int i = 0; i < nU; ++i) { l1[i] = 0.0; l2[i] = ps->cholesky_SSVS_p[i]; Vi[i] = ps->cholesky_SSVS_tau0[i] * ps->cholesky_SSVS_tau0[i]; }
+        break;
+      case BVB_PRIOR_HMP:  // lambda_3 = 0.001, V_i_U = lambda_3 (:239-245); sample_V_i_U_HMP (:370-377)
+        Vprep.assign((size_t)std::max(nU, 1), 1.0);
+        gp[GP_A] = ps->cholesky_lambda_3[0]; gp[GP_B] = ps->cholesky_lambda_3[1]; gp[GP_AUX] = 0.001;
+        for (int i = 0; i < nU; ++i) Vi[i] = 0.001;
+        break;
+      default: return fail_arg(h, "unknown cholesky_U_prior");
+    }
+    const int hyperU = priorU == BVB_PRIOR_DL ? ps->cholesky_DL_hyper : (priorU == BVB_PRIOR_GT ? ps->cholesky_GT_hyper
+                       : (priorU == BVB_PRIOR_SSVS ? ps->cholesky_SSVS_hyper : 0));
+    rc = setup_hyper(h, G.hU, priorU, nU, grpU, 1, gp, ps->cholesky_V_i, ps->cholesky_GL_tol, ps->cholesky_a_vec,
+                     ps->cholesky_a_weight, ps->cholesky_norm_consts, ps->cholesky_c_vec,
+                     (priorU == BVB_PRIOR_DL || priorU == BVB_PRIOR_GT) ? ps->cholesky_grid_len : 0, hyperU,
+                     ps->cholesky_DL_plus, ps->cholesky_c_rel_a, ps->cholesky_GT_priorkernel, ps->cholesky_GT_vs,
+                     ps->cholesky_SSVS_tau0, ps->cholesky_SSVS_tau1, ps->cholesky_SSVS_s_a, ps->cholesky_SSVS_s_b,
+                     ps->cholesky_SSVS_p, Vprep, l1, l2, Vi, STREAM_U_HYPER);
+    if (rc) return rc;
+    G.hU.d.always_active = 1;
+    if (nU > 0) {
+      const int nu = M - 1;
+      if (k2_smem_bytes(nu) > 227 * 1024) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "M=%d exceeds the in-SM panel of sample_U", M); return BVB_ERR_UNSUPPORTED; }
+      make_pair_geom(G.geomU, T, nu);
+      if ((rc = upload(h, G.lutu, G.geomU.lut.data(), G.geomU.nArows))) return rc;
+      if ((rc = upload(h, G.pairsu, G.geomU.pairs.data(), G.geomU.nArows))) return rc;
+      if ((rc = upload(h, G.colbaseu, G.geomU.colbase.data(), G.geomU.colbase.size()))) return rc;
+      const int Nal = ((nu + 7) / 8) * 8 + K1_NMAX;
+      GB_TRY(G.Au.ensure((size_t)G.geomU.nArows * G.geomU.Tp));
+      GB_TRY(G.Wu.ensure((size_t)Nal * G.geomU.Tp, true)); GB_TRY(G.WYu.ensure((size_t)Nal * G.geomU.Tp, true));
+      GB_TRY(G.omegau.ensure((size_t)nu * G.geomU.ldo)); GB_TRY(G.Vu.ensure((size_t)nu * nu));
+      GB_TRY(G.Zu.ensure((size_t)nu * nu)); GB_TRY(G.phiu.ensure((size_t)nu * nu));
+      CholUCtx& c = G.cu;
+      c.T = T; c.Tp = G.geomU.Tp; c.M = M; c.nu = nu; c.resid = G.resid.p; c.dsq = G.dsq.p; c.V_i_U = G.hU.d.V_i;
+      c.zflat = G.zflat.p; c.U = G.U.p; c.A = G.Au.p; c.lut = G.lutu.p; c.pairs = G.pairsu.p; c.colbase = G.colbaseu.p;
+      c.nZtiles = G.geomU.nZtiles; c.ntiles = G.geomU.nZtiles + G.geomU.nXtiles; c.nArows = G.geomU.nArows; c.ldo = G.geomU.ldo;
+      c.W = G.Wu.p; c.WY = G.WYu.p; c.omega = G.omegau.p; c.Vu = G.Vu.p; c.Zu = G.Zu.p; c.phi = G.phiu.p; c.status = G.ustatus.p;
+    }
+  }
 
   // ---- stored-draw ring: one slot = everything bvar_cpp.cpp:751-836 copies per stored sweep
   GibbsStore& st = G.store;
@@ -532,6 +689,26 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   } else if (prior == BVB_PRIOR_HMP) {
     add_seg(st, G.hphi.d.gpar, 1, 2, HYP_GP, GP_AUX, off);
     G.hyper_rows = 2;
+  }
+  G.off_U = off; G.off_uhyper = off; G.uhyper_rows = 0;
+  if (chol && nU > 0) {
+    add_seg(st, G.hU.d.coef, nU, 1, nU, 0, off);   // u = U(trimatu_ind), refreshed by the clamp kernel every sweep
+    G.off_uhyper = off;
+    if (priorU == BVB_PRIOR_DL || priorU == BVB_PRIOR_GT || priorU == BVB_PRIOR_HS) {
+      const int c0 = (priorU == BVB_PRIOR_HS) ? GP_ZETA : GP_A, c1 = (priorU == BVB_PRIOR_HS) ? GP_VARPI : GP_XI;
+      add_seg(st, G.hU.d.gpar, 1, 1, HYP_GP, c0, off);
+      add_seg(st, G.hU.d.gpar, 1, 1, HYP_GP, c1, off);
+      add_seg(st, G.hU.d.loc1, nU, 1, nU, 0, off);
+      add_seg(st, G.hU.d.loc2, nU, 1, nU, 0, off);
+      G.uhyper_rows = 2 + 2 * nU;
+    } else if (priorU == BVB_PRIOR_SSVS) {
+      add_seg(st, G.hU.d.loc1, nU, 1, nU, 0, off);
+      add_seg(st, G.hU.d.loc2, nU, 1, nU, 0, off);
+      G.uhyper_rows = 2 * nU;
+    } else if (priorU == BVB_PRIOR_HMP) {
+      add_seg(st, G.hU.d.gpar, 1, 1, HYP_GP, GP_AUX, off);
+      G.uhyper_rows = 1;
+    }
   }
   G.off_facload = off;  if (r > 0) add_seg(st, G.facload.p, M, r, M, 0, off);
   const int fac_cols = G.tvp_all ? T : 1;
@@ -569,6 +746,9 @@ static void scatter_to_caller(Gibbs& G, const double* chunk, int first, int coun
     if (G.out.sv_para) memcpy(G.out.sv_para + d * 3 * S, src + G.off_svpara, sizeof(double) * 3 * S);
     if (G.out.phi_hyperparameter && G.hyper_rows > 0)
       memcpy(G.out.phi_hyperparameter + d * G.hyper_rows, src + G.off_hyper, sizeof(double) * G.hyper_rows);
+    if (G.out.U && G.nU > 0) memcpy(G.out.U + d * G.nU, src + G.off_U, sizeof(double) * G.nU);
+    if (G.out.u_hyperparameter && G.uhyper_rows > 0)
+      memcpy(G.out.u_hyperparameter + d * G.uhyper_rows, src + G.off_uhyper, sizeof(double) * G.uhyper_rows);
     if (G.out.facload && r > 0) memcpy(G.out.facload + d * M * r, src + G.off_facload, sizeof(double) * M * r);
     if (G.out.fac && r > 0) memcpy(G.out.fac + d * r * fac_cols, src + G.off_fac, sizeof(double) * r * fac_cols);
   }
@@ -696,6 +876,16 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
       return BVB_ERR_NUMERIC;
     }
   }
+  if (G.sigma_type == BVB_SIGMA_CHOLESKY && G.nU > 0) {
+    std::vector<int> us(G.M);
+    GB_TRY(cudaMemcpy(us.data(), G.ustatus.p, sizeof(int) * G.M, cudaMemcpyDeviceToHost));
+    for (int e = 0; e + 1 < G.M; ++e)
+      if (us[e] != 0) {
+        h->err_step = 3; h->err_eq = e + 2; h->err_sweep = G.rep;
+        bvb_set_error(h, BVB_ERR_NUMERIC, "sample_U() failed in run <= %i: univariate_regression_update() failed in equation %i: chol(): decomposition failed", G.rep, e + 2);
+        return BVB_ERR_NUMERIC;
+      }
+  }
   if (hst[0] != 0) {
     h->err_step = 1; h->err_sweep = G.rep;
     bvb_set_error(h, BVB_ERR_NUMERIC, "non-finite PHI in rep <= %i.", G.rep);
@@ -732,7 +922,7 @@ int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,
   if (sv_para) GB_TRY(cudaMemcpy(sv_para, G.sv_para.p, d * 3 * G.S, cudaMemcpyDeviceToHost));
   if (facload && G.r) GB_TRY(cudaMemcpy(facload, G.facload.p, d * G.M * G.r, cudaMemcpyDeviceToHost));
   if (fac && G.r) GB_TRY(cudaMemcpy(fac, G.fac.p, d * G.r * G.T, cudaMemcpyDeviceToHost));
-  (void)U;
+  if (U && G.U.p) GB_TRY(cudaMemcpy(U, G.U.p, d * G.M * G.M, cudaMemcpyDeviceToHost));
   return BVB_OK;
 }
 

@@ -3,6 +3,7 @@
 #include "bvb_internal.cuh"
 #include "hyper.cuh"
 #include "fsv.cuh"
+#include "chol.cuh"
 
 namespace bvb {
 
@@ -74,6 +75,19 @@ struct Gibbs {
   GBuf<double> offset, priorsigma2, priorh0, priorhomo, shrink_a, shrink_c, shrink_d;
   GBuf<unsigned char> mixind;
   GBuf<int> hetero, restr;
+  // cholesky structure
+  int sigma_type = BVB_SIGMA_FACTOR;
+  int nU = 0;
+  PairGeom geomU;
+  GibbsHyper hU;
+  GBuf<double> U, dsq, d2inv, XPHI, Q, rvec, bvec, WYzero, strres, zflat, uvec;
+  GBuf<double> Au, Wu, WYu, omegau, Vu, Zu, phiu;
+  GBuf<int2> lutu, pairsu;
+  GBuf<int> colbaseu, ustatus;
+  CholPhiCtx cphi;
+  CholUCtx cu;
+  size_t off_U = 0, off_uhyper = 0;
+  int uhyper_rows = 0;
   // stored draws
   GibbsStore store;
   GBuf<double> ring;

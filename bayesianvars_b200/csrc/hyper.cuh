@@ -40,6 +40,7 @@ struct HyperDev {
   // HMP: groups are 0 = own-lag, 1 = cross-lag; gpar[g][GP_A..GP_B] = shape, rate
   double* V_prep = nullptr;    // [n]
   uint32_t stream_base = 0;    // Philox stream ids stream_base .. stream_base+3
+  int always_active = 0;       // U block: SSVS / HMP updates run from the first sweep (bvar_cpp.cpp:708-716)
 };
 
 // One full hyper-parameter update (up to four kernels).  The sweep index is read

@@ -13,6 +13,7 @@ namespace bvb {
 
 __device__ __forceinline__ int hyper_active(const HyperDev& hd, uint32_t rep, int burnin) {
   // bvar_cpp.cpp:585 (SSVS: rep > 0.1*burnin || SSVS_hyper), :602 (HMP: rep > 0.1*burnin)
+  if (hd.always_active) return 1;
   const bool late = (double)rep > 0.1 * (double)burnin;
   if (hd.prior == BVB_PRIOR_SSVS) return (late || hd.hyper) ? 1 : 0;
   if (hd.prior == BVB_PRIOR_HMP) return late ? 1 : 0;
