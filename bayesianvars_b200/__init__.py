@@ -7,5 +7,6 @@ tests and bench drive through the same C ABI the Rcpp shim binds).
 """
 from ._lib import BvbError, load  # noqa: F401
 from .api import Handle  # noqa: F401
+from . import bvar  # noqa: F401  (registers the Gibbs entry points with the ctypes loader)
 
 __all__ = ["Handle", "BvbError", "load"]

@@ -30,6 +30,7 @@ SIGNATURES = {
     "bvb_phi_draw_cholesky": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "bvb_sample_u": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
     "bvb_gig": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_uint64, _dp]),
+    "bvb_irf": (C.c_int, [_vp] + [C.c_int] * 9 + [_dp] * 7),
     "bvb_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "bvb_last_timing": (C.c_int, [_vp, _dp]),
 }
@@ -51,7 +52,7 @@ def load():
     if not LIB_PATH.exists():
         raise ImportError(f"{LIB_PATH} not built - run `python -m bayesianvars_b200.build` "
                           "(there is no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -116,3 +116,24 @@ class Handle:
                                C.c_uint64(stream), fptr(out))
         self._check(rc)
         return out
+
+    # -- a14: irf_cpp (src/irf.cpp:468-524) ---------------------------------------
+    def irf_cpp(self, coefficients, factor_loadings, U_vecs, logvar_t, shocks, ahead, rotation=None):
+        """Returns the (variables, shocks, 1+ahead, draws) array R/irf.R:275-276 builds."""
+        coefficients = np.asfortranarray(coefficients, dtype=np.float64)
+        Kp, M, R = coefficients.shape
+        nf = 0 if factor_loadings is None or np.size(factor_loadings) == 0 else np.shape(factor_loadings)[1]
+        has_U = 0 if U_vecs is None or np.size(U_vecs) == 0 or nf > 0 else 1
+        fl = np.asfortranarray(factor_loadings, dtype=np.float64) if nf else None
+        uv = np.asfortranarray(U_vecs, dtype=np.float64) if has_U else None
+        lv = np.asfortranarray(np.asarray(logvar_t, dtype=np.float64).reshape(-1, R)) if logvar_t is not None and np.size(logvar_t) else None
+        shocks = np.asfortranarray(shocks, dtype=np.float64)
+        dim, n_shocks = shocks.shape
+        rot = np.asfortranarray(rotation, dtype=np.float64) if rotation is not None else None
+        out = np.empty((M, n_shocks, ahead + 1, R), order="F")
+        rc = self._lib.bvb_irf(self._h, Kp, M, R, nf, has_U, 0 if lv is None else lv.shape[0], dim, n_shocks, int(ahead),
+                               fptr(coefficients.reshape(-1, order="F")), fptr(fl.reshape(-1, order="F")) if nf else None,
+                               fptr(uv) if has_U else None, fptr(lv) if lv is not None else None, fptr(shocks),
+                               fptr(rot.reshape(-1, order="F")) if rot is not None else None, fptr(out.reshape(-1, order="F")))
+        self._check(rc)
+        return out

@@ -59,7 +59,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(f"[{src.name}]\n{out}\n")
     if failed:
         raise RuntimeError("libbvb.so build failed")
-    link = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart", "-lnccl"]
+    link = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl"]
     subprocess.run(link, check=True)
     return LIB
 

@@ -14,11 +14,41 @@
 #include "chol.cuh"
 
 #include <nccl.h>
+#include <dlfcn.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
 
 using namespace bvb;
+
+// NCCL is bound at run time (dlopen), not at link time: a process that also
+// imports PyTorch already has PyTorch's bundled libnccl.so.2 loaded, and a second,
+// older system copy pulled in through DT_NEEDED would shadow its symbols.
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.lib) return api;
+  api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!api.lib) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+  return api;
+}
+}  // namespace
 
 namespace bvb {
 
@@ -291,9 +321,9 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     if (G.world > 1) {
       // ranks own contiguous blocks of nloc_max columns (PHI is padded to world*nloc_max
       // columns), so the gather is in place: sendbuff == recvbuff + rank*count
-      ncclResult_t nr = ncclAllGather(G.PHI.p + (size_t)G.rank * G.nloc_max * Kp, G.PHI.p, (size_t)G.nloc_max * Kp,
-                                      ncclDouble, (ncclComm_t)G.comm, s);
-      if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather: %s", ncclGetErrorString(nr)); return BVB_ERR_COMM; }
+      ncclResult_t nr = nccl_api().AllGather(G.PHI.p + (size_t)G.rank * G.nloc_max * Kp, G.PHI.p, (size_t)G.nloc_max * Kp,
+                                             ncclDouble, (ncclComm_t)G.comm, s);
+      if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather: %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
     }
     mark(4);
     const size_t nphi = (size_t)Kp * M;
@@ -928,13 +958,13 @@ int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,
 
 }  // extern "C"
 void bvb_comm_release(bvb_handle* h) {
-  if (h && h->comm) { ncclCommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
+  if (h && h->comm) { nccl_api().CommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
 }
 extern "C" {
 int bvb_comm_unique_id(char* unique_id_128) {
   if (!unique_id_128) return BVB_ERR_ARG;
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return BVB_ERR_COMM;
+  if (!nccl_api().ok || nccl_api().GetUniqueId(&id) != ncclSuccess) return BVB_ERR_COMM;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   memcpy(unique_id_128, &id, 128);
   return BVB_OK;
@@ -948,9 +978,10 @@ int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128)
   GB_TRY(cudaSetDevice(h->device));
   ncclUniqueId id;
   memcpy(&id, unique_id_128, 128);
+  if (!nccl_api().ok) { bvb_set_error(h, BVB_ERR_COMM, "libnccl.so.2 could not be loaded"); return BVB_ERR_COMM; }
   ncclComm_t comm;
-  ncclResult_t nr = ncclCommInitRank(&comm, world, id, rank);
-  if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclCommInitRank: %s", ncclGetErrorString(nr)); return BVB_ERR_COMM; }
+  ncclResult_t nr = nccl_api().CommInitRank(&comm, world, id, rank);
+  if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
   h->comm = comm;
   return BVB_OK;
 }

@@ -238,6 +238,19 @@ int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,
 int bvb_comm_unique_id(char* unique_id_128);
 int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128);
 
+/* ---- a14: irf_cpp (src/irf.cpp:468-524) -------------------------------------------
+ * Impulse responses for R stored posterior draws.  coefficients Kp x M x R;
+ * factor_loadings M x n_factors x R (n_factors = 0: NULL); U_vecs n_U x R
+ * (has_U = 0: NULL); logvar_t ld_logvar x R (log-variances at the chosen time
+ * point); shocks dim x n_shocks with dim = n_factors (factor), M (otherwise);
+ * rotation dim x dim x R or NULL.  out: M x n_shocks x (ahead+1) x R - the array
+ * R/irf.R:275-276 builds from the returned field<cube>.  Draws are sharded over
+ * the ranks of bvb_comm_init by the caller (disjoint slices, no collective). */
+int bvb_irf(bvb_handle* h, int Kp, int M, int R, int n_factors, int has_U, int ld_logvar,
+            int dim, int n_shocks, int ahead, const double* coefficients,
+            const double* factor_loadings, const double* U_vecs, const double* logvar_t,
+            const double* shocks, const double* rotation, double* out);
+
 /* ---- diagnostics -------------------------------------------------------------
  * Measured FP64 peaks on this device (own micro-kernels, register-resident):
  * out[0] = DMMA m8n8k4 TFLOP/s, out[1] = DFMA TFLOP/s, out[2] = SM clock MHz
