@@ -207,6 +207,9 @@ def run_cuda(args):
     launches = tm["launches_per_sweep"] * K
     del smp2
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     gf = algorithmic_gflop(w["M"], Kp, w["T"], w["r"])
