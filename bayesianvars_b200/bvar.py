@@ -318,6 +318,22 @@ def specify_prior_sigma(M, type="factor", factor_factors=1, factor_restrict="non
     return dict(prior_sigma_cpp=cpp, general_settings=gs)
 
 
+# --------------------------------------------------------------------------- sharding
+def shard_equations(M, rank, world):
+    """Contiguous block of equations owned by `rank` (mirrors bvb_gibbs_init: blocks of
+    ceil(M / world); trailing ranks may own nothing).  Returns (first, count)."""
+    nloc_max = -(-M // world)
+    j0 = min(M, rank * nloc_max)
+    return j0, max(0, min(M, j0 + nloc_max) - j0)
+
+
+def shard_draws(R, rank, world):
+    """Contiguous range of stored draws a rank processes in irf / predict (disjoint output slices)."""
+    per = -(-R // world)
+    r0 = min(R, rank * per)
+    return r0, max(0, min(R, r0 + per) - r0)
+
+
 # --------------------------------------------------------------------------- bvar()
 def _embed(Y_tmp, lags, intercept):
     """R's embed(Y_tmp, lags+1)[, -(1:M)] (+ ones column): R/bvar_wrapper.R:228-235."""
