@@ -3,6 +3,7 @@
 #include "bvb_internal.cuh"
 #include "gig.cuh"
 #include "chol.cuh"
+#include "huge.cuh"
 
 #include <string.h>
 #include <stdlib.h>
@@ -85,9 +86,23 @@ struct CholWorkspace {
   }
 };
 
+// Scratch of the expert_huge branch of bvb_phi_draw_factor.
+struct HugeWorkspace {
+  PairGeom g;   // pairs of observations: n = T, contraction length Kp
+  DevBuf<double> X, XT, Y, logvar, V, PHI0, lam, fac, z1, delta, PHI, A, Wv, WYzero, omega, u, nrm, wsol, zero_tm;
+  DevBuf<int2> lut, pairs;
+  DevBuf<int> colbase, status;
+  void release() {
+    for (DevBuf<double>* b : {&X, &XT, &Y, &logvar, &V, &PHI0, &lam, &fac, &z1, &delta, &PHI, &A, &Wv, &WYzero, &omega, &u,
+                              &nrm, &wsol, &zero_tm}) b->release();
+    lut.release(); pairs.release(); colbase.release(); status.release();
+  }
+};
+
 struct Scratch {
   PhiWorkspace phi;
   CholWorkspace chol;
+  HugeWorkspace huge;
   uint64_t call_counter = 0;
 };
 
@@ -151,6 +166,81 @@ int setup_geometry(bvb_handle* h, PhiWorkspace& ws, int T, int n, int M, int r) 
 
 }  // namespace
 
+static int phi_draw_factor_huge(bvb_handle* h, int T, int Kp, int M, int r, const double* X, const double* Y,
+                                const double* logvar_idi, const double* V_prior, const double* PHI0,
+                                const double* facload, const double* fac, const double* z, const double* delta,
+                                double* PHI_out) {
+  if (k2_smem_bytes(T) > 227 * 1024) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor(huge): T=%d exceeds the in-SM panel of the T x T solve", T);
+    return BVB_ERR_UNSUPPORTED;
+  }
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  Scratch* sc = scratch_of(h);
+  HugeWorkspace& ws = sc->huge;
+  cudaStream_t s = h->stream;
+  make_pair_geom(ws.g, Kp, T);   // contraction over the Kp coefficients, systems of order T
+  const int Kp_pad = ws.g.Tp;
+  const size_t tm = (size_t)T * M, km = (size_t)Kp * M, d = sizeof(double);
+  const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
+  BVB_CUDA_TRY(ws.lut.ensure(ws.g.nArows)); BVB_CUDA_TRY(ws.pairs.ensure(ws.g.nArows));
+  BVB_CUDA_TRY(ws.colbase.ensure(ws.g.colbase.size()));
+  BVB_CUDA_TRY(ws.A.ensure((size_t)ws.g.nArows * Kp_pad));
+  ws.Wv.release(); ws.WYzero.release(); ws.zero_tm.release();
+  BVB_CUDA_TRY(ws.Wv.ensure((size_t)Nalloc * Kp_pad, true, s));
+  BVB_CUDA_TRY(ws.WYzero.ensure((size_t)Nalloc * Kp_pad, true, s));
+  BVB_CUDA_TRY(ws.zero_tm.ensure(tm, true, s));
+  BVB_CUDA_TRY(ws.omega.ensure((size_t)M * ws.g.ldo));
+  BVB_CUDA_TRY(ws.X.ensure((size_t)T * Kp)); BVB_CUDA_TRY(ws.XT.ensure((size_t)T * Kp)); BVB_CUDA_TRY(ws.Y.ensure(tm));
+  BVB_CUDA_TRY(ws.logvar.ensure(tm)); BVB_CUDA_TRY(ws.V.ensure(km)); BVB_CUDA_TRY(ws.PHI0.ensure(km));
+  BVB_CUDA_TRY(ws.z1.ensure(km)); BVB_CUDA_TRY(ws.delta.ensure(tm)); BVB_CUDA_TRY(ws.PHI.ensure(km));
+  BVB_CUDA_TRY(ws.u.ensure(km)); BVB_CUDA_TRY(ws.nrm.ensure(tm)); BVB_CUDA_TRY(ws.wsol.ensure(tm));
+  BVB_CUDA_TRY(ws.status.ensure(M));
+  if (r > 0) { BVB_CUDA_TRY(ws.lam.ensure((size_t)M * r)); BVB_CUDA_TRY(ws.fac.ensure((size_t)r * T)); }
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.lut.p, ws.g.lut.data(), sizeof(int2) * ws.g.nArows, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.pairs.p, ws.g.pairs.data(), sizeof(int2) * ws.g.nArows, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.colbase.p, ws.g.colbase.data(), sizeof(int) * ws.g.colbase.size(), cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.X.p, X, d * T * Kp, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.Y.p, Y, d * tm, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.logvar.p, logvar_idi, d * tm, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.V.p, V_prior, d * km, cudaMemcpyHostToDevice, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(ws.PHI0.p, PHI0, d * km, cudaMemcpyHostToDevice, s));
+  if (r > 0) {
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.lam.p, facload, d * M * r, cudaMemcpyHostToDevice, s));
+    BVB_CUDA_TRY(cudaMemcpyAsync(ws.fac.p, fac, d * r * T, cudaMemcpyHostToDevice, s));
+  }
+  if (z) BVB_CUDA_TRY(cudaMemcpyAsync(ws.z1.p, z, d * km, cudaMemcpyHostToDevice, s));
+  else fill_normals_kernel<<<(unsigned)((km + 255) / 256), 256, 0, s>>>(ws.z1.p, km, h->seed, (uint32_t)(0x5100u + sc->call_counter));
+  if (delta) BVB_CUDA_TRY(cudaMemcpyAsync(ws.delta.p, delta, d * tm, cudaMemcpyHostToDevice, s));
+  else fill_normals_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(ws.delta.p, tm, h->seed, (uint32_t)(0x5200u + sc->call_counter));
+  sc->call_counter++;
+  BVB_CUDA_TRY(cudaMemsetAsync(ws.status.p, 0, sizeof(int) * M, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  BVB_CUDA_TRY(launch_huge_setup(ws.XT.p, ws.A.p, ws.X.p, ws.pairs.p, T, Kp, Kp_pad, ws.g.nArows, s));
+  HugeCtx c;
+  c.T = T; c.Kp = Kp; c.Kp_pad = Kp_pad; c.M = M; c.r = r; c.X = ws.X.p; c.Y = ws.Y.p; c.logvar = ws.logvar.p; c.V = ws.V.p;
+  c.PHI0 = ws.PHI0.p; c.facload = ws.lam.p; c.fac = ws.fac.p; c.z1 = ws.z1.p; c.delta = ws.delta.p; c.PHI = ws.PHI.p;
+  c.A = ws.A.p; c.lut_h = ws.lut.p; c.pairs_h = ws.pairs.p; c.colbase_h = ws.colbase.p; c.nZtiles = ws.g.nZtiles;
+  c.ntiles = ws.g.nZtiles + ws.g.nXtiles; c.ldo = ws.g.ldo; c.Wv = ws.Wv.p; c.WYzero = ws.WYzero.p; c.omega = ws.omega.p;
+  c.u = ws.u.p; c.nrm = ws.nrm.p; c.wsol = ws.wsol.p; c.zero_tm = ws.zero_tm.p; c.status = ws.status.p;
+  BVB_CUDA_TRY(launch_phi_huge(c, s));
+  BVB_CUDA_TRY(cudaEventRecord(h->ev[1], s));
+  std::vector<int> st(M);
+  BVB_CUDA_TRY(cudaMemcpyAsync(PHI_out, ws.PHI.p, d * km, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaMemcpyAsync(st.data(), ws.status.p, sizeof(int) * M, cudaMemcpyDeviceToHost, s));
+  BVB_CUDA_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->last_ms[0] = h->last_ms[1] = h->last_ms[2] = 0; h->last_ms[3] = ms;
+  h->last_launches = 7;
+  for (int j = 0; j < M; ++j)
+    if (st[j] != 0) {
+      h->err_eq = j + 1;
+      bvb_set_error(h, BVB_ERR_NUMERIC, "univariate_regression_update() failed in %ith eqation: solve(): solution not found", j + 1);
+      return BVB_ERR_NUMERIC;
+    }
+  return BVB_OK;
+}
+
 extern "C" {
 
 const char* bvb_version(void) { return "bvb 0.1 (sm_100a)"; }
@@ -188,6 +278,7 @@ void bvb_destroy(bvb_handle* h) {
   if (h->scratch) {
     scratch_of(h)->phi.release();
     scratch_of(h)->chol.release();
+    scratch_of(h)->huge.release();
     delete scratch_of(h);
   }
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -231,11 +322,7 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
     bvb_set_error(h, BVB_ERR_ARG, "bvb_phi_draw_factor: invalid argument");
     return BVB_ERR_ARG;
   }
-  if (huge) {
-    (void)delta;
-    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor: huge branch not built yet");
-    return BVB_ERR_UNSUPPORTED;
-  }
+  if (huge) return phi_draw_factor_huge(h, T, Kp, M, r, X, Y, logvar_idi, V_prior, PHI0, facload, fac, z, delta, PHI_out);
   if (k2_smem_bytes(Kp) > 227 * 1024) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor: Kp=%d exceeds the in-SM panel of the standard path; use huge", Kp);
     return BVB_ERR_UNSUPPORTED;

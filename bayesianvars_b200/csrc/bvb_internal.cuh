@@ -66,6 +66,11 @@ struct K1Params {
   double* omega;       // [M][ldo]
   int Tp, nZtiles, ntiles, M, n;
   long ldo;
+  // expert_huge mode (sample_coefficients.cpp:40-52): rows are pairs (t, s) of observations, the
+  // contraction runs over the coefficients, and the epilogue writes
+  //   acc * rowscale[t, j] * rowscale[s, j] + (t == s)       (= X_norm V X_norm' + I_T)
+  const int2* pairs = nullptr;      // [nArows] {t, s}
+  const double* rowscale = nullptr; // [n][M] normaliser exp(-h/2); non-null selects the mode
 };
 cudaError_t launch_k1(const K1Params& p, cudaStream_t s);
 

@@ -298,6 +298,17 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
     gibbs_clamp_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
                                                                    G.PHI_tol, h->seed, sw, G.status.p);
+  } else if (K > 0 && G.huge) {
+    // ---- 1) PHI | .  (factor structure, expert_huge: T x T systems; every rank draws all equations)
+    const size_t nz = (size_t)Kp * M, nd = (size_t)T * M;
+    gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, M, Kp, 0, h->seed, sw);
+    gibbs_flat_normals_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, s>>>(G.hdelta.p, nd, h->seed, STREAM_PHI_Z + 2, sw);
+    mark(1);
+    GB_TRY(launch_phi_huge(G.chuge, s));
+    mark(2); mark(3); mark(4);
+    const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
+    gibbs_clamp_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
+                                                                   G.PHI_tol, h->seed, sw, G.status.p);
   } else if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
     // ---- 1) PHI | .  (factor structure: equations independent)
     GB_TRY(launch_prep_factor(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p, G.fac.p, T, G.geom.Tp, M, G.r, s));
@@ -405,10 +416,14 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "cholesky structure does not shard (Gauss-Seidel over equations): run one chain per GPU");
     return BVB_ERR_UNSUPPORTED;
   }
-  if (huge) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_gibbs_init: expert_huge path not built yet"); return BVB_ERR_UNSUPPORTED; }
   const int r = chol ? 0 : ps->factor_factors;
   if (r < 0 || r > FSV_RMAX) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "factor_factors=%d outside [0,%d]", r, FSV_RMAX); return BVB_ERR_UNSUPPORTED; }
-  if (Kp > 0 && k2_smem_bytes(Kp) > 227 * 1024) {
+  const bool use_huge = huge && !chol && K > 0;   // 'expert_huge=TRUE' is ignored for the cholesky structure (R/bvar_wrapper.R:389-391)
+  if (use_huge && k2_smem_bytes(T) > 227 * 1024) {
+    bvb_set_error(h, BVB_ERR_UNSUPPORTED, "expert_huge: T=%d exceeds the in-SM panel of the T x T solve", T);
+    return BVB_ERR_UNSUPPORTED;
+  }
+  if (Kp > 0 && !use_huge && k2_smem_bytes(Kp) > 227 * 1024) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "Kp=%d exceeds the in-SM panel of the standard path; use expert_huge", Kp);
     return BVB_ERR_UNSUPPORTED;
   }
@@ -424,6 +439,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   G.draws = draws; G.burnin = burnin; G.thin = thin; G.tvp_all = tvp_keep_all ? 1 : 0;
   G.nsave = draws / thin; G.PHI_tol = PHI_tol; G.L_tol = L_tol; G.out = *out;
   G.sigma_type = ps->type;
+  G.huge = use_huge ? 1 : 0;
   G.rank = h->rank; G.world = h->world > 0 ? h->world : 1; G.comm = h->comm;
   G.nloc_max = (M + G.world - 1) / G.world;
   G.j0 = std::min(M, G.rank * G.nloc_max);
@@ -449,14 +465,27 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     if ((rc = upload(h, G.lut, G.geom.lut.data(), G.geom.nArows))) return rc;
     if ((rc = upload(h, G.pairs, G.geom.pairs.data(), G.geom.nArows))) return rc;
     if ((rc = upload(h, G.colbase, G.geom.colbase.data(), G.geom.colbase.size()))) return rc;
-    GB_TRY(G.A.ensure((size_t)G.geom.nArows * G.geom.Tp));
+    if (!use_huge) GB_TRY(G.A.ensure((size_t)G.geom.nArows * G.geom.Tp));
     const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
     GB_TRY(G.W.ensure((size_t)Nalloc * G.geom.Tp, true));
     GB_TRY(G.WY.ensure((size_t)Nalloc * G.geom.Tp, true));
-    GB_TRY(G.omega.ensure((size_t)std::max(G.nloc, 1) * G.geom.ldo));
-    GB_TRY(G.Zn.ensure((size_t)Kp * std::max(G.nloc, 1)));
+    if (!use_huge) GB_TRY(G.omega.ensure((size_t)std::max(G.nloc, 1) * G.geom.ldo));
+    GB_TRY(G.Zn.ensure((size_t)Kp * std::max(use_huge ? M : G.nloc, 1)));
     // the pair-product matrix Z is built ONCE per chain: X never changes
-    GB_TRY(launch_build_A(G.A.p, G.X.p, G.pairs.p, T, G.geom.Tp, Kp, G.geom.nArows, 0, s));
+    if (!use_huge) GB_TRY(launch_build_A(G.A.p, G.X.p, G.pairs.p, T, G.geom.Tp, Kp, G.geom.nArows, 0, s));
+    if (use_huge) {
+      make_pair_geom(G.geomH, Kp, T);   // pairs of observations, contraction over the coefficients
+      const int Kp_pad = G.geomH.Tp;
+      if ((rc = upload(h, G.luth, G.geomH.lut.data(), G.geomH.nArows))) return rc;
+      if ((rc = upload(h, G.pairsh, G.geomH.pairs.data(), G.geomH.nArows))) return rc;
+      if ((rc = upload(h, G.colbaseh, G.geomH.colbase.data(), G.geomH.colbase.size()))) return rc;
+      const size_t tm2 = (size_t)T * M;
+      GB_TRY(G.XT.ensure((size_t)T * Kp)); GB_TRY(G.Ah.ensure((size_t)G.geomH.nArows * Kp_pad));
+      GB_TRY(G.Wv.ensure((size_t)Nalloc * Kp_pad, true)); GB_TRY(G.WYzh.ensure((size_t)Nalloc * Kp_pad, true));
+      GB_TRY(G.omegah.ensure((size_t)M * G.geomH.ldo)); GB_TRY(G.hu.ensure((size_t)Kp * M)); GB_TRY(G.hnrm.ensure(tm2));
+      GB_TRY(G.hwsol.ensure(tm2)); GB_TRY(G.hzero.ensure(tm2, true)); GB_TRY(G.hdelta.ensure(tm2));
+      GB_TRY(launch_huge_setup(G.XT.p, G.Ah.p, G.X.p, G.pairsh.p, T, Kp, Kp_pad, G.geomH.nArows, s));
+    }
   }
 
   // ---- prior variances V_prior (Kp x M): V_i on the lag rows, priorIntercept on the last row
@@ -608,6 +637,15 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   F.facloadtol = ps->factor_facloadtol; F.ngprior = ps->factor_ngprior; F.columnwise = ps->factor_columnwise;
   F.interweaving = ps->factor_interweaving > 4 ? 4 : ps->factor_interweaving;
   if (Kp == 0) GB_TRY(cudaMemcpyAsync(G.resid.p, G.Y.p, sizeof(double) * (size_t)T * M, cudaMemcpyDeviceToDevice, s));
+  if (use_huge) {
+    HugeCtx& c = G.chuge;
+    c.T = T; c.Kp = Kp; c.Kp_pad = G.geomH.Tp; c.M = M; c.r = r; c.X = G.X.p; c.Y = G.Y.p; c.logvar = G.logvar.p;
+    c.V = G.Vprior.p; c.PHI0 = G.PHI0.p; c.facload = G.facload.p; c.fac = G.fac.p; c.z1 = G.Zn.p; c.delta = G.hdelta.p;
+    c.PHI = G.PHI.p; c.A = G.Ah.p; c.lut_h = G.luth.p; c.pairs_h = G.pairsh.p; c.colbase_h = G.colbaseh.p;
+    c.nZtiles = G.geomH.nZtiles; c.ntiles = G.geomH.nZtiles + G.geomH.nXtiles; c.ldo = G.geomH.ldo; c.Wv = G.Wv.p;
+    c.WYzero = G.WYzh.p; c.omega = G.omegah.p; c.u = G.hu.p; c.nrm = G.hnrm.p; c.wsol = G.hwsol.p; c.zero_tm = G.hzero.p;
+    c.status = G.eqstatus.p;
+  }
 
   // ---- cholesky structure: U, its prior block, and the contexts of the two sequential draws
   int priorU = BVB_PRIOR_NORMAL;

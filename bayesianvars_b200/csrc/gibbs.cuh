@@ -4,6 +4,7 @@
 #include "hyper.cuh"
 #include "fsv.cuh"
 #include "chol.cuh"
+#include "huge.cuh"
 
 namespace bvb {
 
@@ -88,6 +89,13 @@ struct Gibbs {
   CholUCtx cu;
   size_t off_U = 0, off_uhyper = 0;
   int uhyper_rows = 0;
+  // expert_huge branch (factor structure, T x T systems)
+  int huge = 0;
+  PairGeom geomH;
+  HugeCtx chuge;
+  GBuf<double> XT, Ah, Wv, WYzh, omegah, hu, hnrm, hwsol, hzero, hdelta;
+  GBuf<int2> luth, pairsh;
+  GBuf<int> colbaseh;
   // stored draws
   GibbsStore store;
   GBuf<double> ring;

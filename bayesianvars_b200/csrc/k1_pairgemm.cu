@@ -126,7 +126,11 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 2 ? 3 : 2)) k1_pairgemm(const 
         const int j = n0 + (nt0 + nt) * 8 + 2 * fk + e;
         if (j >= p.M) continue;
         double v = acc[m][nt][e];
-        if (l.y >= 0) {
+        if (p.rowscale) {
+          if (!ztile) continue;   // the right-hand side of the T x T system is written by huge_rhs_kernel
+          const int2 ts = p.pairs[row];
+          v = v * p.rowscale[(size_t)j * p.n + ts.x] * p.rowscale[(size_t)j * p.n + ts.y] + (ts.x == ts.y ? 1.0 : 0.0);
+        } else if (l.y >= 0) {
           const double pv = p.V[(size_t)j * p.n + l.y];
           if (ztile) v += 1.0 / pv;
           else if (p.PHI0) v += p.PHI0[(size_t)j * p.n + l.y] / pv;

@@ -216,3 +216,24 @@ def test_cholesky_storage_and_determinism(handle):
     order = np.lexsort((iu[0], iu[1]))
     assert np.array_equal(st["U"][iu[0][order], iu[1][order]], b.out["U"][:, -1])
     assert np.abs(b.out["U"]).min() >= 1e-18      # L_tol clamp (bvar_cpp.cpp:667-685)
+
+
+def test_expert_huge_chain_matches_standard_chain(handle):
+    """expert_huge only changes HOW each PHI conditional is drawn, not its law: posterior
+    means of the huge chain agree with the standard chain within Monte-Carlo error, and with
+    the oracle's huge chain."""
+    M, p, T = 4, 3, 40      # Kp = 13
+    Y, A = sim_var(M, p, T)
+    pp = B.specify_prior_phi(M, p, "HS")
+    ps = B.specify_prior_sigma(M, factor_factors=1)
+    prep = B.prepare(Y, p, 10.0, pp, ps, rng=np.random.default_rng(3))
+    a = B.Sampler(handle, prep, pp, ps, draws=4000, burnin=1000, expert_huge=True); a.run()
+    b = B.Sampler(handle, prep, pp, ps, draws=4000, burnin=1000, expert_huge=False); b.run()
+    o = og.run(prep, pp, ps, draws=1500, burnin=500, rng=np.random.default_rng(5), huge=True)
+    assert np.isfinite(a.out["PHI"]).all()
+    for other, n2 in ((b.out["PHI"], 4000), (o["PHI"], 1500)):
+        for i in range(prep["Kp"]):
+            for j in range(M):
+                x, y = a.out["PHI"][i, j], other[i, j]
+                se = np.sqrt(batch_means_var(x, 30) + batch_means_var(y, 30))
+                assert abs(x.mean() - y.mean()) < 5 * se + 0.02, (i, j, x.mean(), y.mean(), se)

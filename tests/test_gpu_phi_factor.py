@@ -105,3 +105,28 @@ def test_cholesky_failure_is_reported(handle):
     with pytest.raises(BvbError) as ei:
         run(handle, d)
     assert ei.value.code == 3 and ei.value.equation == 3 and "eqation" in str(ei.value)
+
+
+# ------------------------------------------------------------------ expert_huge branch
+@pytest.mark.parametrize("M,p,T,r", [(3, 2, 5, 0), (8, 6, 30, 1), (12, 10, 60, 2), (20, 8, 100, 1), (30, 14, 150, 1)])
+def test_huge_branch_matches_oracle(handle, M, p, T, r):
+    """sample_coefficients.cpp:40-52 (Bhattacharya et al.): Kp normals for u, then T normals for
+    delta, per equation.  Kp = p*M + 1 > T in most of these shapes."""
+    d = phi_draw_inputs(M, p, T, r, seed=300 + M)
+    rng = np.random.default_rng(M)
+    delta = np.asfortranarray(rng.standard_normal((T, M)))
+    ref = orc.sample_PHI_factor(d["PHI0"], d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"],
+                                d["facload"], d["fac"], True, d["z"], delta)
+    out = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"],
+                                   huge=True, z=d["z"], delta=delta)
+    assert per_eq_relerr(out, ref) < TOL
+
+
+def test_huge_and_standard_agree_in_mean(handle):
+    """With all injected normals zero both branches return the exact posterior mean (Woodbury)."""
+    d = phi_draw_inputs(10, 4, 70, 1, seed=77)
+    z0 = np.zeros_like(d["z"], order="F")
+    a = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"], z=z0)
+    b = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"], huge=True,
+                                 z=z0, delta=np.zeros((70, 10), order="F"))
+    assert per_eq_relerr(b, a) < 1e-8
