@@ -137,3 +137,52 @@ class Handle:
                                fptr(rot.reshape(-1, order="F")) if rot is not None else None, fptr(out.reshape(-1, order="F")))
         self._check(rc)
         return out
+
+    # -- a15: out_of_sample (src/utilities_cpp.cpp:216-393) ----------------------------
+    def out_of_sample(self, each, X_T_plus_1, PHI, U, facload, logvar_T, ahead, sv_mu, sv_phi, sv_sigma,
+                      sv_indicator, factor, LPL, Y_obs, LPL_subset, VoI, simulate_predictive,
+                      z_logvar=None, z_pred=None):
+        """Same argument order and 0-based index vectors as the Rcpp export
+        (R/utility_functions.R:2469-2485); returns the four arrays of its List."""
+        PHI = np.asfortranarray(PHI, dtype=np.float64)
+        Kp, M, R = PHI.shape
+        factor = bool(factor)
+        nf = (0 if facload is None or np.size(facload) == 0 else np.shape(facload)[1]) if factor else 0
+        fl = np.asfortranarray(facload, dtype=np.float64) if nf else None
+        uv = None if factor or M < 2 else np.asfortranarray(np.asarray(U, dtype=np.float64).reshape(-1, R))
+        lv = np.asfortranarray(np.asarray(logvar_T, dtype=np.float64).reshape(-1, R))
+        ahead = np.ascontiguousarray(ahead, dtype=np.int32)
+        svi = np.ascontiguousarray(sv_indicator if sv_indicator is not None else [], dtype=np.int32)
+        nsv = svi.size
+        mu = np.asfortranarray(np.asarray(sv_mu, dtype=np.float64).reshape(-1, R)) if nsv else None
+        ph = np.asfortranarray(np.asarray(sv_phi, dtype=np.float64).reshape(-1, R)) if nsv else None
+        sg = np.asfortranarray(np.asarray(sv_sigma, dtype=np.float64).reshape(-1, R)) if nsv else None
+        x = np.ascontiguousarray(X_T_plus_1, dtype=np.float64).ravel()
+        na, nsave = ahead.size, R * int(each)
+        LPL, LPL_subset, simulate_predictive = bool(LPL), bool(LPL_subset), bool(simulate_predictive)
+        yo = np.asfortranarray(Y_obs, dtype=np.float64) if LPL else None
+        voi = np.ascontiguousarray(VoI if VoI is not None else [], dtype=np.int32)
+        zl = None if z_logvar is None or not nsv else np.ascontiguousarray(z_logvar, dtype=np.float64)
+        zp = None if z_pred is None else np.ascontiguousarray(z_pred, dtype=np.float64)
+        if zl is not None:
+            assert zl.shape == (R, int(ahead.max()), each, nsv)
+        if zp is not None:
+            assert zp.shape == (R, na, each, M)
+        LPLd = np.zeros((na, nsave), order="F") if LPL else np.zeros((0, 0))
+        PLu = np.zeros((na, M, nsave), order="F") if LPL else np.zeros((0, 0, 0))
+        LPLs = np.zeros((na, nsave), order="F") if LPL and LPL_subset else np.zeros((0, 0))
+        pred = np.zeros((na, M, nsave), order="F") if simulate_predictive else np.zeros((0, 0, 0))
+        dp, ip = _lib._dp, _lib._ip
+
+        def P(a):
+            return None if a is None or a.size == 0 else a.ctypes.data_as(dp)
+
+        def I(a):
+            return None if a is None or a.size == 0 else a.ctypes.data_as(ip)
+
+        rc = self._lib.bvb_predict(self._h, int(each), Kp, M, R, nf, lv.shape[0], int(factor), P(x), P(PHI), P(uv), P(fl),
+                                   P(lv), I(ahead), na, P(mu), P(ph), P(sg), I(svi), nsv, int(LPL), P(yo),
+                                   int(LPL_subset), I(voi), voi.size, int(simulate_predictive), P(zl), P(zp),
+                                   P(LPLd), P(PLu), P(LPLs), P(pred))
+        self._check(rc)
+        return dict(LPL_draws=LPLd, PL_univariate_draws=PLu, LPL_sub_draws=LPLs, predictions=pred)

@@ -1,0 +1,409 @@
+// K7 - predictive simulation / log predictive likelihoods over stored draws.
+//
+// Replaces out_of_sample (src/utilities_cpp.cpp:216-393) with its helpers
+// build_sigma (:45-67), PHI_power0 (:125-142), Sigma_pred_uncond (:144-178) and
+// dmvnrm_arma_fast (:19-42).  Every (draw r, replicate j) pair is an independent
+// chain over the horizons, so the grid is persistent CTAs striding over the
+// R*each chains; a chain keeps its Kp x Kp companion covariance, the M x M
+// innovation covariance and its Cholesky factor in a per-CTA global scratch slab
+// (L2-resident) and runs the dense steps (PHI' S, S PHI, PHI-power) through a
+// shared-memory tiled FP64 GEMM.  The reference's arithmetic is followed step by
+// step (same recursion, same symmetrisation, chol -> inverse-free solves).
+// Slice index of chain (r, j) is r + j*R (:352, :364, :376).
+#include "bvb_internal.cuh"
+
+namespace bvb {
+
+constexpr int PR_THREADS = 256;
+
+struct PredictParams {
+  int each, Kp, M, R, nf, nU, ld_lv, na, max_ahead, nsv, factor, lpl, lpl_sub, nvoi, simulate, p;
+  const double *x, *PHI, *U, *facload, *logvar_T, *sv_mu, *sv_phi, *sv_sigma, *Y_obs, *z_logvar, *z_pred;
+  const int *ahead, *sv_ind, *voi;
+  double *LPL, *PLu, *LPLs, *pred;
+  double* scratch;          // per CTA slab
+  size_t slab;              // doubles per CTA
+  uint64_t seed;
+  int* status;
+};
+
+// C[m x n] (ldc) = op(A) * B (+ C if accumulate); A is k x m when transA (lda), else m x k.  All column-major in
+// global memory.  64 x 64 output tile, 4 x 4 per thread, K chunks of 16 through shared memory.
+__device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool transA, const double* B, int ldb, double* C,
+                         int ldc, bool accumulate, double* sA /*[16][65]*/, double* sB /*[16][65]*/) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int m0 = 0; m0 < m; m0 += 64) {
+    for (int n0 = 0; n0 < n; n0 += 64) {
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int k0 = 0; k0 < k; k0 += 16) {
+        for (int i = tid; i < 16 * 64; i += PR_THREADS) {
+          const int kk = i / 64, mm = i % 64;           // sA[kk][mm] = op(A)[m0+mm, k0+kk]
+          const int gm = m0 + mm, gk = k0 + kk;
+          double v = 0.0;
+          if (gm < m && gk < k) v = transA ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
+          sA[kk * 65 + mm] = v;
+          const int gn = n0 + mm;                        // sB[kk][nn] = B[k0+kk, n0+nn]
+          double w = 0.0;
+          if (gn < n && gk < k) w = B[(size_t)gn * ldb + gk];
+          sB[kk * 65 + mm] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) av[a] = sA[kk * 65 + tx + 16 * a];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) bv[b] = sB[kk * 65 + ty + 16 * b];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int gm = m0 + tx + 16 * a, gn = n0 + ty + 16 * b;
+          if (gm < m && gn < n) {
+            double* c = C + (size_t)gn * ldc + gm;
+            *c = accumulate ? *c + acc[a][b] : acc[a][b];
+          }
+        }
+    }
+  }
+  __syncthreads();
+}
+
+// In-place lower Cholesky of the n x n matrix L (ld), right-looking, whole CTA.  Returns false on a bad pivot.
+__device__ bool cta_chol(int n, double* L, int ld, double* sh) {
+  bool ok = true;
+  for (int c = 0; c < n; ++c) {
+    __syncthreads();
+    const double d = L[(size_t)c * ld + c];
+    if (!(d > 0.0)) ok = false;
+    const double piv = sqrt(d > 0.0 ? d : 1.0);
+    __syncthreads();
+    for (int i = c + threadIdx.x; i < n; i += PR_THREADS) L[(size_t)c * ld + i] = (i == c) ? piv : L[(size_t)c * ld + i] / piv;
+    __syncthreads();
+    const int rem = n - c - 1;
+    for (int idx = threadIdx.x; idx < rem * rem; idx += PR_THREADS) {
+      const int a = c + 1 + idx % rem, b = c + 1 + idx / rem;
+      if (a >= b) L[(size_t)b * ld + a] -= L[(size_t)c * ld + a] * L[(size_t)c * ld + b];
+    }
+  }
+  __syncthreads();
+  (void)sh;
+  return ok;
+}
+
+// log N(x; mean, L L') for the n-vector d = x - mean (overwritten with L^-1 d); thread 0 returns the value.
+__device__ double cta_mvn_logdens(int n, const double* L, int ld, double* d) {
+  double out = 0.0;
+  if (threadIdx.x == 0) {
+    double ld_sum = 0.0, q = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double v = d[i];
+      for (int k = 0; k < i; ++k) v -= L[(size_t)k * ld + i] * d[k];
+      v /= L[(size_t)i * ld + i];
+      d[i] = v;
+      q += v * v;
+      ld_sum += log(L[(size_t)i * ld + i]);
+    }
+    out = -ld_sum - 0.5 * n * 1.8378770664093453 - 0.5 * q;   // log(2 pi)
+  }
+  __syncthreads();
+  return out;
+}
+
+__global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams p) {
+  __shared__ double sA[16 * 65], sB[16 * 65];
+  __shared__ double sres[2];
+  const int Kp = p.Kp, M = p.M, R = p.R, P = p.p, tid = threadIdx.x;
+  double* base = p.scratch + (size_t)blockIdx.x * p.slab;
+  double* SL = base;                               // Kp x Kp
+  double* TMP = SL + (size_t)Kp * Kp;              // Kp x Kp
+  double* SIG = TMP + (size_t)Kp * Kp;             // M x M
+  double* LCH = SIG + (size_t)M * M;               // M x M (also used for the VoI sub-matrix)
+  double* UINV = LCH + (size_t)M * M;              // M x M
+  double* PP0 = UINV + (size_t)M * M;              // Kp x M
+  double* PP1 = PP0 + (size_t)Kp * M;              // Kp x M
+  double* lvp = PP1 + (size_t)Kp * M;              // [M + nf]
+  double* lvvar = lvp + (M + p.nf);                // [nsv]
+  double* yp = lvvar + (p.nsv > 0 ? p.nsv : 1);    // [M]
+  double* dv = yp + M;                             // [M]
+  const int nsave = R * p.each;
+  for (int chain = blockIdx.x; chain < nsave; chain += gridDim.x) {
+    const int r = chain % R, j = chain / R;
+    const double* PHI = p.PHI + (size_t)r * Kp * M;
+    const double* lvT = p.logvar_T + (size_t)r * p.ld_lv;
+    for (size_t i = tid; i < (size_t)Kp * Kp; i += PR_THREADS) SL[i] = 0.0;
+    for (size_t i = tid; i < (size_t)Kp * M; i += PR_THREADS) PP0[i] = PHI[i];
+    for (int i = tid; i < p.nsv; i += PR_THREADS) lvvar[i] = 0.0;
+    if (!p.factor) {
+      // U_inv = inv(trimatu(Um)), one thread per column: back substitution on the unit upper triangle
+      const double* u = p.U + (size_t)r * p.nU;
+      for (int c = tid; c < M; c += PR_THREADS) {
+        double* col = UINV + (size_t)c * M;
+        for (int i = M - 1; i >= 0; --i) {
+          double v = (i == c) ? 1.0 : 0.0;
+          if (i < c) for (int k = i + 1; k <= c; ++k) v -= u[(size_t)k * (k - 1) / 2 + i] * col[k];
+          col[i] = (i <= c) ? v : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    double* PPc = PP0;
+    double* PPn = PP1;
+    int counter = 0;
+    for (int i = 0; i < p.max_ahead; ++i) {
+      // ---- log-variance forecast (:300-304, :325-329)
+      for (int s = tid; s < M + p.nf; s += PR_THREADS) lvp[s] = lvT[s];
+      __syncthreads();
+      for (int s = tid; s < p.nsv; s += PR_THREADS) {
+        const double mu = p.sv_mu[(size_t)r * p.nsv + s], ph = p.sv_phi[(size_t)r * p.nsv + s], sg = p.sv_sigma[(size_t)r * p.nsv + s];
+        const int idx = p.sv_ind[s];
+        const double mean = mu + pow(ph, (double)(i + 1)) * (lvT[idx] - mu);
+        const double t = sg * pow(ph, (double)i);
+        const double var = lvvar[s] + t * t;
+        lvvar[s] = var;
+        double z;
+        if (p.z_logvar) z = p.z_logvar[(((size_t)r * p.max_ahead + i) * p.each + j) * p.nsv + s];
+        else { RngStream g(p.seed, 0x700u, (uint32_t)(chain * p.max_ahead + i), (uint32_t)s); z = g.normal(); }
+        lvp[idx] = mean + z * sqrt(var);
+      }
+      // ---- PHI to the power i+1 (:306-309, PHI_power0 :125-142)
+      if (i > 0) {
+        cta_gemm(Kp, M, M, PHI, Kp, false, PPc, Kp, PPn, Kp, false, sA, sB);   // PHI * old[0:M, :]
+        for (size_t e = tid; e < (size_t)Kp * M; e += PR_THREADS) {
+          const int row = (int)(e % Kp);
+          double add = 0.0;
+          if (row < (P - 1) * M) add = PPc[e + M];                 // old rows of the next lag block
+          else if (row >= P * M) add = PPc[e];                     // intercept row
+          PPn[e] += add;
+        }
+        __syncthreads();
+        double* t = PPc; PPc = PPn; PPn = t;
+      }
+      __syncthreads();
+      // ---- Sigma (build_sigma :45-67, return_chol = false)
+      for (int e = tid; e < M * M; e += PR_THREADS) {
+        const int a = e % M, b = e / M;
+        double v = 0.0;
+        if (p.factor) {
+          const double* L = p.facload + (size_t)r * M * p.nf;
+          for (int k = 0; k < p.nf; ++k) v = fma(L[(size_t)k * M + a] * L[(size_t)k * M + b], exp(lvp[M + k]), v);
+          if (a == b) v += exp(lvp[a]);
+        } else {
+          const int lo = a > b ? a : b;  // U_inv is upper triangular: rows m <= min(a, b)
+          (void)lo;
+          const int mm = a < b ? a : b;
+          for (int m2 = 0; m2 <= mm; ++m2) v = fma(UINV[(size_t)a * M + m2] * UINV[(size_t)b * M + m2], exp(lvp[m2]), v);
+        }
+        SIG[e] = v;
+      }
+      __syncthreads();
+      // ---- companion covariance recursion (Sigma_pred_uncond :144-178), n_ahead = i
+      if (P > 1) {
+        if (i > 0) {
+          const int mn = (i < P ? i : P) * M;
+          for (size_t e = tid; e < (size_t)Kp * Kp; e += PR_THREADS) TMP[e] = 0.0;
+          __syncthreads();
+          cta_gemm(M, mn, mn, PHI, Kp, true, SL, Kp, TMP, Kp, false, sA, sB);      // tmp[0:M, 0:mn] = PHI[0:mn,:]' SL[0:mn,0:mn]
+          for (size_t e = tid; e < (size_t)(P - 1) * M * Kp; e += PR_THREADS) {     // tmp.rows(M, pM-1) = SL.rows(0, (p-1)M-1)
+            const int row = (int)(e % ((size_t)(P - 1) * M)), col = (int)(e / ((size_t)(P - 1) * M));
+            TMP[(size_t)col * Kp + M + row] = SL[(size_t)col * Kp + row];
+          }
+          __syncthreads();
+          cta_gemm(M, M, mn, TMP, Kp, false, PHI, Kp, SL, Kp, false, sA, sB);      // SL[0:M,0:M] = tmp[0:M,0:mn] PHI[0:mn,:]
+          for (size_t e = tid; e < (size_t)Kp * (P - 1) * M; e += PR_THREADS) {     // SL.cols(M, pM-1) = tmp.cols(0, (p-1)M-1)
+            const int row = (int)(e % Kp), col = (int)(e / Kp);
+            SL[(size_t)(M + col) * Kp + row] = TMP[(size_t)col * Kp + row];
+          }
+          __syncthreads();
+          for (size_t e = tid; e < (size_t)Kp * Kp; e += PR_THREADS) {              // strict lower <- transposed upper
+            const int row = (int)(e % Kp), col = (int)(e / Kp);
+            if (row > col) SL[e] = SL[(size_t)row * Kp + col];
+          }
+          __syncthreads();
+        }
+      } else if (P == 1) {
+        if (i > 0) {
+          cta_gemm(M, M, M, PHI, Kp, true, SL, Kp, TMP, Kp, false, sA, sB);
+          cta_gemm(M, M, M, TMP, Kp, false, PHI, Kp, SL, Kp, false, sA, sB);
+        }
+      }
+      for (int e = tid; e < M * M; e += PR_THREADS) SL[(size_t)(e / M) * Kp + (e % M)] += SIG[e];
+      __syncthreads();
+      // ---- requested horizon? (:346-380)
+      if (counter < p.na && i == p.ahead[counter] - 1) {
+        for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
+          double v = 0.0;
+          for (int k = 0; k < Kp; ++k) v = fma(p.x[k], PPc[(size_t)m2 * Kp + k], v);
+          yp[m2] = v;
+        }
+        for (int e = tid; e < M * M; e += PR_THREADS) LCH[e] = SL[(size_t)(e / M) * Kp + (e % M)];
+        __syncthreads();
+        const bool ok = cta_chol(M, LCH, M, sA);
+        if (!ok && tid == 0) atomicCAS(p.status, 0, chain + 1);
+        if (p.lpl) {
+          for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
+            const double y = p.Y_obs[(size_t)m2 * p.na + counter];
+            dv[m2] = y - yp[m2];
+            const double sd = sqrt(SL[(size_t)m2 * Kp + m2]);
+            const double zz = (y - yp[m2]) / sd;
+            p.PLu[((size_t)chain * M + m2) * p.na + counter] = exp(-0.5 * zz * zz) / (sd * 2.5066282746310002);
+          }
+          __syncthreads();
+          const double ll = cta_mvn_logdens(M, LCH, M, dv);
+          if (tid == 0) p.LPL[(size_t)chain * p.na + counter] = ll;
+        }
+        if (p.simulate) {
+          for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
+            // y_pred + rand_vec * chol(Sigma) (upper R = L'): component m2 = sum_{k <= m2} z_k L[m2, k]
+            double v = yp[m2];
+            for (int k = 0; k <= m2; ++k) {
+              double z;
+              if (p.z_pred) z = p.z_pred[(((size_t)r * p.na + counter) * p.each + j) * M + k];
+              else { RngStream g(p.seed, 0x701u, (uint32_t)(chain * p.na + counter), (uint32_t)k); z = g.normal(); }
+              v = fma(z, LCH[(size_t)k * M + m2], v);
+            }
+            p.pred[((size_t)chain * M + m2) * p.na + counter] = v;
+          }
+        }
+        __syncthreads();
+        if (p.lpl && p.lpl_sub) {
+          const int nv = p.nvoi;
+          for (int e = tid; e < nv * nv; e += PR_THREADS) LCH[e] = SL[(size_t)p.voi[e / nv] * Kp + p.voi[e % nv]];
+          for (int e = tid; e < nv; e += PR_THREADS) dv[e] = p.Y_obs[(size_t)p.voi[e] * p.na + counter] - yp[p.voi[e]];
+          __syncthreads();
+          const bool ok2 = cta_chol(nv, LCH, nv, sA);
+          const double ll = cta_mvn_logdens(nv, LCH, nv, dv);
+          if (tid == 0) p.LPLs[(size_t)chain * p.na + counter] = ok2 ? ll : nan("");
+        }
+        ++counter;   // every chain owns exactly one replicate j, so the horizon counter advances here
+      }
+      __syncthreads();
+    }
+    (void)sres;
+  }
+}
+
+cudaError_t launch_predict(PredictParams& p, int num_sms, cudaStream_t s, double** scratch_out) {
+  const int nsave = p.R * p.each;
+  int grid = 2 * num_sms;
+  if (grid > nsave) grid = nsave;
+  p.slab = (size_t)2 * p.Kp * p.Kp + (size_t)3 * p.M * p.M + (size_t)2 * p.Kp * p.M + (size_t)(p.M + p.nf) +
+           (size_t)(p.nsv > 0 ? p.nsv : 1) + (size_t)2 * p.M + 8;
+  cudaError_t e = cudaMalloc(scratch_out, p.slab * grid * sizeof(double));
+  if (e != cudaSuccess) return e;
+  p.scratch = *scratch_out;
+  predict_kernel<<<grid, PR_THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace bvb
+
+using namespace bvb;
+
+extern "C" int bvb_predict(bvb_handle* h, int each, int Kp, int M, int R, int n_factors, int ld_logvar, int factor,
+                           const double* X_T_plus_1, const double* PHI, const double* U, const double* facload,
+                           const double* logvar_T, const int* ahead, int n_ahead, const double* sv_mu,
+                           const double* sv_phi, const double* sv_sigma, const int* sv_indicator, int n_sv, int LPL,
+                           const double* Y_obs, int LPL_subset, const int* VoI, int n_voi, int simulate_predictive,
+                           const double* z_logvar, const double* z_pred, double* LPL_draws, double* PL_univariate_draws,
+                           double* LPL_sub_draws, double* predictions) {
+  if (!h) return BVB_ERR_ARG;
+  h->err_code = 0; h->err_step = 5; h->err_sweep = 0; h->err_eq = 0; h->err_msg[0] = 0;
+  if (each <= 0 || Kp <= 0 || M <= 0 || R < 0 || Kp < M || !X_T_plus_1 || !PHI || !logvar_T || !ahead || n_ahead <= 0 ||
+      (factor ? (n_factors > 0 && !facload) : (M > 1 && !U)) || (n_sv > 0 && (!sv_mu || !sv_phi || !sv_sigma || !sv_indicator)) ||
+      (LPL && (!Y_obs || !LPL_draws || !PL_univariate_draws)) || (LPL && LPL_subset && (!VoI || n_voi <= 0 || !LPL_sub_draws)) ||
+      (simulate_predictive && !predictions) || ld_logvar < M + (factor ? n_factors : 0)) {
+    bvb_set_error(h, BVB_ERR_ARG, "bvb_predict: invalid argument");
+    return BVB_ERR_ARG;
+  }
+  if (R == 0) return BVB_OK;
+  int max_ahead = 0;
+  for (int i = 0; i < n_ahead; ++i) {
+    if (ahead[i] <= 0 || (i > 0 && ahead[i] <= ahead[i - 1])) { bvb_set_error(h, BVB_ERR_ARG, "bvb_predict: ahead must be sorted and positive"); return BVB_ERR_ARG; }
+    max_ahead = ahead[i];
+  }
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t d = sizeof(double);
+  const int nsave = R * each;
+  const size_t nU = (size_t)M * (M - 1) / 2;
+  std::vector<void*> allocs;
+  auto fin = [&](int rc) { for (void* q : allocs) cudaFree(q); return rc; };
+#define PR_TRY(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { bvb_set_error(h, BVB_ERR_CUDA, "bvb_predict: %s", cudaGetErrorString(_e)); return fin(BVB_ERR_CUDA); } } while (0)
+  auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+    *dst = nullptr;
+    if (!src || bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    allocs.push_back(*dst);
+    return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s);
+  };
+  PredictParams p{};
+  p.each = each; p.Kp = Kp; p.M = M; p.R = R; p.nf = factor ? n_factors : 0; p.nU = (int)nU; p.ld_lv = ld_logvar; p.na = n_ahead;
+  p.max_ahead = max_ahead; p.nsv = n_sv; p.factor = factor ? 1 : 0; p.lpl = LPL ? 1 : 0; p.lpl_sub = (LPL && LPL_subset) ? 1 : 0;
+  p.nvoi = n_voi; p.simulate = simulate_predictive ? 1 : 0; p.p = Kp / M; p.seed = h->seed;
+  PR_TRY(up(X_T_plus_1, d * Kp, (void**)&p.x));
+  PR_TRY(up(PHI, d * Kp * M * R, (void**)&p.PHI));
+  if (!factor) PR_TRY(up(U, d * nU * R, (void**)&p.U));
+  if (factor && n_factors > 0) PR_TRY(up(facload, d * M * n_factors * R, (void**)&p.facload));
+  PR_TRY(up(logvar_T, d * ld_logvar * R, (void**)&p.logvar_T));
+  PR_TRY(up(ahead, sizeof(int) * n_ahead, (void**)&p.ahead));
+  if (n_sv > 0) {
+    PR_TRY(up(sv_mu, d * n_sv * R, (void**)&p.sv_mu));
+    PR_TRY(up(sv_phi, d * n_sv * R, (void**)&p.sv_phi));
+    PR_TRY(up(sv_sigma, d * n_sv * R, (void**)&p.sv_sigma));
+    PR_TRY(up(sv_indicator, sizeof(int) * n_sv, (void**)&p.sv_ind));
+    PR_TRY(up(z_logvar, d * (size_t)R * max_ahead * each * n_sv, (void**)&p.z_logvar));
+  }
+  if (LPL) PR_TRY(up(Y_obs, d * n_ahead * M, (void**)&p.Y_obs));
+  if (p.lpl_sub) PR_TRY(up(VoI, sizeof(int) * n_voi, (void**)&p.voi));
+  if (simulate_predictive) PR_TRY(up(z_pred, d * (size_t)R * n_ahead * each * M, (void**)&p.z_pred));
+  auto dalloc = [&](size_t n, double** q) -> cudaError_t {
+    cudaError_t e = cudaMalloc(q, d * (n ? n : 1));
+    if (e == cudaSuccess) allocs.push_back(*q);
+    return e;
+  };
+  if (LPL) { PR_TRY(dalloc((size_t)n_ahead * nsave, &p.LPL)); PR_TRY(dalloc((size_t)n_ahead * M * nsave, &p.PLu)); }
+  if (p.lpl_sub) PR_TRY(dalloc((size_t)n_ahead * nsave, &p.LPLs));
+  if (simulate_predictive) PR_TRY(dalloc((size_t)n_ahead * M * nsave, &p.pred));
+  PR_TRY(cudaMalloc(&p.status, sizeof(int)));
+  allocs.push_back(p.status);
+  PR_TRY(cudaMemsetAsync(p.status, 0, sizeof(int), s));
+  double* scratch = nullptr;
+  PR_TRY(cudaEventRecord(h->ev[0], s));
+  cudaError_t le = launch_predict(p, h->num_sms, s, &scratch);
+  if (scratch) allocs.push_back(scratch);
+  PR_TRY(le);
+  PR_TRY(cudaEventRecord(h->ev[1], s));
+  if (LPL) {
+    PR_TRY(cudaMemcpyAsync(LPL_draws, p.LPL, d * n_ahead * nsave, cudaMemcpyDeviceToHost, s));
+    PR_TRY(cudaMemcpyAsync(PL_univariate_draws, p.PLu, d * n_ahead * M * nsave, cudaMemcpyDeviceToHost, s));
+  }
+  if (p.lpl_sub) PR_TRY(cudaMemcpyAsync(LPL_sub_draws, p.LPLs, d * n_ahead * nsave, cudaMemcpyDeviceToHost, s));
+  if (simulate_predictive) PR_TRY(cudaMemcpyAsync(predictions, p.pred, d * n_ahead * M * nsave, cudaMemcpyDeviceToHost, s));
+  int st = 0;
+  PR_TRY(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PR_TRY(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->last_ms[0] = h->last_ms[1] = h->last_ms[2] = 0; h->last_ms[3] = ms;
+  h->last_launches = 1;
+#undef PR_TRY
+  if (st != 0) {
+    bvb_set_error(h, BVB_ERR_NUMERIC, "chol(): decomposition failed in the predictive covariance of draw %d", (st - 1) % R + 1);
+    return fin(BVB_ERR_NUMERIC);
+  }
+  return fin(BVB_OK);
+}

@@ -251,6 +251,29 @@ int bvb_irf(bvb_handle* h, int Kp, int M, int R, int n_factors, int has_U, int l
             const double* factor_loadings, const double* U_vecs, const double* logvar_t,
             const double* shocks, const double* rotation, double* out);
 
+/* ---- a15: out_of_sample (src/utilities_cpp.cpp:216-393) ---------------------------
+ * Predictive simulation and log predictive likelihoods over R stored draws, `each`
+ * replicates per draw (chain (r, j) writes slice r + j*R, as :352/:364/:376).
+ * PHI Kp x M x R; U n_U x R (cholesky) or facload M x n_factors x R (factor);
+ * logvar_T ld_logvar x R (log-variances at T, idiosyncratic then factor);
+ * ahead[n_ahead] strictly increasing horizons (1-based); sv_mu/phi/sigma n_sv x R
+ * and sv_indicator[n_sv] (0-based rows of logvar_T that follow an SV process);
+ * Y_obs n_ahead x M (LPL only); VoI[n_voi] 0-based (LPL_subset only).
+ * z_logvar / z_pred: NULL = counter-based device normals; otherwise the standard
+ * normals the reference takes from R::norm_rand, C-ordered [R][max_ahead][each][n_sv]
+ * (:325-327) and [R][n_ahead][each][M] (:371-374) - used by the parity tests.
+ * Outputs (column-major, any unused one may be NULL): LPL_draws n_ahead x nsave,
+ * PL_univariate_draws n_ahead x M x nsave, LPL_sub_draws n_ahead x nsave,
+ * predictions n_ahead x M x nsave, nsave = R*each. */
+int bvb_predict(bvb_handle* h, int each, int Kp, int M, int R, int n_factors, int ld_logvar,
+                int factor, const double* X_T_plus_1, const double* PHI, const double* U,
+                const double* facload, const double* logvar_T, const int* ahead, int n_ahead,
+                const double* sv_mu, const double* sv_phi, const double* sv_sigma,
+                const int* sv_indicator, int n_sv, int LPL, const double* Y_obs,
+                int LPL_subset, const int* VoI, int n_voi, int simulate_predictive,
+                const double* z_logvar, const double* z_pred, double* LPL_draws,
+                double* PL_univariate_draws, double* LPL_sub_draws, double* predictions);
+
 /* ---- diagnostics -------------------------------------------------------------
  * Measured FP64 peaks on this device (own micro-kernels, register-resident):
  * out[0] = DMMA m8n8k4 TFLOP/s, out[1] = DFMA TFLOP/s, out[2] = SM clock MHz
