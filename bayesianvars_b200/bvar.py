@@ -613,8 +613,11 @@ def bvar(data, lags=1, draws=1000, burnin=1000, thin=1, prior_intercept=10.0, pr
         bench = time.perf_counter() - t0
         res = dict(smp.out)
         res["fac"] = np.transpose(res["fac"], (1, 0, 2))
+        scpp = prior_sigma["prior_sigma_cpp"]
         res.update(Y=prep["Y"], X=prep["X"], lags=lags, bench=bench, timing=smp.timing(),
-                   prior_phi=prior_phi, prior_sigma=prior_sigma)
+                   prior_phi=prior_phi, prior_sigma=prior_sigma, Yraw=data, intercept=bool(prep["intercept"]),
+                   sigma_type=scpp["type"], heteroscedastic=np.asarray(scpp["sv_heteroscedastic"], bool),
+                   datamat=np.hstack([prep["Y"], prep["X"]]))   # bvar_wrapper.R:489-493
         return res
     finally:
         if own:

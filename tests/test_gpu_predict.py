@@ -127,3 +127,36 @@ def test_argument_errors(handle):
     with pytest.raises(BvbError) as e:
         handle.out_of_sample(**bad)
     assert e.value.code == 3 and "chol()" in str(e.value)
+
+
+@pytest.mark.parametrize("sigma", ["factor", "cholesky"])
+def test_predict_method_on_a_fitted_model(handle, sigma):
+    """predict.bayesianVARs_bvar (R/utility_functions.R:2406-2530) on a homoscedastic fit: the log predictive
+    likelihood draws are deterministic functions of the stored draws -> compare with the oracle."""
+    from bayesianvars_b200 import bvar as bv
+    from bayesianvars_b200.predict import predict, stable_bvar
+    rng = np.random.default_rng(20)
+    M, lags, T = 3, 2, 80
+    data = np.cumsum(0.1 * rng.standard_normal((T + 4, M)), axis=0) * 0.2 + rng.standard_normal((T + 4, M))
+    train, test = data[:-4], data[-4:]
+    pp = bv.specify_prior_phi(M, lags, prior="HS")
+    if sigma == "factor":
+        ps = bv.specify_prior_sigma(M, type="factor", factor_factors=1, factor_heteroskedastic=False)
+    else:
+        ps = bv.specify_prior_sigma(M, type="cholesky", cholesky_heteroscedastic=False)
+    mod = bv.bvar(train, lags=lags, draws=60, burnin=40, prior_phi=pp, prior_sigma=ps, handle=handle, rng=np.random.default_rng(3))
+    out = predict(mod, ahead=[1, 2, 3, 4], LPL=True, Y_obs=test, LPL_VoI=[1, 3], handle=handle)
+    st = stable_bvar(mod, quiet=True)
+    R = st["PHI"].shape[2]
+    assert out["predictions"].shape == (4, M, R) and np.isfinite(out["predictions"]).all()
+    x = np.concatenate([train[-1], train[-2], [1.0]])
+    none = np.zeros((0, R))
+    ref = op.out_of_sample(1, x, st["PHI"], st["U"] if sigma == "cholesky" else None,
+                           st["facload"] if sigma == "factor" else None, st["logvar"][-1], np.array([1, 2, 3, 4]), none, none, none,
+                           np.zeros(0, int), sigma == "factor", True, test, True, np.array([0, 2]), False,
+                           np.zeros((R, 4, 1, 0)), None)
+    np.testing.assert_allclose(out["LPL_draws"], ref["LPL_draws"], rtol=RTOL)
+    np.testing.assert_allclose(out["LPL_sub_draws"], ref["LPL_sub_draws"], rtol=RTOL)
+    mx = ref["LPL_draws"].max(axis=1) - 700
+    np.testing.assert_allclose(out["LPL"], np.log(np.exp(ref["LPL_draws"] - mx[:, None]).mean(axis=1)) + mx, rtol=1e-9)
+    assert out["LPL_univariate"].shape == (4, M) and out["LPL_VoI"].shape == (4,)
