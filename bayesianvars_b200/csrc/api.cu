@@ -281,6 +281,7 @@ void bvb_destroy(bvb_handle* h) {
     scratch_of(h)->huge.release();
     delete scratch_of(h);
   }
+  for (int b = 0; b < 2; ++b) if (h->pin[b]) cudaFreeHost(h->pin[b]);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

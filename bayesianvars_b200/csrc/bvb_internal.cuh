@@ -23,6 +23,8 @@ struct bvb_handle {
   void* gibbs = nullptr;    // owned by gibbs.cu (bvb::Gibbs)
   int rank = 0, world = 1;
   void* comm = nullptr;     // ncclComm_t
+  void* pin[2] = {nullptr, nullptr};   // pinned staging of the stored draws, kept across bvb_gibbs_init calls
+  size_t pin_bytes[2] = {0, 0};
 };
 
 void bvb_set_error(bvb_handle* h, int code, const char* fmt, ...);

@@ -11,6 +11,7 @@
 // The sweep counter lives in device memory so the captured graph is replayed
 // unchanged; all Philox streams are keyed by (purpose, element, sweep).
 #include "gibbs.cuh"
+#include <chrono>
 #include "chol.cuh"
 
 #include <nccl.h>
@@ -391,7 +392,6 @@ static void gibbs_free(bvb_handle* h) {
   if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
   if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
   for (int b = 0; b < 2; ++b) if (G->ev_pin[b]) cudaEventDestroy(G->ev_pin[b]);
-  for (int b = 0; b < 2; ++b) if (G->pinned[b]) cudaFreeHost(G->pinned[b]);
   delete G;
   h->gibbs = nullptr;
 }
@@ -429,7 +429,17 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   }
   GB_TRY(cudaSetDevice(h->device));
   GB_TRY(cudaDeviceSynchronize());
+  const bool init_prof = getenv("BVB_INIT_PROF") != nullptr;
+  auto init_t0 = std::chrono::steady_clock::now();
+  auto init_mark = [&](const char* what) {
+    if (!init_prof) return;
+    cudaStreamSynchronize(h->stream);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bvb init] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - init_t0).count());
+    init_t0 = t;
+  };
   gibbs_free(h);
+  init_mark("free previous chain");
   gbuf_stream() = h->stream;
   Gibbs* Gp = new (std::nothrow) Gibbs();
   if (!Gp) return BVB_ERR_CUDA;
@@ -488,6 +498,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     }
   }
 
+  init_mark("data + pair products");
   // ---- prior variances V_prior (Kp x M): V_i on the lag rows, priorIntercept on the last row
   const int n = K * M;
   std::vector<double> Vprior((size_t)std::max(Kp * M, 1), 1.0), V_init((size_t)std::max(n, 1), 1.0);
@@ -575,6 +586,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
                    pp->SSVS_s_a, pp->SSVS_s_b, pp->SSVS_p, V_prep_small, loc1, loc2, V_init, STREAM_PHI_HYPER);
   if (rc) return rc;
 
+  init_mark("prior block");
   // ---- Sigma_t block (factor SV)
   FsvDev& F = G.fsv;
   F.M = M; F.T = T; F.r = r;
@@ -732,6 +744,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     }
   }
 
+  init_mark("Sigma block");
   // ---- stored-draw ring: one slot = everything bvar_cpp.cpp:751-836 copies per stored sweep
   GibbsStore& st = G.store;
   st.burnin = burnin; st.thin = thin; st.nseg = 0;
@@ -782,14 +795,24 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   const int fac_cols = G.tvp_all ? T : 1;
   G.off_fac = off;      if (r > 0) add_seg(st, G.fac.p + (G.tvp_all ? 0 : (size_t)(T - 1) * r), r, fac_cols, r, 0, off);
   st.slot_doubles = off;
-  // ring sized for one bvb_gibbs_run chunk (<= 256 sweeps) but bounded to 1 GiB
-  size_t slots = 256;
+  // ring sized for one sub-chunk of bvb_gibbs_run (<= 32 sweeps) and bounded to 1 GiB
+  size_t slots = 32;
   while (slots > 1 && slots * off * sizeof(double) > ((size_t)1 << 30)) slots /= 2;
   st.ring_slots = (int)slots;
   GB_TRY(G.ring.ensure(slots * off));
   st.ring = G.ring.p;
   st.first_slot = G.first_slot.p;
-  for (int b = 0; b < 2; ++b) GB_TRY(cudaMallocHost(&G.pinned[b], slots * off * sizeof(double)));
+  for (int b = 0; b < 2; ++b) {
+    const size_t need = slots * off * sizeof(double);
+    if (h->pin_bytes[b] < need) {
+      if (h->pin[b]) cudaFreeHost(h->pin[b]);
+      h->pin[b] = nullptr; h->pin_bytes[b] = 0;
+      GB_TRY(cudaMallocHost(&h->pin[b], need));
+      h->pin_bytes[b] = need;
+    }
+    G.pinned[b] = static_cast<double*>(h->pin[b]);
+  }
+  init_mark("ring + pinned staging");
   for (auto& e : G.ev) GB_TRY(cudaEventCreate(&e));
   GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
   GB_TRY(cudaEventCreate(&G.ev_chunk[1]));
@@ -856,7 +879,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   // launched eagerly with CUDA events between the phases (warm caches).
   const bool time_last = (todo >= 8);
   if (time_last) todo -= 1;
-  // Sub-chunks of <= 64 sweeps (and <= ring_slots stored draws).  The D2H copy of a
+  // Sub-chunks of <= 32 sweeps (and <= ring_slots stored draws).  The D2H copy of a
   // sub-chunk's stored draws is queued behind its sweeps; the host scatters the
   // PREVIOUS sub-chunk into the caller's arrays while the GPU runs the next one.
   GB_TRY(cudaEventRecord(G.ev_chunk[0], s));
@@ -872,7 +895,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   int flip = 0;
   while (ran < todo) {
     const int stored_before = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
-    int nsw = std::min(todo - ran, 64);
+    int nsw = std::min(todo - ran, 32);
     while (nsw > 1 && (std::max(0, G.rep + nsw - G.burnin) / G.thin) - stored_before > G.store.ring_slots) --nsw;
     GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
     for (int i = 0; i < nsw; ++i) GB_TRY(cudaGraphLaunch(G.graph_exec, s));
