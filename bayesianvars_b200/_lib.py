@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libbvb.so"
+LIB_PATH = Path(__import__("os").environ.get("BVB_LIB", PKG / "libbvb.so"))   # BVB_LIB: A/B builds of the same ABI
 
 BVB_OK = 0
 ERR_NAMES = {1: "BVB_ERR_CUDA", 2: "BVB_ERR_ARG", 3: "BVB_ERR_NUMERIC", 4: "BVB_ERR_UNSUPPORTED", 5: "BVB_ERR_COMM"}

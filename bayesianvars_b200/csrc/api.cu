@@ -263,7 +263,13 @@ int bvb_create(bvb_handle** out, int device, uint64_t seed) {
     delete h;
     return BVB_ERR_UNSUPPORTED;
   }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BVB_ERR_CUDA; }
+  {
+    // highest priority: the side branch of the sweep graph (hyper-parameters) runs at the lowest, so the critical
+    // path's blocks are placed first when both are pending
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return BVB_ERR_CUDA; }
+  }
   for (auto& e : h->ev) cudaEventCreate(&e);
   h->scratch = new (std::nothrow) Scratch();
   *out = h;
@@ -369,17 +375,21 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
   static long long* d_prof = nullptr;
   if (getenv("BVB_K2_DEBUG")) k2.debug_mode = atoi(getenv("BVB_K2_DEBUG"));
   if (getenv("BVB_K2_PROF")) {
-    if (!d_prof) cudaMalloc(&d_prof, 8 * sizeof(long long));
-    cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), s);
+    if (!d_prof) cudaMalloc(&d_prof, 64 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 64 * sizeof(long long), s);
     k2.prof = d_prof;
   }
   BVB_CUDA_TRY(launch_k2(k2, s));
   BVB_CUDA_TRY(cudaEventRecord(h->ev[3], s));
   if (k2.prof) {
-    long long hp[8];
+    long long hp[64];
     cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
-    fprintf(stderr, "K2 phase cycles (CTA 0): gemm=%lld fill=%lld factor=%lld invert=%lld trsm=%lld writeback=%lld backsolve=%lld\n", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+    fprintf(stderr, "K2 phase cycles (CTA 0) v1: gemm fill factor invert trsm writeback backsolve | v2: partA wait-panel trsm wb+partB fill - backsolve:\n  %lld %lld %lld %lld %lld %lld %lld\n", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+    fprintf(stderr, "K2 v2 panel warp: factor+invert %lld  wait#1 %lld  wait#2 %lld  wait#3 %lld  wait#4 %lld\n", hp[24], hp[25], hp[26], hp[27], hp[28]);
+    fprintf(stderr, "K2 gemm cycles per block column:");
+    for (int k = 0; k < (Kp + 31) / 32 && k < 16; ++k) fprintf(stderr, " %lld", hp[8 + k]);
+    fprintf(stderr, "\n");
   }
   BVB_CUDA_TRY(cudaMemcpyAsync(PHI_out, ws.PHI.p, szKM, cudaMemcpyDeviceToHost, s));
   BVB_CUDA_TRY(cudaMemcpyAsync(ws.h_status.data(), ws.status.p, sizeof(int) * M, cudaMemcpyDeviceToHost, s));

@@ -345,13 +345,27 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   } else {
     mark(1); mark(2); mark(3); mark(4);
   }
-  // ---- 2) hyper-parameters of the prior on PHI
-  if (G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING) {
-    GB_TRY(launch_hyper_update(G.hphi.d, h->seed, sw, G.burnin, s));
-    const size_t nk = (size_t)K * M;
-    gibbs_scatter_V_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(G.Vprior.p, G.hphi.d.V_i, K, Kp, M);
+  // ---- 2) hyper-parameters of the prior on PHI.  They only read PHI and write V_prior / their own state, which
+  // nothing below touches, so outside the timing pass they run on a side stream next to resid + Sigma_t (a fork /
+  // join in the captured graph); the join is before the store.
+  static const bool dbg_skip_hyper = getenv("BVB_DEBUG_SKIP_HYPER") != nullptr;   // timing experiments only (wrong draws)
+  const bool has_hyper = !dbg_skip_hyper && G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING;
+  static const bool dbg_fork_timing = getenv("BVB_DEBUG_FORK_TIMING") != nullptr;
+  const bool forked = has_hyper && (!timing || dbg_fork_timing) && G.side != nullptr;
+  {
+    cudaStream_t hs = forked ? G.side : s;
+    if (forked) {
+      GB_TRY(cudaEventRecord(G.ev_fork, s));
+      GB_TRY(cudaStreamWaitEvent(hs, G.ev_fork, 0));
+    }
+    if (has_hyper) {
+      GB_TRY(launch_hyper_update(G.hphi.d, h->seed, sw, G.burnin, hs));
+      const size_t nk = (size_t)K * M;
+      gibbs_scatter_V_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, hs>>>(G.Vprior.p, G.hphi.d.V_i, K, Kp, M);
+    }
+    if (forked) GB_TRY(cudaEventRecord(G.ev_join, hs));
+    if (timing) cudaEventRecord(ev[5], hs);
   }
-  mark(5);
   // ---- resid = Y - X PHI
   if (Kp > 0) {
     const int tiles = ((T + 7) / 8) * ((M + 7) / 8);
@@ -376,6 +390,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));
   }
   mark(7);
+  if (forked) GB_TRY(cudaStreamWaitEvent(s, G.ev_join, 0));
   // ---- store + advance
   gibbs_store_kernel<<<64, 256, 0, s>>>(G.store, sw, G.nstored.p);
   gibbs_advance_kernel<<<1, 1, 0, s>>>(G.sweep.p);
@@ -389,6 +404,9 @@ static void gibbs_free(bvb_handle* h) {
   Gibbs* G = static_cast<Gibbs*>(h->gibbs);
   if (G->graph_exec) cudaGraphExecDestroy(G->graph_exec);
   for (auto& e : G->ev) if (e) cudaEventDestroy(e);
+  if (G->ev_fork) cudaEventDestroy(G->ev_fork);
+  if (G->ev_join) cudaEventDestroy(G->ev_join);
+  if (G->side) cudaStreamDestroy(G->side);
   if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
   if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
   for (int b = 0; b < 2; ++b) if (G->ev_pin[b]) cudaEventDestroy(G->ev_pin[b]);
@@ -814,6 +832,13 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   }
   init_mark("ring + pinned staging");
   for (auto& e : G.ev) GB_TRY(cudaEventCreate(&e));
+  if (!getenv("BVB_NO_FORK")) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    GB_TRY(cudaStreamCreateWithPriority(&G.side, cudaStreamNonBlocking, lo));
+    GB_TRY(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
+    GB_TRY(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
+  }
   GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
   GB_TRY(cudaEventCreate(&G.ev_chunk[1]));
   for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_pin[b], cudaEventDisableTiming));
@@ -898,7 +923,11 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     int nsw = std::min(todo - ran, 32);
     while (nsw > 1 && (std::max(0, G.rep + nsw - G.burnin) / G.thin) - stored_before > G.store.ring_slots) --nsw;
     GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
-    for (int i = 0; i < nsw; ++i) GB_TRY(cudaGraphLaunch(G.graph_exec, s));
+    static const bool dbg_eager = getenv("BVB_DEBUG_EAGER") != nullptr;
+    for (int i = 0; i < nsw; ++i) {
+      if (dbg_eager) { int rc = enqueue_sweep(h, G); if (rc) return rc; }
+      else GB_TRY(cudaGraphLaunch(G.graph_exec, s));
+    }
     G.rep += nsw;
     ran += nsw;
     const int stored_after = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     }
     cp_async_wait<0>();
     __syncthreads();   // ring is dead from here on; its memory becomes the panel
+    if (prof && k < 16) p.prof[8 + k] += clock64() - tprev;
     K2_TICK(0);
 
     // ---- A: panel = A_orig - acc, straight from the accumulator fragments -------
@@ -429,6 +430,458 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_solve_kernel(const K2Par
   if (tid == 0 && anybad) atomicCAS(&p.status[eq], 0, -1);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K2 v2 - the same factorisation, warp-specialised with one block column of LOOK-AHEAD.
+//
+// In v1 the 32x32 diagonal factor + inverse (one warp, a 32-pivot dependent chain) runs while
+// the other 15 warps wait, and every warp alternates between issuing cp.async and DMMA in
+// lock step, so neither the L2 stream (latency-bound at ~24 B/clk/SM) nor the tensor pipe is
+// kept busy.  Here the 16 warps have three roles:
+//   warp 0      panel warp : factorises + inverts the diagonal block k
+//   warps 1..15 GEMM warps : part A = update of block k+1 with the columns [0, 32k) that do not
+//                            depend on block k (overlaps the panel warp; streamed from L2 through
+//                            a cp.async ring whose loads are issued in the shadow of the DMMAs,
+//                            a quarter of the next chunk after every k-step), part B = the 32
+//                            columns of block k read straight from the shared-memory panel,
+//                            TRSM, write-back, fill.
+// (Measured dead ends: one dedicated loader warp sustains only ~4 B/clk of cp.async - the
+// per-warp limit on copies in flight - and 1-D TMA bulk copies of these 1-3 KB columns were
+// ~15% slower than 16-byte cp.async spread over all warps.)
+// The panel and the ring no longer alias; the ring gets a per-block row stride and as many
+// stages as fit (2..4).  Arithmetic and summation order are those of v1.
+// ---------------------------------------------------------------------------------------------
+constexpr int K2V_G = K2_NWARPS - 1;          // GEMM warps
+constexpr int K2V_GT = K2V_G * 32;            // GEMM threads
+constexpr int K2V_MAXS = 4;                   // ring stages
+
+__host__ __device__ inline int k2v_rs_local(int R) { return ((R + 15) / 16) * 16 + 4; }
+__host__ __device__ inline size_t k2v_misc_doubles(int n) {
+  return (size_t)K2_NB * K2_LS + (size_t)(k2_nblocks(n) * K2_NB + 32) + 32 + 64 + 32 + (size_t)(n + 3) / 2 + 8;
+}
+// smem: [panel 32 x RS] [ring >= 32 x RS] [linvT] [ysol] [sblk] [colbuf] [rsbuf] [colbase ints]
+size_t k2v_smem_bytes(int n, size_t* ring_doubles) {
+  const size_t rs = k2_row_stride(n);
+  const size_t misc = k2v_misc_doubles(n);
+  const size_t cap = (size_t)227 * 1024 / sizeof(double);
+  size_t ring = (size_t)K2V_MAXS * K2_BKC * rs;
+  if ((size_t)K2_NB * rs + ring + misc > cap) ring = cap - misc - (size_t)K2_NB * rs;
+  if (ring_doubles) *ring_doubles = ring;
+  return ((size_t)K2_NB * rs + ring + misc) * sizeof(double);
+}
+bool k2v_fits(int n) {
+  const size_t rs = k2_row_stride(n);
+  return ((size_t)2 * K2_NB * rs + k2v_misc_doubles(n)) * sizeof(double) <= (size_t)227 * 1024 && n + 1 <= K2V_G * K2_MAXQ * 8;
+}
+
+__device__ __forceinline__ void k2v_bar_gemm() { asm volatile("bar.sync 1, %0;" ::"n"(K2V_GT) : "memory"); }
+__device__ __forceinline__ void k2v_bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+// stage MMA for GEMM warp g owning the m8 tiles g + K2V_G q.  NQ is a template parameter on purpose (see v1).
+template <int NQ>
+__device__ __forceinline__ void k2v_stage_mma(double (&acc)[K2_MAXQ][4][2], const double* sb, int RS, int g, int fr, int fk) {
+#pragma unroll
+  for (int ks = 0; ks < K2_BKC / 4; ++ks) {
+    const double* col = sb + (4 * ks + fk) * RS + fr;
+    double b[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = col[8 * nt];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double a = col[8 * (g + K2V_G * q)];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], a, b[nt]);
+    }
+  }
+}
+// (every call site inlines all four bodies, and the kernel is instruction-cache bound between phases: keep the
+// number of call sites at two - the part A chunk loop and the part B loop)
+__device__ __forceinline__ void k2v_stage(int nq, double (&acc)[K2_MAXQ][4][2], const double* sb, int RS, int g, int fr, int fk) {
+  switch (nq) {
+    case 1: k2v_stage_mma<1>(acc, sb, RS, g, fr, fk); break;
+    case 2: k2v_stage_mma<2>(acc, sb, RS, g, fr, fk); break;
+    case 3: k2v_stage_mma<3>(acc, sb, RS, g, fr, fk); break;
+    case 4: k2v_stage_mma<4>(acc, sb, RS, g, fr, fk); break;
+    default: break;
+  }
+}
+
+__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Params p, double* __restrict__ linv_ws, int ring_doubles) {
+  constexpr int NWARPS = K2_NWARPS, MAXQ = K2_MAXQ, NTHREADS = K2_NWARPS * 32;
+  extern __shared__ __align__(16) double smem[];
+  const int n = p.n, n1 = n + 1;
+  const int RS = k2_row_stride(n);
+  const int nbk = k2_nblocks(n);
+  double* panel = smem;                                   // [32][RS]
+  double* ring = smem + (size_t)K2_NB * RS;               // [ring_doubles]
+  double* linvT = ring + ring_doubles;                    // [32][36]
+  double* ysol = linvT + K2_NB * K2_LS;                   // [nbk*32 + 32]
+  double* sblk = ysol + nbk * K2_NB + 32;                 // [32]
+  double* colbuf = sblk + 32;                             // [2][32]
+  double* rsbuf = colbuf + 64;                            // [32]
+  int* colb = reinterpret_cast<int*>(rsbuf + 32);         // [n]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int eq = blockIdx.x;
+  double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
+  double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
+  int fail = 0;  // meaningful on warp 0 only
+  // phase profile (cycles seen by GEMM warp 1 lane 0 of CTA 0): 0 part A, 1 wait for the panel warp, 2 trsm,
+  // 3 writeback + part B, 4 fill, 6 back-solve
+  long long tprev = 0;
+  const bool prof = (p.prof != nullptr) && eq == 0 && tid == 32;
+  if (prof) tprev = clock64();
+#define K2V_TICK(slot) do { if (prof) { const long long tn = clock64(); p.prof[slot] += tn - tprev; tprev = tn; } } while (0)
+
+  for (int i = tid; i < n; i += NTHREADS) colb[i] = p.colbase[i];
+  __syncthreads();
+
+  auto blk_w = [&](int kk) { return min(K2_NB, n - kk * K2_NB); };
+  auto blk_R = [&](int kk) { return K2_NB + n1 - (kk * K2_NB + blk_w(kk)); };
+
+  // All roles execute the same sequence of CTA-wide barriers: two for block 0, then per block column
+  //   #1 Linv(k) ready + part A(k+1) done   #2 TRSM(k) done   #3 panel(k) dead, prefetch landed   #4 panel(k+1) filled
+  if (warp == 0) {
+    // =================================== panel warp ===================================
+    k2v_bar_all();   // block 0 prefetch landed
+    k2v_bar_all();   // panel(0) filled
+    const bool profp = (p.prof != nullptr) && eq == 0 && tid == 0;
+    long long tp = profp ? clock64() : 0;
+#define K2V_PTICK(slot) do { if (profp) { const long long tn = clock64(); p.prof[slot] += tn - tp; tp = tn; } } while (0)
+    for (int k = 0; k < nbk; ++k) {
+      const int c0 = k * K2_NB;
+      const int w = min(K2_NB, n - c0);
+      const int R = K2_NB + n1 - (c0 + w);
+#ifdef K2V_COMPACT_PANEL   // 60 KB less code but 1.6x slower under contention with the GEMM warps (measured): off
+      // ---- C: factor the 32x32 diagonal block and invert it.  Lane i holds row i in registers as a window that
+      // slides with the column (a[u] = D[i][c+u]), so the column loop is NOT unrolled: the fully unrolled form is
+      // ~75 KB of straight-line code that evicts the GEMM warps' loop from the instruction cache once per block.
+      // Same arithmetic and order as v1; window slots of columns >= 32 hold don't-care values.
+      double a[K2_NB];
+#pragma unroll
+      for (int u = 0; u < K2_NB; ++u) a[u] = (u <= lane) ? panel[u * RS + lane] : 0.0;
+      double x = __shfl_sync(0xffffffffu, a[0], 0);
+      if (!(x > 0.0) || !isfinite(x)) { if (fail == 0) fail = c0 + 1; x = 1.0; }
+      double rs = rsqrt(x);
+#pragma unroll 1
+      for (int c = 0; c < K2_NB; ++c) {
+        const double l = (lane >= c) ? a[0] * rs : 0.0;   // lane c: x * rsqrt(x) = sqrt(x)
+        panel[c * RS + lane] = l;                          // final column c (zeros above the diagonal)
+        if (lane == c) rsbuf[c] = rs;
+        __syncwarp();
+        const double* colc = panel + c * RS + c;           // colc[u] = L[c+u][c]
+        a[0] = fma(-l, colc[1], a[1]);                     // next column first: its pivot heads the dependent chain
+        if (c + 1 < K2_NB) {
+          x = __shfl_sync(0xffffffffu, a[0], (c + 1) & 31);
+          if (!(x > 0.0) || !isfinite(x)) { if (fail == 0) fail = c0 + c + 2; x = 1.0; }
+          rs = rsqrt(x);
+        }
+#pragma unroll
+        for (int u = 2; u < K2_NB; ++u) a[u - 1] = fma(-l, colc[u], a[u]);
+        a[K2_NB - 1] = 0.0;
+      }
+      __syncwarp();
+      // lane j solves L x = e_j -> column j of Linv (right-looking substitution, same sliding window)
+      double sacc[K2_NB];
+#pragma unroll
+      for (int u = 0; u < K2_NB; ++u) sacc[u] = (u == lane) ? 1.0 : 0.0;
+#pragma unroll 1
+      for (int kk = 0; kk < K2_NB; ++kk) {
+        const double xk = (kk >= lane) ? sacc[0] * rsbuf[kk] : 0.0;
+        linvT[lane * K2_LS + kk] = xk;                                            // linvT[c'=j][c=i] = Linv[i][j]
+        lws[(size_t)k * (K2_NB * K2_NB) + kk * K2_NB + lane] = xk;                // ws[k][c'=i][c=j] = Linv[i][j]
+        const double* colk = panel + kk * RS + kk;
+#pragma unroll
+        for (int u = 1; u < K2_NB; ++u) sacc[u - 1] = fma(-colk[u], xk, sacc[u]);
+        sacc[K2_NB - 1] = 0.0;
+      }
+#else
+      double a[K2_NB];
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) a[c] = (c <= lane) ? panel[c * RS + lane] : 0.0;
+      double x = __shfl_sync(0xffffffffu, a[0], 0);
+      if (!(x > 0.0) || !isfinite(x)) { if (fail == 0) fail = c0 + 1; x = 1.0; }
+      double rs = rsqrt(x);
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) {
+        const double l = (lane >= c) ? a[c] * rs : 0.0;   // lane c: x * rsqrt(x) = sqrt(x)
+        a[c] = l;
+        double* cb = colbuf + (c & 1) * 32;
+        cb[lane] = l;
+        if (lane == c) rsbuf[c] = rs;
+        __syncwarp();
+        if (c + 1 < K2_NB) {
+          a[c + 1] = fma(-l, cb[c + 1], a[c + 1]);
+          x = __shfl_sync(0xffffffffu, a[c + 1], c + 1);
+          if (!(x > 0.0) || !isfinite(x)) { if (fail == 0) fail = c0 + c + 2; x = 1.0; }
+          rs = rsqrt(x);
+        }
+#pragma unroll
+        for (int c2 = c + 2; c2 < K2_NB; ++c2) a[c2] = fma(-l, cb[c2], a[c2]);
+      }
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) panel[c * RS + lane] = a[c];
+      __syncwarp();
+      double sacc[K2_NB];
+#pragma unroll
+      for (int i = 0; i < K2_NB; ++i) sacc[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int kk = 0; kk < K2_NB; ++kk) {
+        const double xk = (kk >= lane) ? sacc[kk] * rsbuf[kk] : 0.0;
+        sacc[kk] = xk;
+#pragma unroll
+        for (int i = kk + 1; i < K2_NB; ++i) sacc[i] = fma(-panel[kk * RS + i], xk, sacc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < K2_NB; ++i) {
+        linvT[lane * K2_LS + i] = sacc[i];
+        lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = sacc[i];
+      }
+#endif
+      K2V_PTICK(24);
+      k2v_bar_all();   // #1
+      K2V_PTICK(25);
+      k2v_bar_all();   // #2
+      K2V_PTICK(26);
+      ysol[c0 + lane] = (lane < w) ? panel[lane * RS + (R - 1)] : 0.0;            // forward-solved rhs (row n of L)
+      k2v_bar_all();   // #3
+      K2V_PTICK(27);
+      k2v_bar_all();   // #4
+      K2V_PTICK(28);
+    }
+  } else {
+    // =================================== GEMM warps ===================================
+    const int fr = lane >> 2, fk = lane & 3;
+    const int g = warp - 1;                                  // 0..14, owns m8 tiles g + 15 q
+    const int tg = tid - 32;                                 // 0..479
+    // original entries of a FULL block column kk (rows c0.., 32 columns) -> ring as [c][RSl]
+    auto prefetch_block = [&](int kk) {
+      const int c0 = kk * K2_NB, R = blk_R(kk), RSl = k2v_rs_local(R);
+      const int col = tg / 15, r0 = tg - 15 * col;
+      const double* src = om + colb[c0 + col] + c0;
+      double* dst = ring + (size_t)col * RSl;
+      const int npair = (R + 1) >> 1;
+      for (int pr = r0; pr < npair; pr += 15) cp_async16(dst + 2 * pr, src + 2 * pr);
+    };
+    double acc[MAXQ][4][2];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+    // panel(kk) = A_orig - acc   (`pre`: A_orig comes from the prefetched copy in the ring)
+    auto fill_panel = [&](int kk, bool pre) {
+      const int c0 = kk * K2_NB, w = blk_w(kk), kb_end = c0 + w, R = blk_R(kk), RSl = k2v_rs_local(R);
+      const int mtiles = (R + 7) >> 3;
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q) {
+        const int mt = g + K2V_G * q;
+        const int li = 8 * mt + fr;
+        if (mt < mtiles && li < R) {
+          const int gr = li < K2_NB ? (li < w ? c0 + li : -1) : kb_end + li - K2_NB;
+          double orig[4][2];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * nt + 2 * fk + e;
+              double v;
+              if (c < w) v = (gr >= c0 + c) ? (pre ? ring[(size_t)c * RSl + li] : om[colb[c0 + c] + gr]) : 0.0;
+              else v = (li == c) ? 1.0 : 0.0;
+              orig[nt][e] = v;
+            }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * nt + 2 * fk + e;
+              double v = orig[nt][e];
+              if (c < w && gr >= c0 + c) v -= acc[q][nt][e];
+              panel[c * RS + li] = v;
+            }
+        }
+      }
+    };
+
+    // k = -1 is a virtual iteration: nothing to factor yet, it only prefetches and fills block 0 (acc = 0), so
+    // fill_panel / prefetch_block have a single call site each.
+    for (int k = -1; k < nbk; ++k) {
+      const bool real = (k >= 0);
+      const int c0 = k * K2_NB;
+      const int w = min(K2_NB, n - c0);
+      const int kb_end = c0 + w;
+      const int R = K2_NB + n1 - kb_end;
+      const int mtiles = real ? (R + 7) >> 3 : 0;
+      auto grow = [&](int li) -> int { return li < K2_NB ? (li < w ? c0 + li : -1) : kb_end + li - K2_NB; };
+      // next block column
+      const bool have_next = (k + 1 < nbk);
+      const int c0n = c0 + K2_NB;
+      const int wn = have_next ? min(K2_NB, n - c0n) : 0;
+      const int Rn = have_next ? K2_NB + n1 - (c0n + wn) : 0;
+      const bool fulln = (wn == K2_NB);
+      const int mtn = (Rn + 7) >> 3;
+      const int nqn = (have_next && mtn > g) ? (mtn - g + K2V_G - 1) / K2V_G : 0;
+      const int RSl = k2v_rs_local(Rn);
+      const int stage_d = K2_BKC * RSl;
+
+      if (have_next && real) {
+        // ---- part A of block k+1: columns [0, 32k), while warp 0 factorises block k
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+        const int nchunks = c0 / K2_BKC;
+        int S = ring_doubles / stage_d;
+        S = S > K2V_MAXS ? K2V_MAXS : S;                     // >= 2 by construction of the ring
+        const int lcol = tg / 30, lr0 = tg - 30 * lcol;      // loader: 16 columns x 30 threads
+        const int npair = (Rn + 1) >> 1;
+        auto load_chunk = [&](int st, int ch) {
+          double* sdst = ring + (size_t)st * stage_d + lcol * RSl;
+          const double* src = om + colb[ch * K2_BKC + lcol];
+          if (fulln) {
+            for (int pr = lr0; pr < npair; pr += 30) cp_async16(sdst + 2 * pr, src + c0n + 2 * pr);
+          } else {
+            for (int li = lr0; li < Rn; li += 30) {
+              const int gg = li < K2_NB ? (li < wn ? c0n + li : -1) : c0n + wn + li - K2_NB;
+              if (gg >= 0) cp_async8(sdst + li, src + gg);
+              else sdst[li] = 0.0;
+            }
+          }
+        };
+        for (int s = 0; s < S - 1; ++s) {
+          if (s < nchunks) load_chunk(s, s);
+          cp_async_commit();
+        }
+        for (int ch = 0; ch < nchunks; ++ch) {
+          if (S == 2) cp_async_wait<0>(); else if (S == 3) cp_async_wait<1>(); else cp_async_wait<2>();
+          k2v_bar_gemm();                                    // chunk ch landed everywhere; chunk ch-1's stage is free
+          {
+            const int nxt = ch + S - 1;
+            if (nxt < nchunks) load_chunk(nxt % S, nxt);      // issued before the MMAs: the copies are latency-bound
+            cp_async_commit();
+          }
+          k2v_stage(nqn, acc, ring + (size_t)(ch % S) * stage_d, RSl, g, fr, fk);
+        }
+        cp_async_wait<0>();
+        k2v_bar_gemm();                                      // ring is free
+      }
+      if (prof && real && k + 1 < 16) p.prof[8 + k + 1] += clock64() - tprev;
+      K2V_TICK(0);
+      if (have_next && fulln) prefetch_block(k + 1);
+      cp_async_commit();
+      if (real) k2v_bar_all();                               // #1: Linv ready, part A done
+      K2V_TICK(1);
+
+      // ---- D: sub-diagonal rows  X = A * Linv^T  (DMMA, skipping the zero triangle)
+      for (int mt = 4 + g; mt < mtiles; mt += K2V_G) {
+        double t[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) t[nt][0] = t[nt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < K2_NB / 4; ++ks) {
+          const double av = panel[(4 * ks + fk) * RS + 8 * mt + fr];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if (4 * ks <= 8 * nt + 7) {
+              const double bv = linvT[(4 * ks + fk) * K2_LS + 8 * nt + fr];
+              dmma884(t[nt][0], t[nt][1], av, bv);
+            }
+          }
+        }
+        __syncwarp();
+        const int li = 8 * mt + fr;
+        if (li < R) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) panel[(8 * nt + 2 * fk + e) * RS + li] = t[nt][e];
+        }
+      }
+      if (real) k2v_bar_all();                               // #2: panel(k) = L[:, block k]
+      K2V_TICK(2);
+
+      // ---- E: write the factorised panel back; part B of block k+1 straight from the panel
+      for (int c = g; real && c < w; c += K2V_G) {
+        double* dst = om + colb[c0 + c];
+        const double* src = panel + c * RS;
+        for (int li = lane; li < R; li += 32) {
+          const int gg = grow(li);
+          if (gg >= c0 + c) dst[gg] = src[li];
+        }
+      }
+      cp_async_wait<0>();                                    // the prefetched A_orig(k+1) has landed
+      if (have_next && real && !fulln) {
+        // partial (last) block: its rows are not contiguous in the panel.  Gather the two chunks of block k through
+        // the row map into the ring (nothing was prefetched for a partial block, the ring is free)
+        const int lcol = tg / 30, lr0 = tg - 30 * lcol;      // 16 columns x 30 threads
+        for (int hh = 0; hh < 2; ++hh) {
+          double* sdst = ring + (size_t)hh * stage_d + lcol * RSl;
+          const double* src = panel + (size_t)(hh * K2_BKC + lcol) * RS;
+          for (int li = lr0; li < Rn; li += 30) {
+            // block k+1 local row -> global row -> panel(k) local row (panel(k) is a full block: row = 32 + g - c0n)
+            const int gg = li < K2_NB ? (li < wn ? c0n + li : -1) : c0n + wn + li - K2_NB;
+            sdst[li] = (gg >= 0) ? src[K2_NB + gg - c0n] : 0.0;
+          }
+        }
+        k2v_bar_gemm();
+      }
+      if (have_next && real) {
+        // part B: the 32 columns of block k.  Full block: the rows of block k+1 are the panel rows 32.. and its own
+        // 32 rows are the B operand; partial block: the gathered copy in the ring.
+        const double* pb = fulln ? panel + K2_NB : ring;
+        const int pbRS = fulln ? RS : RSl;
+        for (int hh = 0; hh < 2; ++hh) k2v_stage(nqn, acc, pb + (size_t)hh * K2_BKC * pbRS, pbRS, g, fr, fk);
+      }
+      k2v_bar_all();                                         // #3: panel(k) dead, prefetch visible
+      K2V_TICK(3);
+      if (have_next) fill_panel(k + 1, fulln);
+      k2v_bar_all();                                         // #4: panel(k+1) ready
+      K2V_TICK(4);
+    }
+  }
+
+  if (p.mode == 1) {   // factor only: the caller solves later (triangular algorithm)
+    if (tid == 0 && fail) atomicCAS(&p.status[eq], 0, fail);
+    return;
+  }
+  // ---- back-solve  L^T phi = y + z ------------------------------------------------
+  for (int i = tid; i < n; i += NTHREADS) ysol[i] += p.z[(size_t)eq * p.ldz + i];
+  __syncthreads();
+  for (int k = nbk - 1; k >= 0; --k) {
+    const int c0 = k * K2_NB;
+    const int w = min(K2_NB, n - c0);
+    const int kb_end = c0 + w;
+    for (int c = warp; c < K2_NB; c += NWARPS) {
+      double s = 0.0;
+      if (c < w) {
+        const double* colp = om + colb[c0 + c];
+        for (int i = kb_end + lane; i < n; i += 32) s = fma(colp[i], ysol[i], s);
+        s = warp_sum(s);
+      }
+      if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+      double xv0 = 0.0, xv1 = 0.0;
+#pragma unroll
+      for (int cp = 0; cp < K2_NB; cp += 2) {
+        xv0 = fma(wsk[cp * K2_NB + lane], sblk[cp], xv0);
+        xv1 = fma(wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
+      }
+      if (lane < w) ysol[c0 + lane] = xv0 + xv1;
+    }
+    __syncthreads();
+  }
+  bool bad = false;
+  for (int i = tid; i < n; i += NTHREADS) {
+    const double v = ysol[i];
+    p.phi[(size_t)eq * p.ldphi + i] = v;
+    bad |= !isfinite(v);
+  }
+  const int anybad = __syncthreads_or(bad ? 1 : 0);
+  K2V_TICK(6);
+  if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
+}
+
 static double* g_linv_ws = nullptr;
 static size_t g_linv_ws_bytes = 0;
 
@@ -440,6 +893,15 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     cudaError_t e = cudaMalloc(&g_linv_ws, need);
     if (e != cudaSuccess) { g_linv_ws = nullptr; g_linv_ws_bytes = 0; return e; }
     g_linv_ws_bytes = need;
+  }
+  static const bool force_v1 = getenv("BVB_K2_V1") != nullptr;
+  if (!force_v1 && k2v_fits(p.n)) {
+    size_t ring = 0;
+    const size_t smem2 = k2v_smem_bytes(p.n, &ring);
+    cudaError_t e2 = cudaFuncSetAttribute(k2_cholsolve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return e2;
+    k2_cholsolve_v2<<<p.M, K2_NWARPS * 32, smem2, s>>>(p, g_linv_ws, (int)ring);
+    return cudaGetLastError();
   }
   const size_t smem = k2_smem_bytes(p.n);
   if (smem > 227 * 1024 || p.n + 1 > K2_NWARPS * K2_MAXQ * 8) return cudaErrorInvalidValue;
