@@ -207,6 +207,7 @@ def specify_prior_phi(M, lags=1, prior="HS", priormean=0.0, PHI_tol=1e-18, DL_a=
         cpp["SSVS_tau0"] = np.resize(np.asarray(SSVS_c0, float), n)
         cpp["SSVS_tau1"] = np.resize(np.asarray(SSVS_c1, float), n)
         gs["SSVS_semiautomatic"] = bool(SSVS_semiautomatic)
+        gs["SSVS_c0"], gs["SSVS_c1"] = cpp["SSVS_tau0"].copy(), cpp["SSVS_tau1"].copy()   # unscaled (prepare() rescales)
     elif prior == "normal":
         cpp["V_i"] = np.resize(np.asarray(normal_sds, float) ** 2, n)
     return dict(prior_phi_cpp=cpp, general_settings=gs)
@@ -335,6 +336,33 @@ def shard_draws(R, rank, world):
 
 
 # --------------------------------------------------------------------------- bvar()
+def MP_sigma_sq(Y, p):
+    """Residual variances of univariate AR(p) fits (R/aux_functions.R:63-79)."""
+    Y = np.asarray(Y, float)
+    T, M = Y.shape
+    out = np.empty(M)
+    for i in range(M):
+        y = Y[:, i]
+        Xi = np.column_stack([y[p - l:T - l] for l in range(1, p + 1)])
+        yi = y[p:]
+        phi = np.linalg.lstsq(Xi, yi, rcond=None)[0]
+        out[i] = ((yi - Xi @ phi) ** 2).sum() / (T - p)
+    return out
+
+
+def MP_V_prior_prep(sigma_sq, K, M, intercept):
+    """Minnesota prior variances up to the lambdas (R/aux_functions.R:81-108); K counts the intercept row."""
+    V = np.zeros((K, M))
+    for i in range(M):
+        for j in range(K):            # j + 1 is R's 1-based regressor index
+            if j == K - 1 and intercept:
+                V[j, i] = sigma_sq[i]
+            else:
+                r = j // M + 1
+                V[j, i] = 1.0 / r ** 2 if (j - i) % M == 0 else sigma_sq[i] / (r ** 2 * sigma_sq[j % M])
+    return V.reshape(-1, order="F")
+
+
 def _embed(Y_tmp, lags, intercept):
     """R's embed(Y_tmp, lags+1)[, -(1:M)] (+ ones column): R/bvar_wrapper.R:228-235."""
     Traw, M = Y_tmp.shape
@@ -380,6 +408,23 @@ def prepare(data, lags, prior_intercept, prior_phi, prior_sigma, startvals=None,
             sv["PHI"] = V_post @ (P0 @ PHI0 + X.T @ Y)
         else:
             sv["PHI"] = np.zeros((0, M))
+    # "empirical" prior settings (R/bvar_wrapper.R:321-344); written into the prior object like bvar() does with its copy
+    ppc = prior_phi["prior_phi_cpp"]
+    if ppc["prior"] == "SSVS" and gs.get("SSVS_semiautomatic", False) and K > 0:
+        P0 = np.eye(Kp) / 1e3
+        V_post_flat = np.linalg.inv(P0 + X.T @ X)
+        PHI_flat = V_post_flat @ (P0 @ PHI0 + X.T @ Y)
+        E = Y - X @ PHI_flat
+        S_post = np.eye(M) + E.T @ E + (PHI_flat - PHI0).T @ P0 @ (PHI_flat - PHI0)
+        Sigma_flat = S_post / (M + 2 + Tobs - M - 1)
+        sigma_phi = np.sqrt(np.outer(np.diag(Sigma_flat), np.diag(V_post_flat)).reshape(-1))   # diag(Sigma %x% V), equation-major
+        sigma_phi = sigma_phi[i_vec != 0]
+        if sigma_phi.size != lags * M * M:
+            raise ValueError(f"{sigma_phi.size} length(sigma_phi)!= lags*M^2")
+        ppc["SSVS_tau0"] = gs["SSVS_c0"] * sigma_phi
+        ppc["SSVS_tau1"] = gs["SSVS_c1"] * sigma_phi
+    elif ppc["prior"] == "HMP" and np.size(ppc.get("V_i_prep", ())) != Kp * M:
+        ppc["V_i_prep"] = MP_V_prior_prep(MP_sigma_sq(Y_tmp, 6), Kp, M, intercept > 0)
     if pcpp["type"] == "cholesky":
         if "U" not in sv:
             # R/bvar_wrapper.R:310-319: Sigma_flat from the flat conjugate posterior, U = L_flat

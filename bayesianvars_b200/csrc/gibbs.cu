@@ -897,6 +897,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     size_t nn = 0;
     cudaGraphGetNodes(graph, nullptr, &nn);
     G.launches_per_sweep = (int)nn;
+    if (const char* dot = getenv("BVB_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, 0);
     GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
     cudaGraphDestroy(graph);
   }
@@ -992,7 +993,8 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   for (int j = 0; j < G.M; ++j) {
     if (eqs[j] != 0) {
       h->err_step = 1; h->err_eq = j + 1; h->err_sweep = G.rep;
-      bvb_set_error(h, BVB_ERR_NUMERIC, "sample_PHI_factor() failed in run <= %i: univariate_regression_update() failed in %ith eqation: chol(): decomposition failed", G.rep, j + 1);
+      bvb_set_error(h, BVB_ERR_NUMERIC, "%s failed in run <= %i: univariate_regression_update() failed in %ith eqation: chol(): decomposition failed",
+                    G.sigma_type == BVB_SIGMA_CHOLESKY ? "sample_PHI()" : "sample_PHI_factor()", G.rep, j + 1);   // bvar_cpp.cpp:512, :522
       return BVB_ERR_NUMERIC;
     }
   }
