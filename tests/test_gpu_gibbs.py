@@ -237,3 +237,18 @@ def test_expert_huge_chain_matches_standard_chain(handle):
                 x, y = a.out["PHI"][i, j], other[i, j]
                 se = np.sqrt(batch_means_var(x, 30) + batch_means_var(y, 30))
                 assert abs(x.mean() - y.mean()) < 5 * se + 0.02, (i, j, x.mean(), y.mean(), se)
+
+
+@pytest.mark.parametrize("prior", ["HMP", "SSVS", "DL", "R2D2", "NG"])
+def test_cholesky_structure_with_default_phi_priors_runs(handle, prior):
+    """bvar() with the package defaults for each PHI prior on the cholesky structure: the empirical prior
+    settings (Minnesota V_i_prep, semiautomatic SSVS) come from prepare() as in R/bvar_wrapper.R:321-344."""
+    M, p, T = 6, 2, 150
+    Y, A = sim_var(M, p, T)
+    pp = B.specify_prior_phi(M, p, prior)
+    ps = B.specify_prior_sigma(M, type="cholesky")
+    res = B.bvar(Y, lags=p, draws=300, burnin=200, prior_phi=pp, prior_sigma=ps, handle=handle, rng=np.random.default_rng(5))
+    assert np.isfinite(res["PHI"]).all() and np.isfinite(res["U"]).all() and (res["V_prior"] > 0).all()
+    own = np.array([res["PHI"][j, j].mean() for j in range(M)])
+    if prior != "SSVS":   # the default spike (0.01 x s.e.) starts every coefficient excluded and mixes slowly
+        assert np.all(np.abs(own - 0.5) < 0.35), own      # the simulated own-lag coefficient is 0.5
