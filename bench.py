@@ -225,7 +225,8 @@ def run_cuda(args):
     prof = ROOT / "profiles" / "ncu_summary.json"
     if prof.exists():
         try:
-            traffic = json.loads(prof.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+            summ = json.loads(prof.read_text())
+            traffic = (summ.get(dom) or summ.get(dom + "_v2") or {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = dict(bound="tensor", kernel=dom, achieved=kern[dom]["achieved"], peak=peak["dmma_tflops"], unit="TFLOP/s",
