@@ -170,7 +170,7 @@ static int phi_draw_factor_huge(bvb_handle* h, int T, int Kp, int M, int r, cons
                                 const double* logvar_idi, const double* V_prior, const double* PHI0,
                                 const double* facload, const double* fac, const double* z, const double* delta,
                                 double* PHI_out) {
-  if (k2_smem_bytes(T) > 227 * 1024) {
+  if (!k2_supported(T)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor(huge): T=%d exceeds the in-SM panel of the T x T solve", T);
     return BVB_ERR_UNSUPPORTED;
   }
@@ -330,7 +330,7 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
     return BVB_ERR_ARG;
   }
   if (huge) return phi_draw_factor_huge(h, T, Kp, M, r, X, Y, logvar_idi, V_prior, PHI0, facload, fac, z, delta, PHI_out);
-  if (k2_smem_bytes(Kp) > 227 * 1024) {
+  if (!k2_supported(Kp)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_factor: Kp=%d exceeds the in-SM panel of the standard path; use huge", Kp);
     return BVB_ERR_UNSUPPORTED;
   }
@@ -423,7 +423,7 @@ int bvb_phi_draw_cholesky(bvb_handle* h, int T, int Kp, int M, const double* PHI
     bvb_set_error(h, BVB_ERR_ARG, "bvb_phi_draw_cholesky: invalid argument");
     return BVB_ERR_ARG;
   }
-  if (k2_smem_bytes(Kp) > 227 * 1024) {
+  if (!k2_supported(Kp)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_phi_draw_cholesky: Kp=%d exceeds the in-SM panel", Kp);
     return BVB_ERR_UNSUPPORTED;
   }
@@ -506,7 +506,7 @@ int bvb_sample_u(bvb_handle* h, int T, int M, const double* resid, const double*
   const int nu = M > 1 ? M - 1 : 1, ne = M - 1;
   const size_t tm = (size_t)T * M, nU = (size_t)M * (M - 1) / 2, d = sizeof(double);
   make_pair_geom(ws.gu, T, nu);
-  if (k2_smem_bytes(nu) > 227 * 1024) {
+  if (!k2_supported(nu)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "bvb_sample_u: M=%d exceeds the in-SM panel", M);
     return BVB_ERR_UNSUPPORTED;
   }

@@ -92,6 +92,7 @@ struct K2Params {
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s);
 cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s);
 size_t k2_smem_bytes(int n);
+bool k2_supported(int n);   // systems of size n can be factorised (single-tile or row-tiled panel)
 
 // prep kernels
 cudaError_t launch_build_A(double* A, const double* X, const int2* pairs, int T, int Tp, int n,

@@ -437,11 +437,11 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   const int r = chol ? 0 : ps->factor_factors;
   if (r < 0 || r > FSV_RMAX) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "factor_factors=%d outside [0,%d]", r, FSV_RMAX); return BVB_ERR_UNSUPPORTED; }
   const bool use_huge = huge && !chol && K > 0;   // 'expert_huge=TRUE' is ignored for the cholesky structure (R/bvar_wrapper.R:389-391)
-  if (use_huge && k2_smem_bytes(T) > 227 * 1024) {
+  if (use_huge && !k2_supported(T)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "expert_huge: T=%d exceeds the in-SM panel of the T x T solve", T);
     return BVB_ERR_UNSUPPORTED;
   }
-  if (Kp > 0 && !use_huge && k2_smem_bytes(Kp) > 227 * 1024) {
+  if (Kp > 0 && !use_huge && !k2_supported(Kp)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "Kp=%d exceeds the in-SM panel of the standard path; use expert_huge", Kp);
     return BVB_ERR_UNSUPPORTED;
   }
@@ -744,7 +744,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     G.hU.d.always_active = 1;
     if (nU > 0) {
       const int nu = M - 1;
-      if (k2_smem_bytes(nu) > 227 * 1024) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "M=%d exceeds the in-SM panel of sample_U", M); return BVB_ERR_UNSUPPORTED; }
+      if (!k2_supported(nu)) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "M=%d exceeds the in-SM panel of sample_U", M); return BVB_ERR_UNSUPPORTED; }
       make_pair_geom(G.geomU, T, nu);
       if ((rc = upload(h, G.lutu, G.geomU.lut.data(), G.geomU.nArows))) return rc;
       if ((rc = upload(h, G.pairsu, G.geomU.pairs.data(), G.geomU.nArows))) return rc;

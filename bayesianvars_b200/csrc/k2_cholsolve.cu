@@ -38,14 +38,29 @@ __host__ __device__ inline int k2_row_stride(int n) {
 }
 __host__ __device__ inline int k2_nblocks(int n) { return (n + K2_NB - 1) / K2_NB; }
 
+// v1 processes a block column in ROW TILES of the 32 block rows + at most `rt` sub-diagonal rows, so the
+// shared-memory panel no longer has to hold a whole column of the system: rt = n + 1 (one tile, the whole
+// column) whenever that fits, else K2_RT.  Row stride of the staged columns for a given rt:
+constexpr int K2_RT = 320;   // sub-diagonal rows per tile of a system too tall for one tile (multiple of 16)
+__host__ __device__ inline int k2_tile_rows(int n, int rt) { return (n + 1 < K2_NB + rt) ? n + 1 : K2_NB + rt; }
+__host__ __device__ inline int k2_row_stride_rt(int n, int rt) { return k2_row_stride(k2_tile_rows(n, rt) - 1); }
+
 // smem: [stage ring | panel (aliased)] [linvT] [ysol] [sblk] [colbuf 2x32] [rsbuf 32] [colbase ints]
-size_t k2_smem_bytes(int n) {
-  size_t rs = k2_row_stride(n);
+static size_t k2_smem_bytes_rt(int n, int rt) {
+  size_t rs = k2_row_stride_rt(n, rt);
   size_t ring = (size_t)K2_STAGES * K2_BKC * rs, panel = (size_t)K2_NB * rs;
   size_t d = (ring > panel ? ring : panel) + (size_t)K2_NB * K2_LS + (size_t)(k2_nblocks(n) * K2_NB + 32) +
              32 + 64 + 32 + (size_t)(n + 3) / 2 + 8;
   return d * sizeof(double);
 }
+size_t k2_smem_bytes(int n) { return k2_smem_bytes_rt(n, n + 1); }
+// largest sub-row tile for a system of size n (0: not even the tiled form fits - n beyond ~9000)
+int k2_pick_rt(int n) {
+  if (k2_smem_bytes_rt(n, n + 1) <= (size_t)227 * 1024 && n + 1 <= K2_NWARPS * K2_MAXQ * 8) return n + 1;
+  if (k2_smem_bytes_rt(n, K2_RT) <= (size_t)227 * 1024) return K2_RT;
+  return 0;
+}
+bool k2_supported(int n) { return n > 0 && k2_pick_rt(n) > 0; }
 
 
 // DMMA work of one pipeline stage for a warp that owns NQ m8 tiles (mt = warp +
@@ -63,7 +78,7 @@ __device__ __forceinline__ void k2_stage_mma(double (&acc)[K2_MAXQ][4][2], const
     for (int nt = 0; nt < 4; ++nt) b[nt] = col[8 * nt];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const double a = col[8 * (warp + K2_NWARPS * q)];
+      const double a = col[8 * (warp + K2_NWARPS * q)];   // `warp` = first tile of this warp (mt0 + warp id)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], a, b[nt]);
     }
@@ -72,11 +87,11 @@ __device__ __forceinline__ void k2_stage_mma(double (&acc)[K2_MAXQ][4][2], const
 template <>
 __device__ __forceinline__ void k2_stage_mma<0>(double (&)[K2_MAXQ][4][2], const double*, int, int, int, int) {}
 
-__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws) {
+__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws, int rt) {
   constexpr int NWARPS = K2_NWARPS, MAXQ = K2_MAXQ, NTHREADS = K2_NWARPS * 32;
   extern __shared__ __align__(16) double smem[];
   const int n = p.n, n1 = n + 1;
-  const int RS = k2_row_stride(n);
+  const int RS = k2_row_stride_rt(n, rt);
   const int nbk = k2_nblocks(n);
   const size_t ring_d = (size_t)K2_STAGES * K2_BKC * RS, panel_d = (size_t)K2_NB * RS;
   double* stage = smem;                                   // [STAGES][BKC][RS]
@@ -107,12 +122,18 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     const int c0 = k * K2_NB;
     const int w = min(K2_NB, n - c0);
     const int kb_end = c0 + w;
-    const int nsub = n1 - kb_end;
-    const int R = K2_NB + nsub;
+    const int nsub_all = n1 - kb_end;
     const bool full = (w == K2_NB);
+   // row tiles: the 32 block rows + sub-diagonal rows [sub0, sub0 + nsub); tile 0 also factorises the diagonal block
+   for (int sub0 = 0; sub0 < nsub_all; sub0 += rt) {
+    const bool first = (sub0 == 0);
+    const int nsub = min(rt, nsub_all - sub0);
+    const int R = K2_NB + nsub;
     const int mtiles = (R + 7) >> 3;
+    const int mt0 = first ? 0 : 4;                       // later tiles only produce their sub-diagonal rows
+    const int li0 = first ? 0 : K2_NB;
     // local row -> global row (or -1 for the virtual identity rows of a partial block)
-    auto grow = [&](int li) -> int { return li < K2_NB ? (li < w ? c0 + li : -1) : kb_end + li - K2_NB; };
+    auto grow = [&](int li) -> int { return li < K2_NB ? (li < w ? c0 + li : -1) : kb_end + sub0 + li - K2_NB; };
 
     // ---- B: left-looking update with the already-factorised columns -----------
     // chunk = 16 columns of L, one column per warp in the loader (coalesced 16-byte cp.async)
@@ -120,9 +141,13 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     auto load_chunk = [&](int st, int ch) {
       double* sdst = stage + (size_t)st * (K2_BKC * RS) + warp * RS;
       const double* src = om + colb[ch * K2_BKC + warp];
-      if (full) {
+      if (full && first) {
         const int npair = (R + 1) >> 1;
         for (int pr = lane; pr < npair; pr += 32) cp_async16(sdst + 2 * pr, src + c0 + 2 * pr);
+      } else if (full) {
+        if (lane < K2_NB / 2) cp_async16(sdst + 2 * lane, src + c0 + 2 * lane);
+        const int npair = (nsub + 1) >> 1;
+        for (int pr = lane; pr < npair; pr += 32) cp_async16(sdst + K2_NB + 2 * pr, src + kb_end + sub0 + 2 * pr);
       } else {
         for (int li = lane; li < R; li += 32) {
           const int g = grow(li);
@@ -132,7 +157,8 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       }
     };
 
-    const int nq = (mtiles > warp) ? (mtiles - warp + NWARPS - 1) / NWARPS : 0;
+    const int wt = mt0 + warp;                           // first tile of this warp
+    const int nq = (mtiles > wt) ? (mtiles - wt + NWARPS - 1) / NWARPS : 0;
     double acc[MAXQ][4][2];
 #pragma unroll
     for (int q = 0; q < MAXQ; ++q)
@@ -155,10 +181,10 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       const double* sb = stage + (size_t)(ch % K2_STAGES) * (K2_BKC * RS);
       if (p.debug_mode == 1) continue;
       switch (nq) {   // warp-uniform: number of m8 tiles this warp owns in this block column
-        case 1: k2_stage_mma<1>(acc, sb, RS, warp, fr, fk); break;
-        case 2: k2_stage_mma<2>(acc, sb, RS, warp, fr, fk); break;
-        case 3: k2_stage_mma<3>(acc, sb, RS, warp, fr, fk); break;
-        case 4: k2_stage_mma<4>(acc, sb, RS, warp, fr, fk); break;
+        case 1: k2_stage_mma<1>(acc, sb, RS, wt, fr, fk); break;
+        case 2: k2_stage_mma<2>(acc, sb, RS, wt, fr, fk); break;
+        case 3: k2_stage_mma<3>(acc, sb, RS, wt, fr, fk); break;
+        case 4: k2_stage_mma<4>(acc, sb, RS, wt, fr, fk); break;
         default: break;
       }
     }
@@ -170,7 +196,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     // ---- A: panel = A_orig - acc, straight from the accumulator fragments -------
 #pragma unroll
     for (int q = 0; q < MAXQ; ++q) {
-      const int mt = warp + NWARPS * q;
+      const int mt = wt + NWARPS * q;
       const int li = 8 * mt + fr;
       if (mt < mtiles && li < R) {
         const int g = grow(li);
@@ -204,7 +230,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     // is scaled, column c+1 is brought up to date and the NEXT pivot's
     // shuffle + rsqrt chain is started before the remaining (independent) rank-1
     // updates are issued, so the 32-pivot dependent chain is ~(shfl + rsqrt + mul + fma).
-    if (warp == 0) {
+    if (warp == 0 && first) {
       double a[K2_NB];
 #pragma unroll
       for (int c = 0; c < K2_NB; ++c) a[c] = (c <= lane) ? panel[c * RS + lane] : 0.0;
@@ -286,14 +312,15 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     for (int c = warp; c < w; c += NWARPS) {
       double* dst = om + colb[c0 + c];
       const double* src = panel + c * RS;
-      for (int li = lane; li < R; li += 32) {
+      for (int li = li0 + lane; li < R; li += 32) {
         const int g = grow(li);
         if (g >= c0 + c) dst[g] = src[li];
       }
     }
-    if (tid < K2_NB) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;
+    if (tid < K2_NB && sub0 + nsub == nsub_all) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;   // rhs row: last tile
     __syncthreads();
     K2_TICK(5);
+   }
   }
 
   if (p.mode == 1) {   // factor only: the caller solves later (triangular algorithm)
@@ -903,11 +930,12 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     k2_cholsolve_v2<<<p.M, K2_NWARPS * 32, smem2, s>>>(p, g_linv_ws, (int)ring);
     return cudaGetLastError();
   }
-  const size_t smem = k2_smem_bytes(p.n);
-  if (smem > 227 * 1024 || p.n + 1 > K2_NWARPS * K2_MAXQ * 8) return cudaErrorInvalidValue;
+  const int rt = k2_pick_rt(p.n);
+  if (rt == 0) return cudaErrorInvalidValue;
+  const size_t smem = k2_smem_bytes_rt(p.n, rt);
   cudaError_t e = cudaFuncSetAttribute(k2_cholsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k2_cholsolve<<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws);
+  k2_cholsolve<<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws, rt);
   return cudaGetLastError();
 }
 

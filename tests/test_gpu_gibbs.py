@@ -252,3 +252,16 @@ def test_cholesky_structure_with_default_phi_priors_runs(handle, prior):
     own = np.array([res["PHI"][j, j].mean() for j in range(M)])
     if prior != "SSVS":   # the default spike (0.01 x s.e.) starts every coefficient excluded and mixes slowly
         assert np.all(np.abs(own - 0.5) < 0.35), own      # the simulated own-lag coefficient is 0.5
+
+
+@pytest.mark.parametrize("sigma", ["factor", "cholesky"])
+def test_tall_systems_beyond_one_panel(handle, sigma):
+    """Kp = 521: the per-equation system no longer fits one shared-memory panel (row-tiled factorisation)."""
+    M, p, T = 26, 20, 560
+    rng = np.random.default_rng(4)
+    Y = rng.standard_normal((T, M))
+    pp = B.specify_prior_phi(M, p, "HS")
+    ps = B.specify_prior_sigma(M, type=sigma) if sigma == "cholesky" else B.specify_prior_sigma(M, factor_factors=1)
+    res = B.bvar(Y, lags=p, draws=6, burnin=4, prior_phi=pp, prior_sigma=ps, handle=handle, rng=np.random.default_rng(5))
+    assert res["PHI"].shape == (M * p + 1, M, 6) and np.isfinite(res["PHI"]).all()
+    assert np.abs(res["PHI"][:-1]).max() < 1.0        # white noise data: shrunk towards zero

@@ -32,6 +32,9 @@ def run(handle, d, **kw):
     (5, 13, 150, 1, "dl"),     # Kp = 66: 3 column blocks, last one partial (2 cols)
     (16, 4, 120, 3, "dl"),     # Kp = 65
     (50, 4, 300, 6, "dl"),     # config 2
+    (26, 16, 450, 1, "dl"),    # Kp = 417: too tall for the look-ahead kernel (v1, one row tile)
+    (26, 20, 560, 1, "dl"),    # Kp = 521: the panel no longer fits - two row tiles per block column
+    (12, 70, 900, 1, "dl"),    # Kp = 841: three row tiles, last block column partial
 ])
 def test_matches_oracle(handle, M, p, T, r, prior):
     d = phi_draw_inputs(M, p, T, r, seed=100 + M + p, prior=prior)
@@ -108,7 +111,8 @@ def test_cholesky_failure_is_reported(handle):
 
 
 # ------------------------------------------------------------------ expert_huge branch
-@pytest.mark.parametrize("M,p,T,r", [(3, 2, 5, 0), (8, 6, 30, 1), (12, 10, 60, 2), (20, 8, 100, 1), (30, 14, 150, 1)])
+@pytest.mark.parametrize("M,p,T,r", [(3, 2, 5, 0), (8, 6, 30, 1), (12, 10, 60, 2), (20, 8, 100, 1), (30, 14, 150, 1),
+                                     (20, 32, 530, 1)])   # T x T = 530: row-tiled factorisation
 def test_huge_branch_matches_oracle(handle, M, p, T, r):
     """sample_coefficients.cpp:40-52 (Bhattacharya et al.): Kp normals for u, then T normals for
     delta, per equation.  Kp = p*M + 1 > T in most of these shapes."""
