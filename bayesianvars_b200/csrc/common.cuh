@@ -32,8 +32,16 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 16-byte cp.async, `.cg` (bypass L1).  tools/microbench/stream_vs_dmma.cu: a saturated `.cg` stream (42 B/clk/SM)
+// halves the rate of DMMA warps whose operands come through LDS, `.ca` streams 76 B/clk/SM and costs LDS less, an
+// aligned TMA bulk stream costs it nothing - but at the 4-9 B/clk/SM K1 and K2 actually stream, `.ca` measured 1-4%
+// SLOWER than `.cg` in both kernels (-DBVB_CP16_CA to repeat the experiment).
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+#ifdef BVB_CP16_CA
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
+#endif
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem));
