@@ -87,11 +87,21 @@ __device__ __forceinline__ void k2_stage_mma(double (&acc)[K2_MAXQ][4][2], const
 template <>
 __device__ __forceinline__ void k2_stage_mma<0>(double (&)[K2_MAXQ][4][2], const double*, int, int, int, int) {}
 
-__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws, int rt) {
+// Cluster form (CL = true): a thread-block cluster of `csize` CTAs shares one equation.  Every block column is cut into
+// csize row tiles (the owner of block column k - rank k mod csize - takes the 32 block rows + the first tile and
+// factorises the diagonal block); the inverse of the diagonal block travels through global memory (lws), two cluster
+// barriers per block column order "Linv ready" and "column written back".  All reads of data another CTA wrote bypass
+// L1 (cp.async.cg, ld.global.cg).  Used when equations x csize <= SMs (multi-GPU shards, small M): the per-equation
+// latency chain is what bounds K2, and this is the only way more SMs shorten it.
+__device__ __forceinline__ void k2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+template <bool CL>
+__global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params p, double* __restrict__ linv_ws, int rt, int csize) {
   constexpr int NWARPS = K2_NWARPS, MAXQ = K2_MAXQ, NTHREADS = K2_NWARPS * 32;
   extern __shared__ __align__(16) double smem[];
   const int n = p.n, n1 = n + 1;
-  const int RS = k2_row_stride_rt(n, rt);
+  const int RS = k2_row_stride_rt(n, rt);   // (cluster form: rt = rows of the tallest tile, computed by the launcher)
   const int nbk = k2_nblocks(n);
   const size_t ring_d = (size_t)K2_STAGES * K2_BKC * RS, panel_d = (size_t)K2_NB * RS;
   double* stage = smem;                                   // [STAGES][BKC][RS]
@@ -105,13 +115,14 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  const int eq = blockIdx.x;
+  const int eq = CL ? blockIdx.x / csize : blockIdx.x;
+  const int crank = CL ? blockIdx.x % csize : 0;          // rank in the cluster (cluster dims = (csize, 1, 1))
   double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
   double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
   int fail = 0;  // meaningful on warp 0 only
   // optional phase profile (cycles, CTA 0 / thread 0): gemm, fill, factor, invert, trsm, writeback, backsolve
   long long tprev = 0;
-  const bool prof = (p.prof != nullptr) && eq == 0 && tid == 0;
+  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
   if (prof) tprev = clock64();
 #define K2_TICK(slot) do { if (prof) { const long long tn = clock64(); p.prof[slot] += tn - tprev; tprev = tn; } } while (0)
 
@@ -125,9 +136,14 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
     const int nsub_all = n1 - kb_end;
     const bool full = (w == K2_NB);
    // row tiles: the 32 block rows + sub-diagonal rows [sub0, sub0 + nsub); tile 0 also factorises the diagonal block
-   for (int sub0 = 0; sub0 < nsub_all; sub0 += rt) {
+   // cluster form: one tile per CTA and block column, ownership of the diagonal block rotates with k
+   const int rtk = CL ? (((nsub_all + csize - 1) / csize + 7) & ~7) : rt;
+   const int my_tile = CL ? (crank - k % csize + csize) % csize : 0;
+   const bool has_tile = !CL || my_tile * rtk < nsub_all;
+   if (CL && !has_tile) k2_cluster_sync();              // "Linv ready" of a block column this CTA has no rows in
+   for (int sub0 = my_tile * rtk; sub0 < nsub_all; sub0 += (CL ? n1 : rtk)) {
     const bool first = (sub0 == 0);
-    const int nsub = min(rt, nsub_all - sub0);
+    const int nsub = min(rtk, nsub_all - sub0);
     const int R = K2_NB + nsub;
     const int mtiles = (R + 7) >> 3;
     const int mt0 = first ? 0 : 4;                       // later tiles only produce their sub-diagonal rows
@@ -151,8 +167,9 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       } else {
         for (int li = lane; li < R; li += 32) {
           const int g = grow(li);
-          if (g >= 0) cp_async8(sdst + li, src + g);
-          else sdst[li] = 0.0;
+          if (g < 0) sdst[li] = 0.0;
+          else if (CL) sdst[li] = __ldcg(src + g);
+          else cp_async8(sdst + li, src + g);
         }
       }
     };
@@ -207,7 +224,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
           for (int e = 0; e < 2; ++e) {
             const int c = 8 * nt + 2 * fk + e;
             double v;
-            if (c < w) v = (g >= c0 + c) ? om[colb[c0 + c] + g] : 0.0;
+            if (c < w) v = (g >= c0 + c) ? (CL ? __ldcg(om + colb[c0 + c] + g) : om[colb[c0 + c] + g]) : 0.0;
             else v = (li == c) ? 1.0 : 0.0;
             orig[nt][e] = v;
           }
@@ -277,6 +294,13 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
         lws[(size_t)k * (K2_NB * K2_NB) + i * K2_NB + lane] = sacc[i];            // ws[k][c'=i][c=j] = Linv[i][j]
       }
     }
+    if (CL) {
+      k2_cluster_sync();                                 // "Linv ready": the owner's stores to lws are released
+      if (!first) {
+        const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+        for (int t = tid; t < K2_NB * K2_NB; t += NTHREADS) linvT[(t & 31) * K2_LS + (t >> 5)] = __ldcg(wsk + t);
+      }
+    }
     __syncthreads();
     K2_TICK(3);
 
@@ -317,10 +341,19 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
         if (g >= c0 + c) dst[g] = src[li];
       }
     }
-    if (tid < K2_NB && sub0 + nsub == nsub_all) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;   // rhs row: last tile
+    if (!CL && tid < K2_NB && sub0 + nsub == nsub_all) ysol[c0 + tid] = (tid < w) ? panel[tid * RS + (R - 1)] : 0.0;   // rhs row: last tile
     __syncthreads();
     K2_TICK(5);
    }
+   if (CL) k2_cluster_sync();                            // "column written back": the next block column may read it
+  }
+  if (CL) {
+    if (crank != 0) {                                    // the solve is rank 0's; report this CTA's pivots and leave
+      if (tid == 0 && fail) atomicCAS(&p.status[eq], 0, fail);
+      return;
+    }
+    for (int c = tid; c < nbk * K2_NB; c += NTHREADS) ysol[c] = (c < n) ? __ldcg(om + colb[c] + n) : 0.0;   // the rhs row of L
+    __syncthreads();
   }
 
   if (p.mode == 1) {   // factor only: the caller solves later (triangular algorithm)
@@ -338,7 +371,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       double s = 0.0;
       if (c < w) {
         const double* colp = om + colb[c0 + c];
-        for (int i = kb_end + lane; i < n; i += 32) s = fma(colp[i], ysol[i], s);
+        for (int i = kb_end + lane; i < n; i += 32) s = fma(CL ? __ldcg(colp + i) : colp[i], ysol[i], s);
         s = warp_sum(s);
       }
       if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
@@ -349,8 +382,8 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
       double xv0 = 0.0, xv1 = 0.0;
 #pragma unroll
       for (int cp = 0; cp < K2_NB; cp += 2) {
-        xv0 = fma(wsk[cp * K2_NB + lane], sblk[cp], xv0);
-        xv1 = fma(wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
+        xv0 = fma(CL ? __ldcg(wsk + cp * K2_NB + lane) : wsk[cp * K2_NB + lane], sblk[cp], xv0);
+        xv1 = fma(CL ? __ldcg(wsk + (cp + 1) * K2_NB + lane) : wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
       }
       if (lane < w) ysol[c0 + lane] = xv0 + xv1;
     }
@@ -921,6 +954,42 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     if (e != cudaSuccess) { g_linv_ws = nullptr; g_linv_ws_bytes = 0; return e; }
     g_linv_ws_bytes = need;
   }
+  // Thread-block clusters when the equations leave SMs idle: csize = 8 or 4 with M * csize <= SMs.
+  {
+    static int num_sms = 0, forced = -1;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      const char* ev = getenv("BVB_K2_CLUSTER");
+      forced = ev ? atoi(ev) : -1;
+    }
+    int cs = 1;
+    // (measured at n = 401: 13 equations 338 -> 287 us with 8 CTAs, 25 equations 344 -> 305 us with 4; two CTAs per
+    // equation only break even with the look-ahead kernel, so they are not used)
+    for (int c = 8; c >= 4; c >>= 1)
+      if (p.M * c <= num_sms && p.n + 1 - K2_NB >= 64 * c) { cs = c; break; }
+    if (forced == 0 || forced == 1) cs = 1;
+    else if (forced == 2 || forced == 4 || forced == 8) cs = (p.n + 1 - K2_NB >= 8 * forced) ? forced : 1;
+    if (cs > 1) {
+      const int rtc = ((((p.n + 1 - K2_NB) + cs - 1) / cs) + 7) & ~7;      // tallest tile (block column 0)
+      if (k2_smem_bytes_rt(p.n, rtc) <= (size_t)227 * 1024 && K2_NB + rtc <= K2_NWARPS * K2_MAXQ * 8) {
+        const size_t smemc = k2_smem_bytes_rt(p.n, rtc);
+        cudaError_t ec = cudaFuncSetAttribute(k2_cholsolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc);
+        if (ec != cudaSuccess) return ec;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.M * cs));
+        cfg.blockDim = dim3(K2_NWARPS * 32);
+        cfg.dynamicSmemBytes = smemc;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k2_cholsolve<true>, p, g_linv_ws, rtc, cs);
+      }
+    }
+  }
   static const bool force_v1 = getenv("BVB_K2_V1") != nullptr;
   if (!force_v1 && k2v_fits(p.n)) {
     size_t ring = 0;
@@ -933,9 +1002,9 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
   const int rt = k2_pick_rt(p.n);
   if (rt == 0) return cudaErrorInvalidValue;
   const size_t smem = k2_smem_bytes_rt(p.n, rt);
-  cudaError_t e = cudaFuncSetAttribute(k2_cholsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k2_cholsolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k2_cholsolve<<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws, rt);
+  k2_cholsolve<false><<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws, rt, 1);
   return cudaGetLastError();
 }
 

@@ -134,3 +134,13 @@ def test_huge_and_standard_agree_in_mean(handle):
     b = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"], huge=True,
                                  z=z0, delta=np.zeros((70, 10), order="F"))
     assert per_eq_relerr(b, a) < 1e-8
+
+
+@pytest.mark.parametrize("M,p,T", [(13, 31, 450), (25, 16, 430), (6, 9, 120)])
+def test_cluster_form_matches_oracle(handle, M, p, T):
+    """Few equations of a tall system (the shard a rank owns under 4-8 GPU equation sharding): K2 runs one equation
+    per thread-block cluster (8 or 4 CTAs).  (6, 9, 120) is too short for clusters and checks the dispatch."""
+    d = phi_draw_inputs(M, p, T, 1, seed=500 + M)
+    ref = orc.sample_PHI_factor(d["PHI0"], d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"],
+                                d["facload"], d["fac"], False, d["z"])
+    assert per_eq_relerr(run(handle, d), ref) < TOL
