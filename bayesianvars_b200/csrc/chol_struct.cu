@@ -69,28 +69,30 @@ __global__ void __launch_bounds__(256) chol_b_kernel(double* bvec, const double*
 
 // After phi_j is drawn: u = X phi_j_new - X phi_j_old; XPHI[:,j] = X phi_j_new;
 // Q[:, i] -= u U[j,i] (i >= j); and the next equation's r_{j+1}.
-// Block = 32 time points x 8 slices (of the Kp coefficients, then of the M series).
-__global__ void __launch_bounds__(256) chol_upd_kernel(double* Q, double* XPHI, double* rvec, const double* X,
-                                                       const double* PHI, const double* U, const double* d2inv,
-                                                       const double* W, int T, int Tp, int Kp, int M, int j) {
-  __shared__ double sh[8][33];
+// Block = 32 time points x 32 slices (of the Kp coefficients, then of the M series): the kernel sits on the sequential
+// critical path M times per sweep and is pure load latency, so it runs few iterations on many threads.
+constexpr int UPD_SL = 32;
+__global__ void __launch_bounds__(32 * UPD_SL) chol_upd_kernel(double* Q, double* XPHI, double* rvec, const double* X,
+                                                               const double* PHI, const double* U, const double* d2inv,
+                                                               const double* W, int T, int Tp, int Kp, int M, int j) {
+  __shared__ double sh[UPD_SL][33];
   const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int t = blockIdx.x * 32 + tx;
   const double* phi = PHI + (size_t)j * Kp;
   double s = 0.0;
-  if (t < T) for (int k = sl; k < Kp; k += 8) s = fma(X[(size_t)k * T + t], phi[k], s);
+  if (t < T) for (int k = sl; k < Kp; k += UPD_SL) s = fma(X[(size_t)k * T + t], phi[k], s);
   sh[sl][tx] = s;
   __syncthreads();
   double xnew = 0.0;
 #pragma unroll
-  for (int z = 0; z < 8; ++z) xnew += sh[z][tx];
+  for (int z = 0; z < UPD_SL; ++z) xnew += sh[z][tx];
   __syncthreads();
   double u = 0.0;
   if (t < T) u = xnew - XPHI[(size_t)j * T + t];
   // Q update for i >= j (slices split i) and partial q_{j+1}
   double q = 0.0;
   if (t < T) {
-    for (int i = j + sl; i < M; i += 8) {
+    for (int i = j + sl; i < M; i += UPD_SL) {
       const double qv = Q[(size_t)i * T + t] - u * U[(size_t)i * M + j];
       Q[(size_t)i * T + t] = qv;
       if (i >= j + 1 && j + 1 < M) q = fma(U[(size_t)i * M + (j + 1)] * d2inv[(size_t)i * T + t], qv, q);
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(256) chol_upd_kernel(double* Q, double* XPHI, 
     if (j + 1 < M) {
       double qs = 0.0;
 #pragma unroll
-      for (int z = 0; z < 8; ++z) qs += sh[z][tx];
+      for (int z = 0; z < UPD_SL; ++z) qs += sh[z][tx];
       rvec[t] = qs + W[(size_t)(j + 1) * Tp + t] * XPHI[(size_t)(j + 1) * T + t];
     }
   }
@@ -135,7 +137,7 @@ cudaError_t launch_chol_phi(const CholPhiCtx& c, cudaStream_t s) {
     ks.phi = c.PHI + (size_t)j * Kp;
     e = launch_k2_solve(ks, c.bvec, j, 1, s);
     if (e != cudaSuccess) return e;
-    chol_upd_kernel<<<(T + 31) / 32, 256, 0, s>>>(c.Q, c.XPHI, c.rvec, c.X, c.PHI, c.U, c.d2inv, c.W, T, c.Tp, Kp, M, j);
+    chol_upd_kernel<<<(T + 31) / 32, 32 * UPD_SL, 0, s>>>(c.Q, c.XPHI, c.rvec, c.X, c.PHI, c.U, c.d2inv, c.W, T, c.Tp, Kp, M, j);
   }
   return cudaGetLastError();
 }

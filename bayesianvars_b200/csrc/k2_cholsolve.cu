@@ -402,20 +402,30 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
 }
 
 
-// Solve-only companion (triangular algorithm, sample_coefficients.cpp:118-146): the
-// systems were factorised in batch (mode 1); equation `eq`'s right-hand side only
-// becomes known once the previous equations have been drawn.  One CTA:
-//   forward   y_blk = Linv_kk (b_blk - L[blk, 0:c0] y_{0:c0})
-//   backward  phi   = L^-T (y + z)            (same block scheme as above)
+// Solve-only companion (triangular algorithm, sample_coefficients.cpp:118-146): the systems were factorised
+// in batch (mode 1); equation `eq`'s right-hand side only becomes known once the previous equations have been
+// drawn, so this kernel sits on the sequential critical path M times per sweep.  One CTA per solve, bounded by
+// streaming L (2 x 650 KB at n = 401) from L2: both passes walk L by column panels P_k = L[kb_end.., block k]
+// (contiguous runs), prefetched with cp.async two chunks ahead of the dependency chain, which then only touches
+// shared memory:
+//   forward  (right-looking)  y_k = Linv_kk b_k ;  b[rows below] -= P_k y_k
+//   backward                  x_k = Linv_kk^T ( (y+z)_k - P_k^T x[rows below] )
+constexpr int K2S_RC = 176;                    // rows of a staged panel chunk (multiple of 16)
+constexpr int K2S_RCS = K2S_RC + 4;            // its row stride (== 4 mod 16)
+constexpr int K2S_STAGES = 4;                  // three items in flight ahead of the one being consumed
+constexpr int K2S_LS = 33;                     // row stride of a staged Linv block
+
 __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_solve_kernel(const K2Params p, const double* __restrict__ linv_ws,
                                                                      const double* __restrict__ bvec, int eq0) {
   constexpr int NWARPS = K2_NWARPS, NTHREADS = K2_NWARPS * 32;
+  constexpr int STAGE_D = K2_NB * K2S_RCS;                      // >= 32*32: a stage also holds one Linv block
   extern __shared__ __align__(16) double smem[];
   const int n = p.n;
   const int nbk = k2_nblocks(n);
-  double* ysol = smem;                       // [nbk*32 + 32]
-  double* part = ysol + nbk * K2_NB + 32;    // [NWARPS][32]
-  double* sblk = part + NWARPS * K2_NB;      // [32]
+  double* ring = smem;                                          // [STAGES][32][RCS] panel chunks (column-major) / Linv blocks
+  double* xs = ring + (size_t)K2S_STAGES * STAGE_D;             // [nbk*32 + 32] running rhs, then the solution
+  double* ybuf = xs + nbk * K2_NB + 32;                         // [32] y_k of the current block
+  double* sblk = ybuf + 32;                                     // [32] column sums of the backward pass
   int* colb = reinterpret_cast<int*>(sblk + 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int eq = eq0 + blockIdx.x;
@@ -423,73 +433,143 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_solve_kernel(const K2Par
   const double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
   const double* __restrict__ b = bvec + (size_t)blockIdx.x * n;
   for (int i = tid; i < n; i += NTHREADS) colb[i] = p.colbase[i];
-  for (int i = tid; i < nbk * K2_NB + 32; i += NTHREADS) ysol[i] = 0.0;
+  for (int i = tid; i < nbk * K2_NB + 32; i += NTHREADS) xs[i] = (i < n) ? b[i] : 0.0;
   __syncthreads();
-  // ---- forward
-  for (int k = 0; k < nbk; ++k) {
-    const int c0 = k * K2_NB;
-    const int w = min(K2_NB, n - c0);
-    // lanes = the 32 rows of the block, warps split the c0 previous columns
-    double s = 0.0;
-    if (lane < w) {
-      for (int c = warp; c < c0; c += NWARPS) s = fma(om[colb[c] + c0 + lane], ysol[c], s);
-    }
-    part[warp * K2_NB + lane] = s;
-    __syncthreads();
-    if (warp == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < NWARPS; ++ww) t += part[ww * K2_NB + lane];
-      sblk[lane] = (lane < w) ? b[c0 + lane] - t : 0.0;
-      __syncwarp();
-      // y[c] = sum_{c' <= c} Linv[c][c'] s[c'],  ws[c][c'] = Linv[c][c'] -> lane = c'?  use lane = c:
-      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
-      double yv = 0.0;
-#pragma unroll 8
-      for (int cp = 0; cp < K2_NB; ++cp) yv = fma(wsk[lane * K2_NB + cp], sblk[cp], yv);
-      if (lane < w) ysol[c0 + lane] = yv;
-    }
-    __syncthreads();
-  }
-  // ---- backward
-  for (int i = tid; i < n; i += NTHREADS) ysol[i] += p.z[(size_t)blockIdx.x * p.ldz + i];
-  __syncthreads();
-  for (int k = nbk - 1; k >= 0; --k) {
-    const int c0 = k * K2_NB;
-    const int w = min(K2_NB, n - c0);
-    const int kb_end = c0 + w;
-    for (int c = warp; c < K2_NB; c += NWARPS) {
-      double s = 0.0;
-      if (c < w) {
-        const double* colp = om + colb[c0 + c];
-        for (int i = kb_end + lane; i < n; i += 32) s = fma(colp[i], ysol[i], s);
-        s = warp_sum(s);
+
+  // The item stream, in the order the solve consumes it:
+  //   forward  k = 0..nbk-1 :  Linv_k, then the chunks of P_k (rows kb_end.. in steps of RC)
+  //   backward k = nbk-1..0 :  the chunks of P_k, then Linv_k
+  // Fetch cursor: (pass, k, r0) with r0 < 0 meaning "the Linv item of block k"; pass == 2 is the end.
+  auto kb_end_of = [&](int k) { return min(n, (k + 1) * K2_NB); };
+  int fpass = 0, fk = 0, fr0 = -1;
+  auto advance = [&]() {
+    if (fpass == 0) {
+      if (fr0 < 0) fr0 = kb_end_of(fk); else fr0 += K2S_RC;
+      if (fr0 >= n) {                                    // block exhausted: next block's Linv, or turn around
+        if (fk + 1 < nbk) { ++fk; fr0 = -1; }
+        else { fpass = 1; fr0 = kb_end_of(fk); if (fr0 >= n) fr0 = -1; }
       }
-      if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
+    } else if (fpass == 1) {
+      if (fr0 >= 0) { fr0 += K2S_RC; if (fr0 >= n) fr0 = -1; }
+      else {
+        --fk;
+        if (fk < 0) fpass = 2;
+        else { fr0 = kb_end_of(fk); if (fr0 >= n) fr0 = -1; }
+      }
     }
+  };
+  int fetched = 0, consumed = 0;
+  auto issue_next = [&]() {
+    if (fpass < 2) {
+      double* dst = ring + (size_t)(fetched % K2S_STAGES) * STAGE_D;
+      if (fr0 < 0) {
+        // one Linv block, staged with row stride 33 (row c of Linv is read by lane c: stride 32 would be a 32-way
+        // bank conflict); 8-byte copies because the padded rows are not 16-byte aligned
+        const double* src = lws + (size_t)fk * (K2_NB * K2_NB);
+        for (int t = tid; t < K2_NB * K2_NB; t += NTHREADS) cp_async8(dst + (t >> 5) * K2S_LS + (t & 31), src + t);
+      } else {
+        const int c0 = fk * K2_NB, w = min(K2_NB, n - c0);
+        const int nr = min(K2S_RC, n - fr0);
+        const int col = tid >> 4, t16 = tid & 15;        // 32 columns x 16 threads
+        if (col < w) {
+          const double* src = om + colb[c0 + col] + fr0;
+          double* d = dst + (size_t)col * K2S_RCS;
+          const int npair = (nr + 1) >> 1;
+          for (int pr = t16; pr < npair; pr += 16) cp_async16(d + 2 * pr, src + 2 * pr);
+        }
+      }
+      ++fetched;
+      advance();
+    }
+    cp_async_commit();
+  };
+  // wait for the next item of the stream, refill the stage freed by the previous one, return the item's stage
+  auto next_item = [&]() -> const double* {
+    cp_async_wait<K2S_STAGES - 2>();
     __syncthreads();
+    issue_next();
+    const double* st = ring + (size_t)(consumed % K2S_STAGES) * STAGE_D;
+    ++consumed;
+    return st;
+  };
+  for (int sgi = 0; sgi < K2S_STAGES - 1; ++sgi) issue_next();
+
+  // ---- forward (right-looking):  y_k = Linv_kk b_k ;  b[rows below] -= P_k y_k
+  for (int k = 0; k < nbk; ++k) {
+    const int c0 = k * K2_NB, w = min(K2_NB, n - c0), kb_end = c0 + w;
+    {
+      const double* wsk = next_item();                   // wsk[c*33 + c'] = Linv[c][c']
+      if (warp == 0) {
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+        for (int cp = 0; cp < K2_NB; cp += 4) {
+          y0 = fma(wsk[lane * K2S_LS + cp], (cp < w) ? xs[c0 + cp] : 0.0, y0);
+          y1 = fma(wsk[lane * K2S_LS + cp + 1], (cp + 1 < w) ? xs[c0 + cp + 1] : 0.0, y1);
+          y2 = fma(wsk[lane * K2S_LS + cp + 2], (cp + 2 < w) ? xs[c0 + cp + 2] : 0.0, y2);
+          y3 = fma(wsk[lane * K2S_LS + cp + 3], (cp + 3 < w) ? xs[c0 + cp + 3] : 0.0, y3);
+        }
+        double yv = (y0 + y1) + (y2 + y3);
+        yv = (lane < w) ? yv : 0.0;
+        ybuf[lane] = yv;
+        if (lane < w) xs[c0 + lane] = yv;
+      }
+    }
+    for (int r0 = kb_end; r0 < n; r0 += K2S_RC) {
+      const double* P = next_item();                     // (its barrier also publishes ybuf)
+      const int nr = min(K2S_RC, n - r0);
+      if (tid < nr) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < K2_NB; c += 2) {
+          s0 = fma(P[(size_t)c * K2S_RCS + tid], (c < w) ? ybuf[c] : 0.0, s0);
+          s1 = fma(P[(size_t)(c + 1) * K2S_RCS + tid], (c + 1 < w) ? ybuf[c + 1] : 0.0, s1);
+        }
+        xs[r0 + tid] -= s0 + s1;
+      }
+    }
+  }
+  // ---- backward:  L^T phi = y + z ;  x_k = Linv_kk^T ( (y+z)_k - P_k^T x[rows below] )
+  __syncthreads();
+  for (int i = tid; i < n; i += NTHREADS) xs[i] += p.z[(size_t)blockIdx.x * p.ldz + i];
+  for (int k = nbk - 1; k >= 0; --k) {
+    const int c0 = k * K2_NB, w = min(K2_NB, n - c0), kb_end = c0 + w;
+    __syncthreads();                                     // previous block's x_k (and the z add) visible; sblk free
+    if (tid < K2_NB) sblk[tid] = 0.0;
+    for (int r0 = kb_end; r0 < n; r0 += K2S_RC) {
+      const double* P = next_item();
+      const int nr = min(K2S_RC, n - r0);
+      for (int c = warp; c < w; c += NWARPS) {           // one warp per column: no race on sblk[c]
+        const double* colp = P + (size_t)c * K2S_RCS;
+        double sc = 0.0;
+        for (int i = lane; i < nr; i += 32) sc = fma(colp[i], xs[r0 + i], sc);
+        sc = warp_sum(sc);
+        if (lane == 0) sblk[c] += sc;
+      }
+    }
+    const double* wsk = next_item();                     // (its barrier also publishes sblk)
     if (warp == 0) {
-      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+      // x[c'] = sum_{c >= c'} Linv[c][c'] (y[c] - s[c])
       double xv0 = 0.0, xv1 = 0.0;
 #pragma unroll
       for (int cp = 0; cp < K2_NB; cp += 2) {
-        xv0 = fma(wsk[cp * K2_NB + lane], sblk[cp], xv0);
-        xv1 = fma(wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
+        xv0 = fma(wsk[cp * K2S_LS + lane], (cp < w) ? xs[c0 + cp] - sblk[cp] : 0.0, xv0);
+        xv1 = fma(wsk[(cp + 1) * K2S_LS + lane], (cp + 1 < w) ? xs[c0 + cp + 1] - sblk[cp + 1] : 0.0, xv1);
       }
-      if (lane < w) ysol[c0 + lane] = xv0 + xv1;
+      __syncwarp();
+      if (lane < w) xs[c0 + lane] = xv0 + xv1;
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
   bool bad = false;
   for (int i = tid; i < n; i += NTHREADS) {
-    const double v = ysol[i];
+    const double v = xs[i];
     p.phi[(size_t)blockIdx.x * p.ldphi + i] = v;
     bad |= !isfinite(v);
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
   if (tid == 0 && anybad) atomicCAS(&p.status[eq], 0, -1);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // K2 v2 - the same factorisation, warp-specialised with one block column of LOOK-AHEAD.
@@ -1013,8 +1093,10 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
 cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s) {
   if (!g_linv_ws) return cudaErrorInvalidValue;
   const int nbk = k2_nblocks(p.n);
-  const size_t smem = ((size_t)(nbk * K2_NB + 32) + K2_NWARPS * K2_NB + 32) * sizeof(double) + (size_t)(p.n + 4) * sizeof(int);
-  if (smem > 48 * 1024) {
+  const size_t smem = ((size_t)K2S_STAGES * K2_NB * K2S_RCS + (size_t)(nbk * K2_NB + 32) + 64) * sizeof(double) +
+                      (size_t)(p.n + 4) * sizeof(int);
+  if (smem > (size_t)227 * 1024) return cudaErrorInvalidValue;
+  {
     cudaError_t e = cudaFuncSetAttribute(k2_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
