@@ -868,21 +868,32 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
         for (int q = 0; q < MAXQ; ++q)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
-        const int nchunks = c0 / K2_BKC;
-        int S = ring_doubles / stage_d;
-        S = S > K2V_MAXS ? K2V_MAXS : S;                     // >= 2 by construction of the ring
+        // A ring stage holds `cm` sub-chunks of 16 columns: late block columns have few rows, so 16 columns are too
+        // little work per barrier (measured ~1.6k cycles per 16-column chunk regardless of its size); cm = 1, 2, 4 or 8.
+        const int sub_d = K2_BKC * RSl;                      // one 16-column sub-chunk
+        int cm = 1;
+        if (ring_doubles >= 2 * 8 * sub_d) cm = 8; else if (ring_doubles >= 2 * 4 * sub_d) cm = 4; else if (ring_doubles >= 2 * 2 * sub_d) cm = 2;
+        const int stage_cd = cm * sub_d;
+        const int nsubs = c0 / K2_BKC;                       // 16-column sub-chunks to go through
+        const int nchunks = (nsubs + cm - 1) / cm;
+        int S = ring_doubles / stage_cd;
+        S = S > 4 ? 4 : S;                                   // >= 2 by construction of the ring
         const int lcol = tg / 30, lr0 = tg - 30 * lcol;      // loader: 16 columns x 30 threads
         const int npair = (Rn + 1) >> 1;
         auto load_chunk = [&](int st, int ch) {
-          double* sdst = ring + (size_t)st * stage_d + lcol * RSl;
-          const double* src = om + colb[ch * K2_BKC + lcol];
-          if (fulln) {
-            for (int pr = lr0; pr < npair; pr += 30) cp_async16(sdst + 2 * pr, src + c0n + 2 * pr);
-          } else {
-            for (int li = lr0; li < Rn; li += 30) {
-              const int gg = li < K2_NB ? (li < wn ? c0n + li : -1) : c0n + wn + li - K2_NB;
-              if (gg >= 0) cp_async8(sdst + li, src + gg);
-              else sdst[li] = 0.0;
+          for (int u = 0; u < cm; ++u) {
+            const int sc = ch * cm + u;
+            if (sc >= nsubs) break;
+            double* sdst = ring + (size_t)st * stage_cd + (size_t)u * sub_d + lcol * RSl;
+            const double* src = om + colb[sc * K2_BKC + lcol];
+            if (fulln) {
+              for (int pr = lr0; pr < npair; pr += 30) cp_async16(sdst + 2 * pr, src + c0n + 2 * pr);
+            } else {
+              for (int li = lr0; li < Rn; li += 30) {
+                const int gg = li < K2_NB ? (li < wn ? c0n + li : -1) : c0n + wn + li - K2_NB;
+                if (gg >= 0) cp_async8(sdst + li, src + gg);
+                else sdst[li] = 0.0;
+              }
             }
           }
         };
@@ -898,7 +909,9 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
             if (nxt < nchunks) load_chunk(nxt % S, nxt);      // issued before the MMAs: the copies are latency-bound
             cp_async_commit();
           }
-          k2v_stage(nqn, acc, ring + (size_t)(ch % S) * stage_d, RSl, g, fr, fk);
+          const int usub = min(cm, nsubs - ch * cm);
+          for (int u = 0; u < usub; ++u)
+            k2v_stage(nqn, acc, ring + (size_t)(ch % S) * stage_cd + (size_t)u * sub_d, RSl, g, fr, fk);
         }
         cp_async_wait<0>();
         k2v_bar_gemm();                                      // ring is free
