@@ -28,54 +28,65 @@ struct PredictParams {
 };
 
 // C[m x n] (ldc) = op(A) * B (+ C if accumulate); A is k x m when transA (lda), else m x k.  All column-major in
-// global memory.  64 x 64 output tile, 4 x 4 per thread, K chunks of 16 through shared memory.
+// global memory.  64 x 64 output tile per pass, K chunks of 16 staged k-major in shared memory (row stride 68 == 4
+// mod 16: conflict-free m8n8k4 fragment loads), 8 warps as 4 (m) x 2 (n), each 16 x 32 of the tile on FP64 DMMA.
+constexpr int PR_LD = 68;
 __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool transA, const double* B, int ldb, double* C,
-                         int ldc, bool accumulate, double* sA /*[16][65]*/, double* sB /*[16][65]*/) {
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+                         int ldc, bool accumulate, double* sA /*[16][PR_LD]*/, double* sB /*[16][PR_LD]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
   for (int m0 = 0; m0 < m; m0 += 64) {
     for (int n0 = 0; n0 < n; n0 += 64) {
-      double acc[4][4];
+      double acc[2][4][2];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
       for (int k0 = 0; k0 < k; k0 += 16) {
         for (int i = tid; i < 16 * 64; i += PR_THREADS) {
-          const int kk = i / 64, mm = i % 64;           // sA[kk][mm] = op(A)[m0+mm, k0+kk]
+          // sA[kk][mm] = op(A)[m0+mm, k0+kk];  sB[kk][nn] = B[k0+kk, n0+nn].  The fastest index follows the operand's
+          // contiguous dimension so the global reads coalesce.
+          int kk, mm;
+          if (transA) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
           const int gm = m0 + mm, gk = k0 + kk;
           double v = 0.0;
           if (gm < m && gk < k) v = transA ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
-          sA[kk * 65 + mm] = v;
-          const int gn = n0 + mm;                        // sB[kk][nn] = B[k0+kk, n0+nn]
+          sA[kk * PR_LD + mm] = v;
+          const int kb = i & 15, nn = i >> 4;
+          const int gn = n0 + nn, gkb = k0 + kb;
           double w = 0.0;
-          if (gn < n && gk < k) w = B[(size_t)gn * ldb + gk];
-          sB[kk * 65 + mm] = w;
+          if (gn < n && gkb < k) w = B[(size_t)gn * ldb + gkb];
+          sB[kb * PR_LD + nn] = w;
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          double av[4], bv[4];
+        for (int ks = 0; ks < 4; ++ks) {
+          const double* ap = sA + (4 * ks + fk) * PR_LD + 16 * wm + fr;
+          const double* bp = sB + (4 * ks + fk) * PR_LD + 32 * wn + fr;
+          const double a0 = ap[0], a1 = ap[8];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) av[a] = sA[kk * 65 + tx + 16 * a];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) bv[b] = sB[kk * 65 + ty + 16 * b];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+          for (int b = 0; b < 4; ++b) {
+            const double bv = bp[8 * b];
+            dmma884(acc[0][b][0], acc[0][b][1], a0, bv);
+            dmma884(acc[1][b][0], acc[1][b][1], a1, bv);
+          }
         }
         __syncthreads();
       }
+      // accumulator fragment: rows 8a + fr, columns 8b + 2 fk + {0, 1}
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int gm = m0 + tx + 16 * a, gn = n0 + ty + 16 * b;
-          if (gm < m && gn < n) {
-            double* c = C + (size_t)gn * ldc + gm;
-            *c = accumulate ? *c + acc[a][b] : acc[a][b];
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int gm = m0 + 16 * wm + 8 * a + fr, gn = n0 + 32 * wn + 8 * b + 2 * fk + e;
+            if (gm < m && gn < n) {
+              double* c = C + (size_t)gn * ldc + gm;
+              *c = accumulate ? *c + acc[a][b][e] : acc[a][b][e];
+            }
           }
-        }
     }
   }
   __syncthreads();
@@ -123,7 +134,7 @@ __device__ double cta_mvn_logdens(int n, const double* L, int ld, double* d) {
 }
 
 __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams p) {
-  __shared__ double sA[16 * 65], sB[16 * 65];
+  __shared__ double sA[16 * PR_LD], sB[16 * PR_LD];
   __shared__ double sres[2];
   const int Kp = p.Kp, M = p.M, R = p.R, P = p.p, tid = threadIdx.x;
   double* base = p.scratch + (size_t)blockIdx.x * p.slab;
