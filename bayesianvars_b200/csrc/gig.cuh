@@ -9,7 +9,8 @@
 //   * lambda < 0 handled through X ~ GIG(lambda,chi,psi) <=> 1/X ~ GIG(-lambda,psi,chi),
 //   * lambda > 2 or omega > 3            : ratio-of-uniforms with mode shift,
 //   * lambda >= 1-2.25 omega^2 or omega > 0.2 : ratio-of-uniforms without shift,
-//   * otherwise (0 <= lambda < 1, small omega) : three-part hat ("new approach").
+//   * otherwise (0 <= lambda < 1, small omega) : three-part hat ("new approach"),
+//   * |lambda| = 1/2 exactly: the (reciprocal) inverse Gaussian law, sampled in closed form (Michael et al. 1976).
 // Value-level parity with GIGrvg is unpinned (different uniform stream); the tests
 // are distributional (KS against scipy.stats.geninvgauss and the gamma limits).
 #pragma once
@@ -71,54 +72,74 @@ __host__ __device__ inline double gig_rou_shift(RngStream& g, double lambda, dou
   return X;
 }
 
-// Three-part hat for 0 <= lambda < 1 and small omega (Hoermann & Leydold, Alg. 3).
+// Three-part hat for 0 <= lambda < 1 and small omega (Hoermann & Leydold, Alg. 3).  This is the branch the DL / NG /
+// R2D2 local scales hit for coefficients shrunk to zero, i.e. almost all of them, so it is written in log space:
+// x^y as exp(y log x) with the logs shared (no pow), the hat value carried as its logarithm so the acceptance test
+// needs no exp, and log X produced by the inversion itself where possible.  Two uniforms per attempt as before.
 __host__ __device__ inline double gig_newapproach(RngStream& g, double lambda, double omega) {
   const double xm = gig_mode(lambda, omega);
   const double x0 = omega / (1.0 - lambda);
-  const double k0 = exp((lambda - 1.0) * log(xm) - 0.5 * omega * (xm + 1.0 / xm));
-  const double A0 = k0 * x0;
-  double k1, A1, k2, A2;
-  if (x0 >= 2.0 / omega) {
-    k1 = 0.0;
-    A1 = 0.0;
-    k2 = pow(x0, lambda - 1.0);
-    A2 = k2 * 2.0 * exp(-omega * x0 / 2.0) / omega;
+  const double lm1 = lambda - 1.0, hw = 0.5 * omega;
+  const double lk0 = lm1 * log(xm) - hw * (xm + 1.0 / xm);      // log k0
+  const double A0 = exp(lk0) * x0;
+  const double lx0 = log(x0), l2w = log(2.0 / omega);
+  const bool two = (x0 >= 2.0 / omega);                          // no middle part
+  double lk1 = 0.0, A1 = 0.0, lk2, A2, x0lam = 0.0, k1inv = 0.0;
+  if (two) {
+    lk2 = lm1 * lx0;
+    A2 = exp(lk2 - hw * x0) * 2.0 / omega;
   } else {
-    k1 = exp(-omega);
-    A1 = (lambda == 0.0) ? k1 * log(2.0 / (omega * omega))
-                         : k1 / lambda * (pow(2.0 / omega, lambda) - pow(x0, lambda));
-    k2 = pow(2.0 / omega, lambda - 1.0);
-    A2 = k2 * 2.0 * exp(-1.0) / omega;
+    lk1 = -omega;
+    const double k1 = exp(lk1);
+    k1inv = 1.0 / k1;
+    if (lambda == 0.0) A1 = k1 * (2.0 * l2w - 0.6931471805599453);   // k1 log(2 / omega^2)
+    else { x0lam = exp(lambda * lx0); A1 = k1 / lambda * (exp(lambda * l2w) - x0lam); }
+    lk2 = lm1 * l2w;
+    A2 = exp(lk2 - 1.0) * 2.0 / omega;
   }
   const double Atot = A0 + A1 + A2;
+  const double aa = two ? x0 : 2.0 / omega;
+  const double ea = exp(-hw * aa), c2 = omega / (2.0 * exp(lk2));
   double X = xm;
   for (int it = 0; it < 100000; ++it) {
     double V = Atot * g.uniform();
-    double hx;
+    double lhx, lX;
     if (V <= A0) {
       X = x0 * V / A0;
-      hx = k0;
+      lX = log(X);
+      lhx = lk0;
     } else {
       V -= A0;
       if (V <= A1) {
         if (lambda == 0.0) {
-          X = omega * exp(exp(omega) * V);
-          hx = k1 / X;
+          lX = log(omega) + k1inv * V;                          // X = omega exp(exp(omega) V)
+          X = exp(lX);
         } else {
-          X = pow(pow(x0, lambda) + (lambda / k1 * V), 1.0 / lambda);
-          hx = k1 * pow(X, lambda - 1.0);
+          lX = log(x0lam + lambda * k1inv * V) / lambda;          // X = (x0^lambda + lambda V / k1)^(1/lambda)
+          X = exp(lX);
         }
+        lhx = lk1 + lm1 * lX;                                     // hat = k1 X^(lambda-1)
       } else {
         V -= A1;
-        const double a = (x0 > 2.0 / omega) ? x0 : 2.0 / omega;
-        X = -2.0 / omega * log(exp(-omega / 2.0 * a) - omega / (2.0 * k2) * V);
-        hx = k2 * exp(-omega / 2.0 * X);
+        X = -2.0 / omega * log(ea - c2 * V);
+        lX = log(X);
+        lhx = lk2 - hw * X;                                       // hat = k2 exp(-omega X / 2)
       }
     }
-    const double U = g.uniform() * hx;
-    if (log(U) <= (lambda - 1.0) * log(X) - omega / 2.0 * (X + 1.0 / X)) break;
+    if (log(g.uniform()) + lhx <= lm1 * lX - hw * (X + 1.0 / X)) break;
   }
   return X;
+}
+
+// Inverse Gaussian IG(mean mu, shape sh) by the transformation of Michael, Schucany & Haas (1976), smaller root in
+// its cancellation-free form.  GIG(-1/2, chi, psi) = IG(sqrt(chi/psi), chi) exactly, and GIG(1/2, chi, psi) is its
+// reciprocal with the roles of chi and psi swapped - the DL psi draw and the R2D2 / NG-exponential-kernel draws are
+// of this kind, one normal and one uniform instead of a rejection loop.
+__host__ __device__ inline double inverse_gaussian(RngStream& g, double mu, double sh) {
+  const double z = g.normal();
+  const double w = mu * z * z / (2.0 * sh);
+  const double y = mu / (1.0 + w + sqrt(w * (2.0 + w)));
+  return (g.uniform() * (mu + y) <= mu) ? y : mu * mu / y;
 }
 
 // One GIG(lambda, chi, psi) variate.  Returns NaN for invalid parameters (the
@@ -135,6 +156,8 @@ __host__ __device__ inline double gig_draw(RngStream& g, double lambda, double c
     // inverse-gamma limit (X = 1 / Gamma(|lambda|, scale 2/chi))
     return 1.0 / (g.gamma(fabs(lambda)) * (2.0 / chi));
   }
+  if (lambda == -0.5) return inverse_gaussian(g, sqrt(chi / psi), chi);
+  if (lambda == 0.5) return 1.0 / inverse_gaussian(g, sqrt(psi / chi), psi);
   const double lambda_old = lambda;
   if (lambda < 0.0) lambda = -lambda;
   const double alpha = sqrt(chi / psi), omega = sqrt(psi * chi);

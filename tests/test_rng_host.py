@@ -71,13 +71,19 @@ def test_gamma(hostrng, shape):
 
 # (lambda, chi, psi): every branch of the sampler and the regimes the priors hit
 GIG_CASES = [
-    (0.5, 1.0, 1.0),           # ROU no shift
-    (-0.5, 1.0, 3.0),          # R2D2 psi draw: lambda < 0 reflected
+    (0.5, 1.0, 1.0),           # |lambda| = 1/2: closed-form (reciprocal) inverse Gaussian
+    (-0.5, 1.0, 3.0),          # R2D2 psi draw
+    (0.5, 1e-12, 1.0),         # ... across the dynamic range the DL psi draw sees
+    (0.5, 1e6, 1e-3),
+    (-0.5, 1e-8, 2.0),
+    (0.4999, 1.0, 1.0),        # next to 1/2: ROU no shift
+    (0.6, 1e-6, 1.0),          # small omega, generic lambda: new approach, all three parts
+    (0.3, 2e-3, 5e-2),
     (3.0, 2.0, 5.0),           # lambda > 2: ROU with shift
     (0.7, 40.0, 2.0),          # omega > 3: ROU with shift
     (0.9975, 2e-3, 1.0),       # DL lambda draw reflected (|lambda| ~ 1, small omega): new approach
     (-0.9975, 2e-4, 1.0),      # DL lambda draw as called: GIG(a-1, 2|phi|, 2 xi)
-    (0.5, 1e-6, 1.0),          # DL psi draw, tiny chi: new approach
+    (0.5, 1e-6, 1.0),          # DL psi draw, tiny chi
     (0.0, 0.01, 0.02),         # lambda == 0 branch of the new approach
     (0.1, 1e-4, 1e-3),
     (-0.4, 0.5, 0.5),          # R2D2 lambda draw  GIG(a - 1/2, ...) with a = 0.1
