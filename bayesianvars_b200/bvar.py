@@ -556,7 +556,7 @@ class Sampler:
     """A chain set up on the device (bvb_gibbs_init); `run(n)` advances it."""
 
     def __init__(self, handle: Handle, prep, prior_phi, prior_sigma, draws, burnin, thin=1, sv_keep="last",
-                 expert_huge=False):
+                 expert_huge=False, out=None):
         self.h = handle
         self.lib = handle._lib
         self.prep = prep
@@ -582,6 +582,12 @@ class Sampler:
             phi_hyperparameter=np.zeros((hyper_rows, ns), order="F"),
             facload=np.zeros((M, r, ns), order="F"), fac=np.zeros((r, tv, ns), order="F"),
             U=np.zeros((n_U, ns if chol else 0), order="F"), u_hyperparameter=np.zeros((uh_rows, ns if uh_rows else 0), order="F"))
+        if out is not None:   # caller-owned (already allocated / touched) output arrays of exactly these shapes
+            for k, a in self.out.items():
+                b = out[k]
+                if b.shape != a.shape or b.dtype != np.float64 or not (b.flags.f_contiguous or b.size == 0):
+                    raise ValueError(f"out[{k!r}]: expected a float64 Fortran-ordered array of shape {a.shape}")
+            self.out = {k: out[k] for k in self.out}
         d = Draws()
         for k in ("PHI", "V_prior", "logvar", "sv_para", "phi_hyperparameter", "facload", "fac", "U", "u_hyperparameter"):
             if self.out[k].size:
