@@ -370,11 +370,12 @@ __global__ void __launch_bounds__(32 * FAC_SLICES) fsv_factors_kernel(const FsvD
   const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int t = blockIdx.x * 32 + tx;
   const int r = d.r;
+  const int nsl = blockDim.x >> 5;     // row slices (FAC_SLICES unless the reduction buffer would not fit)
   const int nred = r * (r + 1) / 2 + r;
   double A[FSV_RMAX * FSV_RMAX], b[FSV_RMAX];
   for (int p = 0; p < r; ++p) { b[p] = 0.0; for (int q = 0; q <= p; ++q) A[p * FSV_RMAX + q] = 0.0; }
   if (t < d.T) {
-    for (int i = sl; i < d.M; i += FAC_SLICES) {
+    for (int i = sl; i < d.M; i += nsl) {
       const double w = d.wexp[(size_t)i * d.T + t];
       const double y = d.resid[(size_t)i * d.T + t];
       for (int p = 0; p < r; ++p) {
@@ -398,12 +399,12 @@ __global__ void __launch_bounds__(32 * FAC_SLICES) fsv_factors_kernel(const FsvD
     for (int p = 0; p < r; ++p)
       for (int q = 0; q <= p; ++q, ++k) {
         double v = 0.0;
-        for (int z = 0; z < FAC_SLICES; ++z) v += fsm[((size_t)z * nred + k) * 32 + tx];
+        for (int z = 0; z < nsl; ++z) v += fsm[((size_t)z * nred + k) * 32 + tx];
         A[p * FSV_RMAX + q] = v;
       }
     for (int p = 0; p < r; ++p, ++k) {
       double v = 0.0;
-      for (int z = 0; z < FAC_SLICES; ++z) v += fsm[((size_t)z * nred + k) * 32 + tx];
+      for (int z = 0; z < nsl; ++z) v += fsm[((size_t)z * nred + k) * 32 + tx];
       b[p] = v;
     }
   }
@@ -430,9 +431,12 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
     fsv_loadings_kernel<<<(d.M + 3) / 4, 128, 0, s>>>(d, seed, sweep);
     if (d.interweaving != 0) fsv_interweave_kernel<<<d.r, 32, 0, s>>>(d, seed, sweep);
     {
-      const size_t fsmem = (size_t)FAC_SLICES * (d.r * (d.r + 1) / 2 + d.r) * 32 * sizeof(double);
+      const size_t per_slice = (size_t)(d.r * (d.r + 1) / 2 + d.r) * 32 * sizeof(double);
+      int nsl = FAC_SLICES;
+      while (nsl > 1 && nsl * per_slice > (size_t)200 * 1024) --nsl;      // r > 13: fewer row slices
+      const size_t fsmem = nsl * per_slice;
       if (fsmem > 48 * 1024) cudaFuncSetAttribute(fsv_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-      fsv_factors_kernel<<<(d.T + 31) / 32, 32 * FAC_SLICES, fsmem, s>>>(d, seed, sweep);
+      fsv_factors_kernel<<<(d.T + 31) / 32, 32 * nsl, fsmem, s>>>(d, seed, sweep);
     }
   }
   return cudaGetLastError();
