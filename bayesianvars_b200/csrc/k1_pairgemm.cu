@@ -23,6 +23,7 @@
 // so 4 warps per scheduler are resident (the DMMA pipe needs that many to stay
 // fed: with 2 warps per scheduler ncu showed 58% pipe activity).
 #include "bvb_internal.cuh"
+#include <cuda.h>      // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links to libcuda
 #include <stdlib.h>
 
 namespace bvb {
@@ -141,6 +142,161 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : 2)) k1_pairgemm(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA variant.  Same tiling and arithmetic; the operand tiles arrive as two 2-D tensor-map copies per
+// stage (A: BM rows x 20 columns, W / WY: 8 NT rows x 20 columns, dense 160-byte rows = the layout the
+// fragment loads already use) issued by one thread, completion on an mbarrier per stage.  Why: a
+// cp.async.cg stream fills shared memory one 32-byte sector at a time and that contends with the LDS
+// operand loads of the DMMA warps (tools/microbench/stream_vs_dmma.cu: at 42 B/clk/SM the DMMA rate
+// halves, an aligned TMA stream costs it nothing); K1 streams ~14 B/clk/SM.  It also removes ~20
+// address/issue instructions per thread and stage.
+// ---------------------------------------------------------------------------------------------
+struct K1Maps { CUtensorMap a, w, wy; };
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NT, int MW, int ST>
+__global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : (MW <= 4 ? 2 : 1))) k1_pairgemm_tma(const K1Params p, const __grid_constant__ K1Maps maps) {
+  constexpr int BM = 16 * MW;
+  constexpr int NB = 8 * NT;
+  constexpr int NTW = (NT + 1) / 2;
+  constexpr int A_STAGE = BM * K1_BK;              // doubles (BM x 160 B: a multiple of 128 B)
+  constexpr int B_STAGE = NB * K1_BK;
+  constexpr int STAGE = A_STAGE + ((B_STAGE + 15) / 16) * 16;   // keep every stage 128-byte aligned
+  extern __shared__ __align__(128) double smem_t[];
+  __shared__ __align__(8) uint64_t full[ST];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int nt0 = wn * NTW;
+  const int ntc = wn == 0 ? NTW : NT - NTW;
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * NB;
+  const bool ztile = tile < p.nZtiles;
+  const int nk = p.Tp / K1_BK;
+  if (tid == 0) {
+    for (int i = 0; i < ST; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto load_stage = [&](int stage, int kc) {   // thread 0 only
+    double* da = smem_t + (size_t)stage * STAGE;
+    mbar_arrive_expect_tx(&full[stage], (uint32_t)((A_STAGE + B_STAGE) * sizeof(double)));
+    tma_load_2d(da, &maps.a, kc * K1_BK, tile * BM, &full[stage]);
+    tma_load_2d(da + A_STAGE, ztile ? &maps.w : &maps.wy, kc * K1_BK, n0, &full[stage]);
+  };
+
+  double acc[2][NTW][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) acc[m][nt][0] = acc[m][nt][1] = 0.0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s)
+      if (s < nk) load_stage(s, s);
+  }
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int kc = 0; kc < nk; ++kc) {
+    const int st = kc % ST;
+    __syncthreads();                               // every warp is done with the stage refilled below
+    if (tid == 0) {
+      const int nxt = kc + ST - 1;
+      if (nxt < nk) { fence_proxy_async(); load_stage(nxt % ST, nxt); }
+    }
+    mbar_wait(&full[st], (uint32_t)((kc / ST) & 1));
+    const double* a = smem_t + (size_t)st * STAGE + (wm * 16 + fr) * K1_BK + fk;
+    const double* b = smem_t + (size_t)st * STAGE + A_STAGE + (nt0 * 8 + fr) * K1_BK + fk;
+    if (wn == 0) k1_stage_mma<NTW, NTW>(acc, a, b);
+    else if (NT - NTW > 0) k1_stage_mma<(NT - NTW > 0 ? NT - NTW : 1), NTW>(acc, a, b);
+  }
+
+  // Epilogue: add prior terms, scatter into the packed augmented systems.
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int row = tile * BM + wm * 16 + m * 8 + fr;
+    const int2 l = p.lut[row];
+    if (l.x < 0) continue;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      if (nt >= ntc) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = n0 + (nt0 + nt) * 8 + 2 * fk + e;
+        if (j >= p.M) continue;
+        double v = acc[m][nt][e];
+        if (p.rowscale) {
+          if (!ztile) continue;   // the right-hand side of the T x T system is written by huge_rhs_kernel
+          const int2 ts = p.pairs[row];
+          v = v * p.rowscale[(size_t)j * p.n + ts.x] * p.rowscale[(size_t)j * p.n + ts.y] + (ts.x == ts.y ? 1.0 : 0.0);
+        } else if (l.y >= 0) {
+          const double pv = p.V[(size_t)j * p.n + l.y];
+          if (ztile) v += 1.0 / pv;
+          else if (p.PHI0) v += p.PHI0[(size_t)j * p.n + l.y] / pv;
+        }
+        p.omega[(size_t)j * p.ldo + l.x] = v;
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// rows x Tp doubles, row-major (K-major), box = box_rows x K1_BK
+static bool make_map(CUtensorMap* m, const double* base, int rows, int Tp, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)Tp, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Tp * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)K1_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NT, int MW, int ST>
+static cudaError_t launch_k1_tma_cfg(const K1Params& p, cudaStream_t s, bool* used) {
+  constexpr int BM = 16 * MW, NB = 8 * NT;
+  constexpr int STAGE = BM * K1_BK + ((NB * K1_BK + 15) / 16) * 16;
+  *used = false;
+  const int rows = p.ntiles * K1_BM;
+  dim3 grid(rows / BM, (p.M + NB - 1) / NB);
+  K1Maps maps;
+  const int wrows = (int)grid.y * NB;
+  if (!make_map(&maps.a, p.A, rows, p.Tp, BM) || !make_map(&maps.w, p.W, wrows, p.Tp, NB) ||
+      !make_map(&maps.wy, p.WY, wrows, p.Tp, NB))
+    return cudaSuccess;                              // no encoder / unsupported shape: the caller falls back to cp.async
+  const size_t smem = (size_t)ST * STAGE * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(k1_pairgemm_tma<NT, MW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  K1Params q = p;
+  q.nZtiles = p.nZtiles * K1_BM / BM;
+  k1_pairgemm_tma<NT, MW, ST><<<grid, MW * 64, smem, s>>>(q, maps);
+  *used = true;
+  return cudaGetLastError();
+}
+
 template <int NT, int MW>
 static cudaError_t launch_k1_cfg(const K1Params& p, cudaStream_t s) {
   const size_t smem = (size_t)K1_STAGES * (16 * MW + 8 * NT) * K1_BK * sizeof(double);
@@ -161,6 +317,20 @@ static cudaError_t launch_k1_nt(const K1Params& p, cudaStream_t s) {
     const char* e = getenv("BVB_K1_MW");
     mw = e ? atoi(e) : 2;   // measured at the headline shape: 32-row tiles 328 us, 48-row 377 us, 64-row 335 us
     if (mw != 2 && mw != 3 && mw != 4) mw = 2;
+  }
+  static int tma = -1, st = 0, mwt = 0;
+  if (tma < 0) {
+    const char* e = getenv("BVB_K1_TMA"); tma = e ? atoi(e) : 1;
+    e = getenv("BVB_K1_ST"); st = e ? atoi(e) : 3;
+    e = getenv("BVB_K1_MW"); mwt = e ? atoi(e) : 4;      // TMA kernel: 64-row tiles by default
+  }
+  if (tma) {
+    bool used = false;
+    cudaError_t e;
+    if (mwt == 2) e = st == 4 ? launch_k1_tma_cfg<NT, 2, 4>(p, s, &used) : launch_k1_tma_cfg<NT, 2, 3>(p, s, &used);
+    else if (mwt == 8) e = st == 4 ? launch_k1_tma_cfg<NT, 8, 4>(p, s, &used) : launch_k1_tma_cfg<NT, 8, 3>(p, s, &used);
+    else e = st == 4 ? launch_k1_tma_cfg<NT, 4, 4>(p, s, &used) : launch_k1_tma_cfg<NT, 4, 3>(p, s, &used);
+    if (e != cudaSuccess || used) return e;
   }
   return mw == 2 ? launch_k1_cfg<NT, 2>(p, s) : mw == 3 ? launch_k1_cfg<NT, 3>(p, s) : launch_k1_cfg<NT, 4>(p, s);
 }

@@ -12,9 +12,9 @@ void make_pair_geom(PairGeom& g, int T, int n) {
   g.Tp = ((T + K1_BK - 1) / K1_BK) * K1_BK;
   g.n = n;
   g.P = n * (n + 1) / 2;
-  // 64-row tiles, both sections padded to a multiple of 3 tiles so that 32-, 48- and 64-row CTA tiles all divide them
-  g.nZtiles = ((g.P + K1_BM - 1) / K1_BM + 2) / 3 * 3;
-  g.nXtiles = ((n + K1_BM - 1) / K1_BM + 2) / 3 * 3;
+  // 64-row tiles, both sections padded to a multiple of 6 tiles so that 32-, 48-, 64- and 128-row CTA tiles divide them
+  g.nZtiles = ((g.P + K1_BM - 1) / K1_BM + 5) / 6 * 6;
+  g.nXtiles = ((n + K1_BM - 1) / K1_BM + 5) / 6 * 6;
   g.nArows = K1_BM * (g.nZtiles + g.nXtiles);
   g.colbase.assign(n > 0 ? n : 1, 0);
   // column c stores rows c..n at colbase[c] + row; colbase[c] even.
