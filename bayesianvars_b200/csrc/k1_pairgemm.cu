@@ -247,6 +247,155 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : (MW <= 4 ? 2 : 1))) k1
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stream-K form of the TMA kernel.  1272 tiles over 296 resident CTAs are 4.3 waves: ncu shows the SM
+// sub-partitions idle 11% of the kernel (the tail).  Here the work is the flat list of (tile, K-chunk)
+// units, cut into one contiguous range per resident CTA, so every CTA gets the same number of chunks
+// and the TMA pipeline runs straight through tile boundaries.  A tile cut by a range boundary is
+// finished by the CTA that owns its FIRST chunks (it reaches the tile at the end of its range): the CTA
+// owning the last chunks reaches them at the very start of its range, parks its accumulators in a
+// workspace slot and raises a flag; the finisher adds them (fixed order: deterministic) and runs the
+// epilogue.  The finisher only ever waits for a CTA with a higher index that started at the same time
+// (all CTAs are co-resident, checked with the occupancy API), never for work that lies in the future.
+// MEASURED: parity-green but 381 us against 317 us for the plain tiled TMA kernel at the headline shape - the
+// resident CTAs of an SM now reach their tile ends (epilogue, pipeline drain) in lock step instead of staggered,
+// and the kernel needs 126 registers.  Kept behind BVB_K1_STREAMK=1 as a recorded experiment.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int MW, int ST>
+__global__ void __launch_bounds__(MW * 64, 2) k1_pairgemm_sk(const K1Params p, const __grid_constant__ K1Maps maps,
+                                                             double* __restrict__ ws, int* __restrict__ flags, int ntiles_rows) {
+  constexpr int BM = 16 * MW;
+  constexpr int NTHREADS = MW * 64;
+  constexpr int NB = 8 * NT;
+  constexpr int NTW = (NT + 1) / 2;
+  constexpr int A_STAGE = BM * K1_BK;
+  constexpr int B_STAGE = NB * K1_BK;
+  constexpr int STAGE = A_STAGE + ((B_STAGE + 15) / 16) * 16;
+  constexpr int NACC = 2 * NTW * 2;                  // accumulator doubles per thread
+  extern __shared__ __align__(128) double smem_k[];
+  __shared__ __align__(8) uint64_t full[ST];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int nt0 = wn * NTW;
+  const int ntc = wn == 0 ? NTW : NT - NTW;
+  const int nk = p.Tp / K1_BK;
+  const int fr = lane >> 2, fk = lane & 3;
+  // my range of units; unit u = (tile u / nk, chunk u % nk); tile = rowtile + ntiles_rows * ytile
+  const long long U = (long long)ntiles_rows * gridDim.y * nk;   // (gridDim.y = 1: one equation tile)
+  const long long u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
+  if (tid == 0) {
+    for (int i = 0; i < ST; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto load_unit = [&](int stage, long long u) {     // thread 0 only
+    const int t = (int)(u / nk), kc = (int)(u - (long long)t * nk);
+    const int rt = t % ntiles_rows, yt = t / ntiles_rows;
+    double* da = smem_k + (size_t)stage * STAGE;
+    mbar_arrive_expect_tx(&full[stage], (uint32_t)((A_STAGE + B_STAGE) * sizeof(double)));
+    tma_load_2d(da, &maps.a, kc * K1_BK, rt * BM, &full[stage]);
+    tma_load_2d(da + A_STAGE, rt < p.nZtiles ? &maps.w : &maps.wy, kc * K1_BK, yt * NB, &full[stage]);
+  };
+
+  double acc[2][NTW][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) acc[m][nt][0] = acc[m][nt][1] = 0.0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s)
+      if (u0 + s < u1) load_unit(s, u0 + s);
+  }
+  int it = 0;                                        // units consumed by this CTA (stage / parity bookkeeping)
+  for (long long u = u0; u < u1; ++u, ++it) {
+    const int st = it % ST;
+    __syncthreads();                                 // every warp is done with the stage refilled below
+    if (tid == 0) {
+      const long long nxt = u + ST - 1;
+      if (nxt < u1) { fence_proxy_async(); load_unit((it + ST - 1) % ST, nxt); }
+    }
+    mbar_wait(&full[st], (uint32_t)((it / ST) & 1));
+    const double* a = smem_k + (size_t)st * STAGE + (wm * 16 + fr) * K1_BK + fk;
+    const double* b = smem_k + (size_t)st * STAGE + A_STAGE + (nt0 * 8 + fr) * K1_BK + fk;
+    if (wn == 0) k1_stage_mma<NTW, NTW>(acc, a, b);
+    else if (NT - NTW > 0) k1_stage_mma<(NT - NTW > 0 ? NT - NTW : 1), NTW>(acc, a, b);
+
+    const int t = (int)(u / nk), kc = (int)(u - (long long)t * nk);
+    const bool tile_done = (kc == nk - 1), range_done = (u + 1 == u1);
+    if (!tile_done && !range_done) continue;
+    if (tile_done && u - kc < u0) {
+      // This tile was started by the previous CTA, which reaches it at the END of its range; I reach it at the START
+      // of mine.  So I park my partial sums (the tile's last chunks) right away and the previous CTA finishes the
+      // tile when it gets there - nobody waits for work that lies in the future.
+      double* slot = ws + (size_t)blockIdx.x * (NACC * NTHREADS);
+      int i = 0;
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e, ++i) { slot[(size_t)i * NTHREADS + tid] = acc[m][nt][e]; acc[m][nt][e] = 0.0; }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(&flags[blockIdx.x], 1);
+      continue;
+    }
+    if (!tile_done) {
+      // my range ends inside this tile: the next CTA has (long ago) parked the rest of it; fixed order: mine + theirs
+      if (tid == 0) {
+        while (atomicAdd(&flags[blockIdx.x + 1], 0) == 0) __nanosleep(64);
+      }
+      __syncthreads();
+      __threadfence();
+      const double* slot = ws + (size_t)(blockIdx.x + 1) * (NACC * NTHREADS);
+      int i = 0;
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e, ++i) acc[m][nt][e] += __ldcg(slot + (size_t)i * NTHREADS + tid);
+      __syncthreads();
+      if (tid == 0) atomicExch(&flags[blockIdx.x + 1], 0);   // consumed: the slot is free for the next launch
+    }
+    // epilogue of tile t: add prior terms, scatter into the packed augmented systems
+    {
+      const int rt = t % ntiles_rows, yt = t / ntiles_rows;
+      const bool ztile = rt < p.nZtiles;
+      const int n0 = yt * NB;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int row = rt * BM + wm * 16 + m * 8 + fr;
+        const int2 l = p.lut[row];
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = n0 + (nt0 + nt) * 8 + 2 * fk + e;
+            double v = acc[m][nt][e];
+            acc[m][nt][e] = 0.0;
+            if (l.x < 0 || nt >= ntc || j >= p.M) continue;
+            if (p.rowscale) {
+              if (!ztile) continue;   // the right-hand side of the T x T system is written by huge_rhs_kernel
+              const int2 ts = p.pairs[row];
+              v = v * p.rowscale[(size_t)j * p.n + ts.x] * p.rowscale[(size_t)j * p.n + ts.y] + (ts.x == ts.y ? 1.0 : 0.0);
+            } else if (l.y >= 0) {
+              const double pv = p.V[(size_t)j * p.n + l.y];
+              if (ztile) v += 1.0 / pv;
+              else if (p.PHI0) v += p.PHI0[(size_t)j * p.n + l.y] / pv;
+            }
+            p.omega[(size_t)j * p.ldo + l.x] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -310,6 +459,61 @@ static cudaError_t launch_k1_cfg(const K1Params& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+static double* g_sk_ws = nullptr;
+static int* g_sk_flags = nullptr;
+static size_t g_sk_ws_bytes = 0;
+static int g_sk_flags_n = 0;
+
+template <int NT, int MW, int ST>
+static cudaError_t launch_k1_sk_cfg(const K1Params& p, cudaStream_t s, bool* used) {
+  constexpr int BM = 16 * MW, NB = 8 * NT;
+  constexpr int STAGE = BM * K1_BK + ((NB * K1_BK + 15) / 16) * 16;
+  constexpr int NACC = 2 * ((NT + 1) / 2) * 2;
+  *used = false;
+  const int rows = p.ntiles * K1_BM;
+  const int ntr = rows / BM, ny = (p.M + NB - 1) / NB;
+  const int nk = p.Tp / K1_BK;
+  const size_t smem = (size_t)ST * STAGE * sizeof(double);
+  static int num_sms = 0;
+  if (num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  cudaError_t e = cudaFuncSetAttribute(k1_pairgemm_sk<NT, MW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_pairgemm_sk<NT, MW, ST>, MW * 64, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm > 2) per_sm = 2;
+  const int resident = per_sm * num_sms;
+  const long long tiles = (long long)ntr * ny;
+  // every CTA needs a range of at least one whole tile (then a tile is cut at most once)
+  int G = (int)(tiles < resident ? tiles : resident);
+  if (G < 1 || per_sm < 1 || (tiles * nk) / G < nk) return cudaSuccess;
+  K1Maps maps;
+  if (!make_map(&maps.a, p.A, rows, p.Tp, BM) || !make_map(&maps.w, p.W, ny * NB, p.Tp, NB) ||
+      !make_map(&maps.wy, p.WY, ny * NB, p.Tp, NB))
+    return cudaSuccess;
+  const size_t need = (size_t)G * NACC * (MW * 64) * sizeof(double);
+  if (need > g_sk_ws_bytes) {
+    if (g_sk_ws) cudaFree(g_sk_ws);
+    e = cudaMalloc(&g_sk_ws, need);
+    if (e != cudaSuccess) { g_sk_ws = nullptr; g_sk_ws_bytes = 0; return e; }
+    g_sk_ws_bytes = need;
+  }
+  if (G > g_sk_flags_n) {
+    if (g_sk_flags) cudaFree(g_sk_flags);
+    e = cudaMalloc(&g_sk_flags, sizeof(int) * 2048);
+    if (e != cudaSuccess) { g_sk_flags = nullptr; g_sk_flags_n = 0; return e; }
+    e = cudaMemsetAsync(g_sk_flags, 0, sizeof(int) * 2048, s);
+    if (e != cudaSuccess) return e;
+    g_sk_flags_n = 2048;
+  }
+  K1Params q = p;
+  q.nZtiles = p.nZtiles * K1_BM / BM;
+  if (ny != 1) return cudaSuccess;                   // one equation tile (M <= 104) only; wider systems fall back
+  k1_pairgemm_sk<NT, MW, ST><<<dim3(G, 1), MW * 64, smem, s>>>(q, maps, g_sk_ws, g_sk_flags, ntr);
+  *used = true;
+  return cudaGetLastError();
+}
+
 template <int NT>
 static cudaError_t launch_k1_nt(const K1Params& p, cudaStream_t s) {
   static int mw = 0;
@@ -323,6 +527,13 @@ static cudaError_t launch_k1_nt(const K1Params& p, cudaStream_t s) {
     const char* e = getenv("BVB_K1_TMA"); tma = e ? atoi(e) : 1;
     e = getenv("BVB_K1_ST"); st = e ? atoi(e) : 3;
     e = getenv("BVB_K1_MW"); mwt = e ? atoi(e) : 4;      // TMA kernel: 64-row tiles by default
+  }
+  static int sk = -1;
+  if (sk < 0) { const char* e = getenv("BVB_K1_STREAMK"); sk = e ? atoi(e) : 0; }   // off: measured 381 us vs 317 us
+  if (tma && sk && mwt == 4) {
+    bool used = false;
+    cudaError_t e = (st == 4) ? launch_k1_sk_cfg<NT, 4, 4>(p, s, &used) : launch_k1_sk_cfg<NT, 4, 3>(p, s, &used);
+    if (e != cudaSuccess || used) return e;
   }
   if (tma) {
     bool used = false;
