@@ -136,9 +136,17 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       v[0] += a; v[1] += b; v[2] += a * b; v[3] += a * a; v[4] += b * b;
     }
     block_sum<5>(v, red);
+    const SvCSums cs = {v[0], v[1], v[2], v[3], v[4]};
+    // residual sum of squares from the residuals themselves (see sv_draw_centered: the raw-sum form cancels)
+    double rss[1] = {0.0};
+    {
+      double b0 = 0.0, b1 = phi, B00, B01, B11;
+      if (!pr.mu_const) sv_centered_coef(T, cs, b0, b1, B00, B01, B11);
+      for (int t = 1 + tid; t <= T; t += SV_THREADS) { const double e = hh[t] - b0 - b1 * hh[t - 1]; rss[0] += e * e; }
+    }
+    block_sum<1>(rss, red);
     if (tid == 0) {
-      SvCSums cs = {v[0], v[1], v[2], v[3], v[4]};
-      sv_draw_centered(rng, T, cs, hh[0], mu, phi, sigma, pr);
+      sv_draw_centered(rng, T, cs, hh[0], mu, phi, sigma, pr, rss[0]);
       bc[0] = mu; bc[1] = phi; bc[2] = sigma;
     }
     __syncthreads();

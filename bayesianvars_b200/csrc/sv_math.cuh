@@ -130,16 +130,30 @@ __host__ __device__ inline void sv_awol(int T, double off, double* od, double* c
 struct SvCSums { double s_prev, s_cur, s_cross, s_prev2, s_cur2; };
 
 // Centered update of (mu, phi, sigma) given h_{0:T}.
+// Posterior mean (b0, b1) of (gamma, phi) in the centered regression h_t = gamma + phi h_{t-1} + sigma eta_t under the
+// N(0, sigma^2 diag(1/B011INV, 1/B022INV)) prior, and the posterior covariance factor B.
+__host__ __device__ inline void sv_centered_coef(int T, const SvCSums& S, double& b0, double& b1, double& B00, double& B01,
+                                                 double& B11) {
+  const double x00 = T + BVB_SV_B011INV, x01 = S.s_prev, x11 = S.s_prev2 + BVB_SV_B022INV;
+  const double det = x00 * x11 - x01 * x01;
+  B00 = x11 / det; B01 = -x01 / det; B11 = x00 / det;
+  b0 = B00 * S.s_cur + B01 * S.s_cross;
+  b1 = B01 * S.s_cur + B11 * S.s_cross;
+}
+
+// `rss`: sum_t (h_t - b0 - b1 h_{t-1})^2 (mu_const: sum_t (h_t - phi h_{t-1})^2) accumulated from the residuals.  The
+// scale of the sigma^2 draw is y'y - b'(X'X + B0^-1) b = rss + b' B0^-1 b; formed from the raw sums it cancels
+// catastrophically once a series is nearly deterministic (sigma small) and can come out <= 0, which collapsed sigma to
+// 1e-150 and the chain with it (seen after ~1900 sweeps of one test chain).  rss < 0 = not supplied: raw-sum form.
 __host__ __device__ inline void sv_draw_centered(RngStream& g, int T, const SvCSums& S, double h0, double& mu,
-                                                 double& phi, double& sigma, const SvPrior& pr) {
+                                                 double& phi, double& sigma, const SvPrior& pr, double rss = -1.0) {
   if (!pr.mu_const) {
     // 2-block: sigma^2 marginally over (gamma, phi), then (gamma, phi) | sigma^2
-    const double x00 = T + BVB_SV_B011INV, x01 = S.s_prev, x11 = S.s_prev2 + BVB_SV_B022INV;
-    const double det = x00 * x11 - x01 * x01;
-    const double B00 = x11 / det, B01 = -x01 / det, B11 = x00 / det;
-    const double b0 = B00 * S.s_cur + B01 * S.s_cross, b1 = B01 * S.s_cur + B11 * S.s_cross;
+    double b0, b1, B00, B01, B11;
+    sv_centered_coef(T, S, b0, b1, B00, B01, B11);
     const double cT = 0.5 * (T - 1.0);
-    double CT = 0.5 * (S.s_cur2 - (S.s_cur * b0 + S.s_cross * b1));
+    double CT = (rss >= 0.0) ? 0.5 * (rss + BVB_SV_B011INV * b0 * b0 + BVB_SV_B022INV * b1 * b1)
+                             : 0.5 * (S.s_cur2 - (S.s_cur * b0 + S.s_cross * b1));
     if (!(CT > 0.0)) CT = 1e-300;
     const double s2_old = sigma * sigma;
     const double s2_prop = CT / g.gamma(cT);
@@ -172,7 +186,8 @@ __host__ __device__ inline void sv_draw_centered(RngStream& g, int T, const SvCS
   } else {
     // mu fixed at 0: sigma^2 | phi, then phi | sigma^2
     const double stat0 = (pr.h0_var <= 0.0) ? (1.0 - phi * phi) * h0 * h0 : h0 * h0 / pr.h0_var;
-    double CT = 0.5 * (S.s_cur2 - 2.0 * phi * S.s_cross + phi * phi * S.s_prev2 + stat0);
+    double CT = (rss >= 0.0) ? 0.5 * (rss + stat0)
+                             : 0.5 * (S.s_cur2 - 2.0 * phi * S.s_cross + phi * phi * S.s_prev2 + stat0);
     if (!(CT > 0.0)) CT = 1e-300;
     const double cT = 0.5 * T;
     const double s2_old = sigma * sigma;
@@ -264,7 +279,15 @@ __host__ __device__ inline void sv_update_series(RngStream& g, int T, const doub
     cs.s_cur += hh[t]; cs.s_cur2 += hh[t] * hh[t];
     cs.s_cross += hh[t - 1] * hh[t];
   }
-  sv_draw_centered(g, T, cs, hh[0], mu, phi, sigma, pr);
+  double rss = 0.0;
+  if (!pr.mu_const) {
+    double b0, b1, B00, B01, B11;
+    sv_centered_coef(T, cs, b0, b1, B00, B01, B11);
+    for (int t = 1; t <= T; ++t) { const double e = hh[t] - b0 - b1 * hh[t - 1]; rss += e * e; }
+  } else {
+    for (int t = 1; t <= T; ++t) { const double e = hh[t] - phi * hh[t - 1]; rss += e * e; }
+  }
+  sv_draw_centered(g, T, cs, hh[0], mu, phi, sigma, pr, rss);
   const double mu_c = mu, sg_c = sigma;
   SvNSums ns = {0, 0, 0, 0, 0, 0, 0};
   for (int t = 1; t <= T; ++t)

@@ -84,9 +84,12 @@ def draw_theta_centered(h0, h, mu, phi, sigma, prior, rng):
     det = x00 * x11 - x01 ** 2
     B00, B01, B11 = x11 / det, -x01 / det, x00 / det
     b0, b1 = B00 * s_cur + B01 * s_cross, B01 * s_cur + B11 * s_cross
-    CT_free = np.maximum(0.5 * (s_cur2 - (s_cur * b0 + s_cross * b1)), 1e-300)
+    # y'y - b'(X'X + B0^-1) b = |y - X b|^2 + b' B0^-1 b, from the residuals: the raw-sum form cancels
+    # catastrophically for a nearly deterministic series and can come out <= 0
+    rss_free = ((h - b0[None, :] - b1[None, :] * hp) ** 2).sum(0)
+    CT_free = np.maximum(0.5 * (rss_free + B011INV * b0 ** 2 + B022INV * b1 ** 2), 1e-300)
     stat0 = np.where(stat, (1 - phi ** 2) * h0 ** 2, h0 ** 2 / np.where(stat, 1.0, h0v))
-    CT_fix = np.maximum(0.5 * (s_cur2 - 2 * phi * s_cross + phi ** 2 * s_prev2 + stat0), 1e-300)
+    CT_fix = np.maximum(0.5 * (((h - phi[None, :] * hp) ** 2).sum(0) + stat0), 1e-300)
     cT = np.where(free, 0.5 * (T - 1.0), 0.5 * T)
     CT = np.where(free, CT_free, CT_fix)
     s2_prop = CT / rng.gamma(cT)
