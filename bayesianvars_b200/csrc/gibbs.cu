@@ -66,6 +66,32 @@ __global__ void gibbs_normals_kernel(double* out, int n, int M, int ld, int j0, 
   out[(size_t)j * ld + i] = rng.normal();
 }
 
+// Start of a factor-structure sweep, one launch: blocks [0, M) build the GEMM's B operands W = exp(-h), WY = W * yhat
+// (prep.cu: prep_factor_kernel) for every equation, the remaining blocks draw the normals of the local equations.
+__global__ void __launch_bounds__(256) gibbs_prep_normals_kernel(double* __restrict__ W, double* __restrict__ WY,
+                                                                 const double* __restrict__ Y, const double* __restrict__ logvar,
+                                                                 const double* __restrict__ facload, const double* __restrict__ fac,
+                                                                 int T, int Tp, int M, int r, double* zout, int n, int Mloc,
+                                                                 int j0, uint64_t seed, const uint32_t* sweep) {
+  if ((int)blockIdx.x < M) {
+    const int j = blockIdx.x;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      double yh = Y[(size_t)j * T + t];
+      for (int k = 0; k < r; ++k) yh -= facload[(size_t)k * M + j] * fac[(size_t)t * r + k];
+      const double nrm = exp(-0.5 * logvar[(size_t)j * T + t]);   // squared like the reference's X_norm'X_norm
+      const double w = nrm * nrm;
+      W[(size_t)j * Tp + t] = w;
+      WY[(size_t)j * Tp + t] = w * yh;
+    }
+    return;
+  }
+  const size_t idx = (size_t)(blockIdx.x - M) * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * Mloc) return;
+  const int j = (int)(idx / n), i = (int)(idx % n);
+  RngStream rng(seed, STREAM_PHI_Z, (uint32_t)((size_t)(j0 + j) * n + i), *sweep);
+  zout[(size_t)j * n + i] = rng.normal();
+}
+
 // PHI_diff = PHI - PHI0 on the K lag rows, pushed away from zero for DL / GT
 // (bvar_cpp.cpp:534-559); also the non-finite check of :529-531.
 __global__ void gibbs_clamp_kernel(double* PHI, const double* PHI0, double* coef, int K, int Kp, int M,
@@ -100,24 +126,29 @@ __global__ void gibbs_scatter_V_kernel(double* Vprior, const double* V_i, int K,
   Vprior[(size_t)j * Kp + k] = V_i[idx];
 }
 
-// resid = Y - X PHI  (T x M, bvar_cpp.cpp:611).  One warp per 8 x 8 output tile:
-// DMMA m8n8k4 with both operands read straight from L2 (X 1.6 MB and PHI 0.3 MB
-// stay resident); A[m][k] = X[t0+m, k], B[k][n] = PHI[k, j0+n].
-__global__ void __launch_bounds__(128) gibbs_resid_kernel(double* __restrict__ resid, const double* __restrict__ Y,
-                                                          const double* __restrict__ X, const double* __restrict__ PHI,
-                                                          int T, int Kp, int M) {
-  const int lane = threadIdx.x & 31;
+// resid = Y - X PHI  (T x M, bvar_cpp.cpp:611).  One CTA per 8 x 8 output tile, its four warps split the Kp
+// contraction (fixed-order reduction through shared memory): DMMA m8n8k4 with both operands read straight from L2
+// (X 1.6 MB and PHI 0.3 MB stay resident); A[m][k] = X[t0+m, k], B[k][n] = PHI[k, j0+n].  The kernel is pure L2
+// latency (every trip of the k loop is one round trip), so the contraction is cut four ways: 24 -> 9 us.
+constexpr int RESID_SPLIT = 4;
+__global__ void __launch_bounds__(32 * RESID_SPLIT) gibbs_resid_kernel(double* __restrict__ resid, const double* __restrict__ Y,
+                                                                       const double* __restrict__ X, const double* __restrict__ PHI,
+                                                                       int T, int Kp, int M) {
+  __shared__ double part[RESID_SPLIT][64];
+  const int lane = threadIdx.x & 31, wk = threadIdx.x >> 5;
   const int ntj = (M + 7) / 8;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile >= ((T + 7) / 8) * ntj) return;
+  const int tile = blockIdx.x;
   const int t0 = (tile / ntj) * 8, j0 = (tile % ntj) * 8;
   const int fr = lane >> 2, fk = lane & 3;
   const int tr = min(t0 + fr, T - 1), jc = min(j0 + fr, M - 1);
   const double* xa = X + tr;
   const double* pb = PHI + (size_t)jc * Kp;
+  // this warp's slice of k: multiples of 4
+  const int steps = (Kp + 3) / 4, per = (steps + RESID_SPLIT - 1) / RESID_SPLIT;
+  const int kbeg = min(Kp, 4 * per * wk), kend = min(Kp, 4 * per * (wk + 1));
   double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-  int k = 0;
-  for (; k + 32 <= Kp; k += 32) {   // 8 k4-steps per trip: 16 independent L2 loads in flight per lane
+  int k = kbeg;
+  for (; k + 32 <= kend; k += 32) {   // 8 k4-steps per trip: 16 independent L2 loads in flight per lane
     double av[8], bv[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) { av[q] = xa[(size_t)(k + 4 * q + fk) * T]; bv[q] = pb[k + 4 * q + fk]; }
@@ -127,46 +158,71 @@ __global__ void __launch_bounds__(128) gibbs_resid_kernel(double* __restrict__ r
       dmma884(d0, d1, av[q + 1], bv[q + 1]);
     }
   }
-  for (; k < Kp; k += 4) {
-    const int kk = k + fk;
-    const double a0 = kk < Kp ? xa[(size_t)kk * T] : 0.0;
-    const double b0 = kk < Kp ? pb[kk] : 0.0;
-    dmma884(c0, c1, a0, b0);
+  {   // remainder of the slice (< 8 k4-steps), loads issued together
+    double av[8], bv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int kk = k + 4 * q + fk;
+      av[q] = kk < kend ? xa[(size_t)kk * T] : 0.0;
+      bv[q] = kk < kend ? pb[kk] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      dmma884(c0, c1, av[q], bv[q]);
+      dmma884(d0, d1, av[q + 1], bv[q + 1]);
+    }
   }
   c0 += d0; c1 += d1;
-  const int t = t0 + fr, j = j0 + 2 * fk;
-  if (t < T) {
-    if (j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - c0;
-    if (j + 1 < M) resid[(size_t)(j + 1) * T + t] = Y[(size_t)(j + 1) * T + t] - c1;
+  part[wk][fr * 8 + 2 * fk] = c0;
+  part[wk][fr * 8 + 2 * fk + 1] = c1;
+  __syncthreads();
+  if (wk == 0) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int idx = fr * 8 + 2 * fk + e;
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < RESID_SPLIT; ++w) v += part[w][idx];
+      const int t = t0 + fr, j = j0 + 2 * fk + e;
+      if (t < T && j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - v;
+    }
   }
 }
 
 cudaError_t launch_resid(double* resid, const double* Y, const double* X, const double* PHI, int T, int Kp, int M,
                          cudaStream_t s) {
   const int tiles = ((T + 7) / 8) * ((M + 7) / 8);
-  gibbs_resid_kernel<<<(tiles + 3) / 4, 128, 0, s>>>(resid, Y, X, PHI, T, Kp, M);
+  gibbs_resid_kernel<<<tiles, 32 * RESID_SPLIT, 0, s>>>(resid, Y, X, PHI, T, Kp, M);
   return cudaGetLastError();
 }
 
 // Copy the current state into slot `slot` of the device ring if this sweep is stored.
-__global__ void gibbs_store_kernel(const GibbsStore st, const uint32_t* sweep, int* nstored) {
+__global__ void gibbs_store_kernel(const GibbsStore st, uint32_t* sweep, int* nstored) {
+  // nstored[0] = highest slot written + 1; nstored[1] = blocks of this launch that are done (the last one advances
+  // the sweep counter - every block has read it by then - so there is no separate one-thread "advance" launch)
   const int rep = (int)*sweep;
-  if (rep < st.burnin || ((rep + 1 - st.burnin) % st.thin) != 0) return;
-  const int slot = (((rep + 1 - st.burnin) / st.thin) - 1) - *st.first_slot;
-  if (slot < 0 || slot >= st.ring_slots) return;
-  double* dst = st.ring + (size_t)slot * st.slot_doubles;
+  const bool stored = !(rep < st.burnin || ((rep + 1 - st.burnin) % st.thin) != 0);
+  const int slot = stored ? (((rep + 1 - st.burnin) / st.thin) - 1) - *st.first_slot : -1;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  for (int s = 0; s < st.nseg; ++s) {
-    const GibbsSeg& sg = st.seg[s];
-    for (size_t i = tid; i < (size_t)sg.rows * sg.cols; i += nth) {
-      const size_t c = i / sg.rows, rr = i % sg.rows;
-      dst[sg.dst_off + i] = sg.src[c * sg.src_ld + sg.src_row0 + rr];
+  if (slot >= 0 && slot < st.ring_slots) {
+    double* dst = st.ring + (size_t)slot * st.slot_doubles;
+    for (int s = 0; s < st.nseg; ++s) {
+      const GibbsSeg& sg = st.seg[s];
+      for (size_t i = tid; i < (size_t)sg.rows * sg.cols; i += nth) {
+        const size_t c = i / sg.rows, rr = i % sg.rows;
+        dst[sg.dst_off + i] = sg.src[c * sg.src_ld + sg.src_row0 + rr];
+      }
+    }
+    if (tid == 0) atomicMax(nstored, slot + 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(nstored + 1, 1) == (int)gridDim.x - 1) {
+      nstored[1] = 0;
+      *sweep = (uint32_t)rep + 1u;
     }
   }
-  if (tid == 0) atomicMax(nstored, slot + 1);
 }
-
-__global__ void gibbs_advance_kernel(uint32_t* sweep) { *sweep += 1; }
 
 // Cholesky structure: push |U_ij| (i < j) away from zero for DL / GT priors
 // (bvar_cpp.cpp:667-685) and gather u = U(trimatu_ind) (:688) - column-major upper
@@ -312,7 +368,12 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
                                                                    G.PHI_tol, h->seed, sw, G.status.p);
   } else if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
     // ---- 1) PHI | .  (factor structure: equations independent)
-    GB_TRY(launch_prep_factor(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p, G.fac.p, T, G.geom.Tp, M, G.r, s));
+    {
+      const size_t nz = (size_t)Kp * G.nloc;
+      gibbs_prep_normals_kernel<<<(unsigned)(M + (nz + 255) / 256), 256, 0, s>>>(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p,
+                                                                                G.fac.p, T, G.geom.Tp, M, G.r, G.Zn.p, Kp,
+                                                                                G.nloc, G.j0, h->seed, sw);
+    }
     mark(1);
     K1Params k1{};
     k1.A = G.A.p; k1.W = G.W.p + (size_t)G.j0 * G.geom.Tp; k1.WY = G.WY.p + (size_t)G.j0 * G.geom.Tp; k1.lut = G.lut.p;
@@ -321,10 +382,6 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     k1.M = G.nloc; k1.n = Kp; k1.ldo = G.geom.ldo;
     GB_TRY(launch_k1(k1, s));
     mark(2);
-    {
-      const size_t nz = (size_t)Kp * G.nloc;
-      gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, G.nloc, Kp, G.j0, h->seed, sw);
-    }
     K2Params k2{};
     k2.omega = G.omega.p; k2.colbase = G.colbase.p; k2.z = G.Zn.p; k2.phi = G.PHI.p + (size_t)G.j0 * Kp;
     k2.status = G.eqstatus.p + G.j0; k2.n = Kp; k2.M = G.nloc; k2.ldo = G.geom.ldo; k2.ldz = Kp; k2.ldphi = Kp;
@@ -369,7 +426,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   // ---- resid = Y - X PHI
   if (Kp > 0) {
     const int tiles = ((T + 7) / 8) * ((M + 7) / 8);
-    gibbs_resid_kernel<<<(tiles + 3) / 4, 128, 0, s>>>(G.resid.p, G.Y.p, G.X.p, G.PHI.p, T, Kp, M);
+    gibbs_resid_kernel<<<tiles, 32 * RESID_SPLIT, 0, s>>>(G.resid.p, G.Y.p, G.X.p, G.PHI.p, T, Kp, M);
   }
   mark(6);
   // ---- 3) Sigma_t
@@ -392,8 +449,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   mark(7);
   if (forked) GB_TRY(cudaStreamWaitEvent(s, G.ev_join, 0));
   // ---- store + advance
-  gibbs_store_kernel<<<64, 256, 0, s>>>(G.store, sw, G.nstored.p);
-  gibbs_advance_kernel<<<1, 1, 0, s>>>(G.sweep.p);
+  gibbs_store_kernel<<<64, 256, 0, s>>>(G.store, G.sweep.p, G.nstored.p);   // also advances the sweep counter
   mark(8);
   GB_TRY(cudaGetLastError());
   return BVB_OK;
@@ -482,7 +538,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   GB_TRY(G.resid.ensure((size_t)T * M));
   GB_TRY(G.status.ensure(8, true));
   GB_TRY(G.sweep.ensure(1, true));
-  GB_TRY(G.nstored.ensure(1, true));
+  GB_TRY(G.nstored.ensure(2, true));
   GB_TRY(G.eqstatus.ensure(std::max(M, 1), true));
   if (Kp > 0) {
     if ((rc = upload(h, G.X, X, (size_t)T * Kp))) return rc;
