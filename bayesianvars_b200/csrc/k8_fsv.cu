@@ -276,12 +276,29 @@ __global__ void __launch_bounds__(128) fsv_loadings_kernel(const FsvDev d, uint6
   }
 }
 
-// Interweaving (Kastner et al. 2017, section 3): one warp per factor.
-__global__ void fsv_interweave_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+// Interweaving (Kastner et al. 2017, section 3): one CTA (IW_THREADS) per factor; the column / time sums are block
+// reductions in a fixed order, the scalar draw runs on thread 0.
+constexpr int IW_THREADS = 256;
+__device__ __forceinline__ double iw_block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();                                   // sh may still be read from the previous reduction
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < IW_THREADS / 32; ++w) t += sh[w];
+  return t;
+}
+__global__ void __launch_bounds__(IW_THREADS) fsv_interweave_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+  __shared__ double sh[IW_THREADS / 32];
+  __shared__ double shb[IW_THREADS / 32];
+  __shared__ int shi[IW_THREADS / 32];
+  __shared__ double bc[3];
+  __shared__ int bci[2];
   const uint32_t sweep = *sweep_p;
-  const int j = blockIdx.x, lane = threadIdx.x & 31;
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (j >= d.r || d.interweaving == 0) return;
-  const int S = d.M + d.r;
   const bool deep = (d.interweaving == 2 || d.interweaving == 4);
   const bool largest = (d.interweaving >= 3);
   // leading element: diagonal, or the largest absolute loading of the column
@@ -289,9 +306,9 @@ __global__ void fsv_interweave_kernel(const FsvDev d, uint64_t seed, const uint3
   if (largest) {
     double best = -1.0;
     int bi = 0x7fffffff;
-    for (int i = lane; i < d.M; i += 32) {
+    for (int i = tid; i < d.M; i += IW_THREADS) {
       const double a = fabs(d.facload[(size_t)j * d.M + i]);
-      if (d.restr[(size_t)j * d.M + i] && a > best) { best = a; bi = i; }
+      if (d.restr[(size_t)j * d.M + i] && (a > best || (a == best && i < bi))) { best = a; bi = i; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {   // max |loading|, ties -> smallest row (as a serial scan would pick)
@@ -299,73 +316,86 @@ __global__ void fsv_interweave_kernel(const FsvDev d, uint64_t seed, const uint3
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (bi != 0x7fffffff) lead = bi;
+    if (lane == 0) { shb[warp] = best; shi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < IW_THREADS / 32; ++w)
+        if (shb[w] > best || (shb[w] == best && shi[w] < bi)) { best = shb[w]; bi = shi[w]; }
+      bci[0] = bi;
+    }
+    __syncthreads();
+    if (bci[0] != 0x7fffffff) lead = bci[0];
   }
   const double Lold = d.facload[(size_t)j * d.M + lead];
-  if (!(fabs(Lold) > 0.0)) return;
+  if (!(fabs(Lold) > 0.0)) return;                   // uniform: every thread reads the same value
   // column statistics: psi_s = sum_i (Lambda_ij / Lambda_lj)^2 / tau2_ij, n_j = #unrestricted
   double psis = 0.0, nj = 0.0;
-  for (int i = lane; i < d.M; i += 32) {
+  for (int i = tid; i < d.M; i += IW_THREADS) {
     if (d.restr[(size_t)j * d.M + i]) {
       const double l = d.facload[(size_t)j * d.M + i] / Lold;
       psis += l * l / d.tau2[(size_t)j * d.M + i];
       nj += 1.0;
     }
   }
-  psis = warp_sum(psis);
-  nj = warp_sum(nj);
+  psis = iw_block_sum(psis, sh);
+  nj = iw_block_sum(nj, sh);
   double* hf = d.logvar + (size_t)(d.M + j) * d.T;
-  RngStream rng(seed, STREAM_FSV_IW, (uint32_t)j, sweep);
-  double scale = 1.0;  // new Lambda_.j = scale * old, new f_j = old / scale
-  bool accept = false;
-  double mu_old = 0.0, mu_prop = 0.0;
+  double mu_old = 0.0;
+  double stat = 0.0;                                 // shallow: chi; deep: sum_t (h_t + mu) - phi (h_{t-1} + mu)
+  const bool hetero = d.hetero[d.M + j] != 0;
+  double phi = 0.0, sigma = 0.0, h0o = 0.0;
   if (!deep) {
-    // shallow: Lambda_lj^2 | f*, Lambda* ~ GIG((n_j - T)/2, sum_t f*_t^2 e^{-h_t}, psi_s)
-    double chi = 0.0;
-    for (int t = lane; t < d.T; t += 32) { const double f = d.fac[(size_t)t * d.r + j]; chi += f * f * exp(-hf[t]); }
-    chi = warp_sum(chi) * Lold * Lold;
-    const double x = gig_draw(rng, 0.5 * (nj - d.T), chi, psis);
-    if (isfinite(x) && x > 0.0) { scale = sqrt(x) / fabs(Lold); accept = true; }
-  } else if (d.hetero[d.M + j]) {
-    // deep: MH on mu* = log Lambda_lj^2 through the level of the factor log-variance
-    const double phi = d.sv_para[3 * (d.M + j) + 1], sigma = d.sv_para[3 * (d.M + j) + 2];
+    for (int t = tid; t < d.T; t += IW_THREADS) { const double f = d.fac[(size_t)t * d.r + j]; stat += f * f * exp(-hf[t]); }
+    stat = iw_block_sum(stat, sh) * Lold * Lold;
+  } else if (hetero) {
+    phi = d.sv_para[3 * (d.M + j) + 1]; sigma = d.sv_para[3 * (d.M + j) + 2];
     mu_old = log(Lold * Lold);
-    const double h0o = d.logvar0[d.M + j] + mu_old;
-    double tmph = 0.0;
-    for (int t = lane; t < d.T; t += 32) {
+    h0o = d.logvar0[d.M + j] + mu_old;
+    for (int t = tid; t < d.T; t += IW_THREADS) {
       const double prev = (t == 0) ? h0o : hf[t - 1] + mu_old;
-      tmph += (hf[t] + mu_old) - phi * prev;
+      stat += (hf[t] + mu_old) - phi * prev;
     }
-    tmph = warp_sum(tmph);
-    const double den = d.T + BVB_SV_B011INV;
-    const double gam_old = (1.0 - phi) * mu_old;
-    const double gam_prop = tmph / den + sigma / sqrt(den) * rng.normal();
-    mu_prop = gam_prop / (1.0 - phi);
-    double lr = 0.0;
-    if (d.priorh0[d.M + j] <= 0.0) {
-      const double sd0 = sigma / sqrt(1.0 - phi * phi);
-      lr += sv_log_norm(h0o, mu_prop, sd0) - sv_log_norm(h0o, mu_old, sd0);
-    } else {
-      const double sd0 = sigma * sqrt(d.priorh0[d.M + j]);
-      lr += sv_log_norm(h0o, mu_prop, sd0) - sv_log_norm(h0o, mu_old, sd0);
-    }
-    // prior of the rescaled column: x = e^mu has density x^{n_j/2 - 1} exp(-x psi_s / 2) dx
-    lr += 0.5 * nj * (mu_prop - mu_old) - 0.5 * psis * (exp(mu_prop) - exp(mu_old));
-    lr += sv_log_norm(gam_old, 0.0, sigma / sqrt(BVB_SV_B011INV)) - sv_log_norm(gam_prop, 0.0, sigma / sqrt(BVB_SV_B011INV));
-    if (log(rng.uniform()) < lr) { accept = true; scale = exp(0.5 * mu_prop) / Lold; }
+    stat = iw_block_sum(stat, sh);
   }
-  accept = __shfl_sync(0xffffffffu, accept ? 1 : 0, 0) != 0;
-  scale = __shfl_sync(0xffffffffu, scale, 0);
-  mu_prop = __shfl_sync(0xffffffffu, mu_prop, 0);
-  if (!accept) return;
-  for (int i = lane; i < d.M; i += 32) d.facload[(size_t)j * d.M + i] *= scale;
-  for (int t = lane; t < d.T; t += 32) d.fac[(size_t)t * d.r + j] /= scale;
+  if (tid == 0) {
+    RngStream rng(seed, STREAM_FSV_IW, (uint32_t)j, sweep);
+    double scale = 1.0, mu_prop = 0.0;   // new Lambda_.j = scale * old, new f_j = old / scale
+    bool accept = false;
+    if (!deep) {
+      // shallow: Lambda_lj^2 | f*, Lambda* ~ GIG((n_j - T)/2, sum_t f*_t^2 e^{-h_t}, psi_s)
+      const double x = gig_draw(rng, 0.5 * (nj - d.T), stat, psis);
+      if (isfinite(x) && x > 0.0) { scale = sqrt(x) / fabs(Lold); accept = true; }
+    } else if (hetero) {
+      // deep: MH on mu* = log Lambda_lj^2 through the level of the factor log-variance
+      const double den = d.T + BVB_SV_B011INV;
+      const double gam_old = (1.0 - phi) * mu_old;
+      const double gam_prop = stat / den + sigma / sqrt(den) * rng.normal();
+      mu_prop = gam_prop / (1.0 - phi);
+      double lr = 0.0;
+      if (d.priorh0[d.M + j] <= 0.0) {
+        const double sd0 = sigma / sqrt(1.0 - phi * phi);
+        lr += sv_log_norm(h0o, mu_prop, sd0) - sv_log_norm(h0o, mu_old, sd0);
+      } else {
+        const double sd0 = sigma * sqrt(d.priorh0[d.M + j]);
+        lr += sv_log_norm(h0o, mu_prop, sd0) - sv_log_norm(h0o, mu_old, sd0);
+      }
+      // prior of the rescaled column: x = e^mu has density x^{n_j/2 - 1} exp(-x psi_s / 2) dx
+      lr += 0.5 * nj * (mu_prop - mu_old) - 0.5 * psis * (exp(mu_prop) - exp(mu_old));
+      lr += sv_log_norm(gam_old, 0.0, sigma / sqrt(BVB_SV_B011INV)) - sv_log_norm(gam_prop, 0.0, sigma / sqrt(BVB_SV_B011INV));
+      if (log(rng.uniform()) < lr) { accept = true; scale = exp(0.5 * mu_prop) / Lold; }
+    }
+    bc[0] = scale; bc[1] = mu_prop; bci[1] = accept ? 1 : 0;
+  }
+  __syncthreads();
+  if (!bci[1]) return;
+  const double scale = bc[0], mu_prop = bc[1];
+  for (int i = tid; i < d.M; i += IW_THREADS) d.facload[(size_t)j * d.M + i] *= scale;
+  for (int t = tid; t < d.T; t += IW_THREADS) d.fac[(size_t)t * d.r + j] /= scale;
   if (deep) {
     const double shift = mu_old - mu_prop;
-    for (int t = lane; t < d.T; t += 32) hf[t] += shift;
-    if (lane == 0) d.logvar0[d.M + j] += shift;
+    for (int t = tid; t < d.T; t += IW_THREADS) hf[t] += shift;
+    if (tid == 0) d.logvar0[d.M + j] += shift;
   }
-  (void)S;
 }
 
 // Factors: T independent r-variate regressions with M observations each.
@@ -437,7 +467,7 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
       fsv_ng_kernel<<<(units + 63) / 64, 64, 0, s>>>(d, seed, sweep);
     }
     fsv_loadings_kernel<<<(d.M + 3) / 4, 128, 0, s>>>(d, seed, sweep);
-    if (d.interweaving != 0) fsv_interweave_kernel<<<d.r, 32, 0, s>>>(d, seed, sweep);
+    if (d.interweaving != 0) fsv_interweave_kernel<<<d.r, IW_THREADS, 0, s>>>(d, seed, sweep);
     {
       const size_t per_slice = (size_t)(d.r * (d.r + 1) / 2 + d.r) * 32 * sizeof(double);
       int nsl = FAC_SLICES;
