@@ -75,61 +75,102 @@ __host__ __device__ inline double gig_rou_shift(RngStream& g, double lambda, dou
 // Three-part hat for 0 <= lambda < 1 and small omega (Hoermann & Leydold, Alg. 3).  This is the branch the DL / NG /
 // R2D2 local scales hit for coefficients shrunk to zero, i.e. almost all of them, so it is written in log space:
 // x^y as exp(y log x) with the logs shared (no pow), the hat value carried as its logarithm so the acceptance test
-// needs no exp, and log X produced by the inversion itself where possible.  Two uniforms per attempt as before.
-__host__ __device__ inline double gig_newapproach(RngStream& g, double lambda, double omega) {
-  const double xm = gig_mode(lambda, omega);
-  const double x0 = omega / (1.0 - lambda);
-  const double lm1 = lambda - 1.0, hw = 0.5 * omega;
-  const double lk0 = lm1 * log(xm) - hw * (xm + 1.0 / xm);      // log k0
-  const double A0 = exp(lk0) * x0;
-  const double lx0 = log(x0), l2w = log(2.0 / omega);
-  const bool two = (x0 >= 2.0 / omega);                          // no middle part
-  double lk1 = 0.0, A1 = 0.0, lk2, A2, x0lam = 0.0, k1inv = 0.0;
+// needs no exp, and log X produced by the inversion itself where possible.  One attempt consumes exactly one Philox
+// block (two uniforms), so attempt number a of a draw is a pure function of (stream, counter base + a): the warp form
+// below evaluates 32 attempts at once and takes the first accepted one - the same variate the serial loop returns.
+struct GigHat {
+  double lambda, omega, xm, x0, lm1, hw, lk0, A0, lk1, A1, lk2, A2, x0lam, k1inv, Atot, ea, c2;
+};
+__host__ __device__ inline GigHat gig_hat_setup(double lambda, double omega) {
+  GigHat h;
+  h.lambda = lambda; h.omega = omega;
+  h.xm = gig_mode(lambda, omega);
+  h.x0 = omega / (1.0 - lambda);
+  h.lm1 = lambda - 1.0; h.hw = 0.5 * omega;
+  h.lk0 = h.lm1 * log(h.xm) - h.hw * (h.xm + 1.0 / h.xm);      // log k0
+  h.A0 = exp(h.lk0) * h.x0;
+  const double lx0 = log(h.x0), l2w = log(2.0 / omega);
+  const bool two = (h.x0 >= 2.0 / omega);                        // no middle part
+  h.lk1 = 0.0; h.A1 = 0.0; h.x0lam = 0.0; h.k1inv = 0.0;
   if (two) {
-    lk2 = lm1 * lx0;
-    A2 = exp(lk2 - hw * x0) * 2.0 / omega;
+    h.lk2 = h.lm1 * lx0;
+    h.A2 = exp(h.lk2 - h.hw * h.x0) * 2.0 / omega;
   } else {
-    lk1 = -omega;
-    const double k1 = exp(lk1);
-    k1inv = 1.0 / k1;
-    if (lambda == 0.0) A1 = k1 * (2.0 * l2w - 0.6931471805599453);   // k1 log(2 / omega^2)
-    else { x0lam = exp(lambda * lx0); A1 = k1 / lambda * (exp(lambda * l2w) - x0lam); }
-    lk2 = lm1 * l2w;
-    A2 = exp(lk2 - 1.0) * 2.0 / omega;
+    h.lk1 = -omega;
+    const double k1 = exp(h.lk1);
+    h.k1inv = 1.0 / k1;
+    if (lambda == 0.0) h.A1 = k1 * (2.0 * l2w - 0.6931471805599453);   // k1 log(2 / omega^2)
+    else { h.x0lam = exp(lambda * lx0); h.A1 = k1 / lambda * (exp(lambda * l2w) - h.x0lam); }
+    h.lk2 = h.lm1 * l2w;
+    h.A2 = exp(h.lk2 - 1.0) * 2.0 / omega;
   }
-  const double Atot = A0 + A1 + A2;
-  const double aa = two ? x0 : 2.0 / omega;
-  const double ea = exp(-hw * aa), c2 = omega / (2.0 * exp(lk2));
-  double X = xm;
-  for (int it = 0; it < 100000; ++it) {
-    double V = Atot * g.uniform();
-    double lhx, lX;
-    if (V <= A0) {
-      X = x0 * V / A0;
-      lX = log(X);
-      lhx = lk0;
+  h.Atot = h.A0 + h.A1 + h.A2;
+  const double aa = two ? h.x0 : 2.0 / omega;
+  h.ea = exp(-h.hw * aa);
+  h.c2 = omega / (2.0 * exp(h.lk2));
+  return h;
+}
+// one attempt from the uniforms (u1, u2); true = accepted, X the candidate
+__host__ __device__ inline bool gig_hat_attempt(const GigHat& h, double u1, double u2, double& X) {
+  double V = h.Atot * u1;
+  double lhx, lX;
+  if (V <= h.A0) {
+    X = h.x0 * V / h.A0;
+    lX = log(X);
+    lhx = h.lk0;
+  } else {
+    V -= h.A0;
+    if (V <= h.A1) {
+      if (h.lambda == 0.0) lX = log(h.omega) + h.k1inv * V;                   // X = omega exp(exp(omega) V)
+      else lX = log(h.x0lam + h.lambda * h.k1inv * V) / h.lambda;             // X = (x0^lambda + lambda V / k1)^(1/lambda)
+      X = exp(lX);
+      lhx = h.lk1 + h.lm1 * lX;                                               // hat = k1 X^(lambda-1)
     } else {
-      V -= A0;
-      if (V <= A1) {
-        if (lambda == 0.0) {
-          lX = log(omega) + k1inv * V;                          // X = omega exp(exp(omega) V)
-          X = exp(lX);
-        } else {
-          lX = log(x0lam + lambda * k1inv * V) / lambda;          // X = (x0^lambda + lambda V / k1)^(1/lambda)
-          X = exp(lX);
-        }
-        lhx = lk1 + lm1 * lX;                                     // hat = k1 X^(lambda-1)
-      } else {
-        V -= A1;
-        X = -2.0 / omega * log(ea - c2 * V);
-        lX = log(X);
-        lhx = lk2 - hw * X;                                       // hat = k2 exp(-omega X / 2)
-      }
+      V -= h.A1;
+      X = -2.0 / h.omega * log(h.ea - h.c2 * V);
+      lX = log(X);
+      lhx = h.lk2 - h.hw * X;                                                 // hat = k2 exp(-omega X / 2)
     }
-    if (log(g.uniform()) + lhx <= lm1 * lX - hw * (X + 1.0 / X)) break;
+  }
+  return log(u2) + lhx <= h.lm1 * lX - h.hw * (X + 1.0 / X);
+}
+__host__ __device__ inline double gig_newapproach(RngStream& g, double lambda, double omega) {
+  const GigHat h = gig_hat_setup(lambda, omega);
+  g.have = 0;                                          // attempts start on a Philox block boundary
+  double X = h.xm;
+  for (int it = 0; it < 100000; ++it) {
+    const double u1 = g.uniform(), u2 = g.uniform();
+    if (gig_hat_attempt(h, u1, u2, X)) break;
   }
   return X;
 }
+#ifdef __CUDACC__
+// Warp form: all 32 lanes hold the SAME stream state; returns the same variate in every lane and leaves the
+// stream where the serial loop would have left it.
+__device__ inline double gig_newapproach_warp(RngStream& g, double lambda, double omega, int lane) {
+  const GigHat h = gig_hat_setup(lambda, omega);
+  g.have = 0;
+  const uint32_t c0 = g.ctr;
+  double X = h.xm;
+  for (int round = 0; round < 3200; ++round) {
+    RngStream a = g;
+    a.ctr = c0 + (uint32_t)(round * 32 + lane);
+    a.have = 0;
+    const double u1 = a.uniform(), u2 = a.uniform();
+    double Xt;
+    const bool ok = gig_hat_attempt(h, u1, u2, Xt);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) {
+      const int w = __ffs(m) - 1;
+      X = __shfl_sync(0xffffffffu, Xt, w);
+      g.ctr = c0 + (uint32_t)(round * 32 + w + 1);
+      g.have = 0;
+      break;
+    }
+  }
+  return X;
+}
+#endif
 
 // Inverse Gaussian IG(mean mu, shape sh) by the transformation of Michael, Schucany & Haas (1976), smaller root in
 // its cancellation-free form.  GIG(-1/2, chi, psi) = IG(sqrt(chi/psi), chi) exactly, and GIG(1/2, chi, psi) is its
@@ -167,5 +208,22 @@ __host__ __device__ inline double gig_draw(RngStream& g, double lambda, double c
   else X = gig_newapproach(g, lambda, omega);
   return (lambda_old < 0.0) ? alpha / X : alpha * X;
 }
+
+#ifdef __CUDACC__
+// gig_draw called by the 32 lanes of a warp together, every lane with the same stream state and arguments: the
+// rejection loop of the three-part hat (whose worst lane would otherwise set the pace of the whole kernel) runs 32
+// attempts at a time; the other branches are simply evaluated redundantly.  Same variate as gig_draw.
+__device__ inline double gig_draw_warp(RngStream& g, double lambda, double chi, double psi, int lane) {
+  if (!(isfinite(lambda) && isfinite(chi) && isfinite(psi)) || chi < 0.0 || psi < 0.0 ||
+      (chi == 0.0 && lambda <= 0.0) || (psi == 0.0 && lambda >= 0.0))
+    return nan("");
+  if (chi < BVB_GIG_ZTOL || psi < BVB_GIG_ZTOL || lambda == -0.5 || lambda == 0.5) return gig_draw(g, lambda, chi, psi);
+  const double la = fabs(lambda);
+  const double alpha = sqrt(chi / psi), omega = sqrt(psi * chi);
+  if (la > 2.0 || omega > 3.0 || la >= 1.0 - 2.25 * omega * omega || omega > 0.2) return gig_draw(g, lambda, chi, psi);
+  const double X = gig_newapproach_warp(g, la, omega, lane);
+  return (lambda < 0.0) ? alpha / X : alpha * X;
+}
+#endif
 
 }  // namespace bvb
