@@ -124,7 +124,66 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
     for (int t = tid; t <= T; t += SV_THREADS)
       sv_system_row(t, T, t > 0 ? ys[t - 1] : 0.0, t > 0 ? rr[t - 1] : 0, mu, phi, s2inv, B0inv, od[t], c[t]);
     __syncthreads();
-    if (tid == 0) sv_awol(T, -phi * s2inv, od, c, lo, ep, hh);
+    // AWOL draw with a TWISTED factorisation of the tridiagonal precision (eliminate from both ends towards the
+    // middle row m, substitute from m outwards): the same law as sv_awol's one-sided Cholesky - any factor F with
+    // F F' = Omega maps N(0, I) noise to N(0, Omega^-1) - but two threads (in different warps) each walk half of the
+    // dependent chain, which is what the kernel's time is made of (1002 steps x ~70 cycles on one thread).
+    {
+      const double off = -phi * s2inv;
+      const int m = (T + 1) / 2;                       // rows 0..m-1 from the top, T..m+1 from the bottom
+      if (tid == 0) {
+        double lprev = 0.0, aprev = 0.0;
+        double od_n = od[0], c_n = c[0];
+        for (int t = 0; t < m; ++t) {
+          const double od_t = od_n, c_t = c_n;
+          od_n = od[t + 1]; c_n = c[t + 1];
+          const double ri = rsqrt(od_t - lprev * lprev);
+          const double at = (c_t - lprev * aprev) * ri;
+          od[t] = ri; c[t] = at;
+          lprev = off * ri;
+          lo[t] = lprev;                               // couples row t with row t+1
+          aprev = at;
+        }
+      } else if (tid == 32) {
+        double lprev = 0.0, aprev = 0.0;
+        double od_n = od[T], c_n = c[T];
+        for (int t = T; t > m; --t) {
+          const double od_t = od_n, c_t = c_n;
+          od_n = od[t - 1]; c_n = c[t - 1];
+          const double ri = rsqrt(od_t - lprev * lprev);
+          const double at = (c_t - lprev * aprev) * ri;
+          od[t] = ri; c[t] = at;
+          lprev = off * ri;
+          lo[t] = lprev;                               // couples row t with row t-1
+          aprev = at;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {                                  // middle row: both neighbours are eliminated
+        const double lu = (m > 0) ? lo[m - 1] : 0.0, au = (m > 0) ? c[m - 1] : 0.0;
+        const double ld = (m < T) ? lo[m + 1] : 0.0, ad = (m < T) ? c[m + 1] : 0.0;
+        const double ri = rsqrt(od[m] - lu * lu - ld * ld);
+        const double at = (c[m] - lu * au - ld * ad) * ri;
+        od[m] = ri; c[m] = at;
+        hh[m] = (at + ep[m]) * ri;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double hnext = hh[m];
+        for (int t = m - 1; t >= 0; --t) {
+          const double ht = (c[t] + ep[t] - lo[t] * hnext) * od[t];
+          hh[t] = ht;
+          hnext = ht;
+        }
+      } else if (tid == 32) {
+        double hprev = hh[m];
+        for (int t = m + 1; t <= T; ++t) {
+          const double ht = (c[t] + ep[t] - lo[t] * hprev) * od[t];
+          hh[t] = ht;
+          hprev = ht;
+        }
+      }
+    }
     __syncthreads();
   }
   // (b) centered draw
