@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[8 * (SV_THREADS / 32)];
   __shared__ double bc[4];
+  __shared__ SvVariates rvs;
   const uint32_t sweep = *sweep_p;
   const int S = d.M + d.r, T = d.T, tid = threadIdx.x;
   const int s = blockIdx.x;
@@ -144,6 +145,25 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
           lo[t] = lprev;                               // couples row t with row t+1
           aprev = at;
         }
+      } else if (tid >= 64 && tid < 69) {
+        // Meanwhile warps 2 and 3 draw the variates of the parameter updates (they do not depend on the state): the
+        // five normals in lock step on five lanes of warp 2, the three log-uniforms and the gamma on warp 3.
+        // Disjoint counter ranges of the series' stream.
+        RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+        gq.ctr = 16u * (uint32_t)(tid - 64 + 1);
+        const double z = gq.normal();
+        double* dst[5] = {&rvs.z1, &rvs.z2, &rvs.nz1, &rvs.nz0, &rvs.nzphi};
+        *dst[tid - 64] = z;
+      } else if (tid >= 96 && tid < 99) {
+        RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+        gq.ctr = 16u * (uint32_t)(tid - 96 + 8);
+        const double lu = log(gq.uniform());
+        double* dst[3] = {&rvs.lu_s2, &rvs.lu_mh, &rvs.nlu};
+        *dst[tid - 96] = lu;
+      } else if (tid == 99) {
+        RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+        gq.ctr = 4096u;
+        rvs.gam = gq.gamma(sv_gamma_shape(T, pr));
       } else if (tid == 32) {
         double lprev = 0.0, aprev = 0.0;
         double od_n = od[T], c_n = c[T];
@@ -187,7 +207,6 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
     __syncthreads();
   }
   // (b) centered draw
-  RngStream rng(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
   {
     double v[5] = {0, 0, 0, 0, 0};
     for (int t = 1 + tid; t <= T; t += SV_THREADS) {
@@ -204,9 +223,10 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       for (int t = 1 + tid; t <= T; t += SV_THREADS) { const double e = hh[t] - b0 - b1 * hh[t - 1]; rss[0] += e * e; }
     }
     block_sum<1>(rss, red);
-    if (tid == 0) {
-      sv_draw_centered(rng, T, cs, hh[0], mu, phi, sigma, pr, rss[0]);
-      bc[0] = mu; bc[1] = phi; bc[2] = sigma;
+    if (tid < 32) {   // warp 0, all lanes with identical arguments: the lanes share the terms of the MH ratio
+      const SvVariates rv = rvs;
+      sv_draw_centered(rv, T, cs, hh[0], mu, phi, sigma, pr, rss[0], tid);
+      if (tid == 0) { bc[0] = mu; bc[1] = phi; bc[2] = sigma; }
     }
     __syncthreads();
     mu = bc[0]; phi = bc[1]; sigma = bc[2];
@@ -219,11 +239,12 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       sv_nc_accumulate(ns, (hh[t] - mu_c) / sg_c, (hh[t - 1] - mu_c) / sg_c, ys[t - 1], rr[t - 1]);
     double v[7] = {ns.p00, ns.p01, ns.p11, ns.l0, ns.l1, ns.n_prev2, ns.n_cross};
     block_sum<7>(v, red);
-    if (tid == 0) {
+    if (tid < 32) {
+      const SvVariates rv = rvs;
       SvNSums tot = {v[0], v[1], v[2], v[3], v[4], v[5], v[6]};
       double mu_n, sg_n;
-      sv_draw_noncentered(rng, tot, (hh[0] - mu_c) / sg_c, mu_n, sg_n, phi, pr);
-      bc[0] = mu_n; bc[1] = sg_n; bc[2] = phi;
+      sv_draw_noncentered(rv, tot, (hh[0] - mu_c) / sg_c, mu_n, sg_n, phi, pr, tid);
+      if (tid == 0) { bc[0] = mu_n; bc[1] = sg_n; bc[2] = phi; }
     }
     __syncthreads();
     const double mu_n = bc[0], sg_n = bc[1];

@@ -68,6 +68,49 @@ __host__ __device__ inline int sv_draw_indicator(double resid /* y*_t - h_t */, 
   return r;
 }
 
+// Sum of n independent terms term(k), k < n.  lane < 0: one thread evaluates them in order (host, tests).
+// lane >= 0 (device): the 32 lanes of a warp call this together with IDENTICAL arguments; lane k evaluates term k and
+// the warp adds them up - the log-density terms of an MH ratio are independent chains of log / divide.
+template <class F>
+__host__ __device__ inline double sv_sum_terms(int n, int lane, F term) {
+#ifdef __CUDA_ARCH__
+  if (lane >= 0) {
+    double v = (lane < n) ? term(lane) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+#endif
+  double t = 0.0;
+  for (int k = 0; k < n; ++k) t += term(k);
+  return t;
+}
+
+// The random variates one series consumes in its parameter updates.  They do not depend on the state, so the
+// device draws them on otherwise idle warps WHILE the AWOL chains run and hands them to the update functions; the
+// host (tests) draws them in this order from one stream.
+struct SvVariates {
+  double gam;      // Gamma(cT, 1) of the sigma^2 proposal (centered)
+  double lu_s2;    // log U of the sigma^2 independence-MH step
+  double z1, z2;   // N(0,1): phi and gamma proposals (centered)
+  double lu_mh;    // log U of the (gamma, phi) MH step
+  double nz1, nz0; // N(0,1): sigma and mu draws (non-centered)
+  double nzphi;    // N(0,1): phi proposal (non-centered)
+  double nlu;      // log U of the non-centered phi MH step
+};
+__host__ __device__ inline double sv_gamma_shape(int T, const SvPrior& pr) { return pr.mu_const ? 0.5 * T : 0.5 * (T - 1.0); }
+__host__ __device__ inline void sv_draw_variates(RngStream& g, int T, const SvPrior& pr, SvVariates& v) {
+  v.gam = g.gamma(sv_gamma_shape(T, pr));
+  v.lu_s2 = log(g.uniform());
+  v.z1 = g.normal();
+  v.z2 = g.normal();
+  v.lu_mh = log(g.uniform());
+  v.nz1 = g.normal();
+  v.nz0 = g.normal();
+  v.nzphi = g.normal();
+  v.nlu = log(g.uniform());
+}
+
 __host__ __device__ inline double sv_log_beta_kernel(double phi, double a, double b) {
   // log density kernel of (phi+1)/2 ~ Beta(a, b)
   return (a - 1.0) * log(0.5 * (1.0 + phi)) + (b - 1.0) * log(0.5 * (1.0 - phi));
@@ -145,43 +188,47 @@ __host__ __device__ inline void sv_centered_coef(int T, const SvCSums& S, double
 // scale of the sigma^2 draw is y'y - b'(X'X + B0^-1) b = rss + b' B0^-1 b; formed from the raw sums it cancels
 // catastrophically once a series is nearly deterministic (sigma small) and can come out <= 0, which collapsed sigma to
 // 1e-150 and the chain with it (seen after ~1900 sweeps of one test chain).  rss < 0 = not supplied: raw-sum form.
-__host__ __device__ inline void sv_draw_centered(RngStream& g, int T, const SvCSums& S, double h0, double& mu,
-                                                 double& phi, double& sigma, const SvPrior& pr, double rss = -1.0) {
+__host__ __device__ inline void sv_draw_centered(const SvVariates& rv, int T, const SvCSums& S, double h0, double& mu,
+                                                 double& phi, double& sigma, const SvPrior& pr, double rss = -1.0,
+                                                 int lane = -1) {
   if (!pr.mu_const) {
     // 2-block: sigma^2 marginally over (gamma, phi), then (gamma, phi) | sigma^2
     double b0, b1, B00, B01, B11;
     sv_centered_coef(T, S, b0, b1, B00, B01, B11);
-    const double cT = 0.5 * (T - 1.0);
     double CT = (rss >= 0.0) ? 0.5 * (rss + BVB_SV_B011INV * b0 * b0 + BVB_SV_B022INV * b1 * b1)
                              : 0.5 * (S.s_cur2 - (S.s_cur * b0 + S.s_cross * b1));
     if (!(CT > 0.0)) CT = 1e-300;
     const double s2_old = sigma * sigma;
-    const double s2_prop = CT / g.gamma(cT);
-    if (log(g.uniform()) < (s2_old - s2_prop) * pr.s2_rate) sigma = sqrt(s2_prop);
+    const double s2_prop = CT / rv.gam;
+    if (rv.lu_s2 < (s2_old - s2_prop) * pr.s2_rate) sigma = sqrt(s2_prop);
     // (gamma, phi) ~ N(b, sigma^2 B)
     const double sg = sigma;
-    const double phi_prop = b1 + sg * sqrt(B11) * g.normal();
+    const double phi_prop = b1 + sg * sqrt(B11) * rv.z1;
     const double cm = b0 + B01 / B11 * (phi_prop - b1);
     double cv = B00 - B01 * B01 / B11;
     if (cv < 0.0) cv = 0.0;
-    const double gam_prop = cm + sg * sqrt(cv) * g.normal();
-    const double u = g.uniform();
+    const double gam_prop = cm + sg * sqrt(cv) * rv.z2;
     if (phi_prop > -1.0 && phi_prop < 1.0) {
       const double gam_old = mu * (1.0 - phi);
       const double mu_prop = gam_prop / (1.0 - phi_prop);
-      double lr = 0.0;
-      if (pr.h0_var <= 0.0) {
-        lr += sv_log_norm(h0, mu_prop, sg / sqrt(1.0 - phi_prop * phi_prop)) -
-              sv_log_norm(h0, mu, sg / sqrt(1.0 - phi * phi));
-      } else {
-        lr += sv_log_norm(h0, mu_prop, sg * sqrt(pr.h0_var)) - sv_log_norm(h0, mu, sg * sqrt(pr.h0_var));
-      }
-      lr += sv_log_norm(gam_prop, pr.mu_mean * (1.0 - phi_prop), pr.mu_sd * (1.0 - phi_prop)) -
-            sv_log_norm(gam_old, pr.mu_mean * (1.0 - phi), pr.mu_sd * (1.0 - phi));
-      lr += sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b) - sv_log_beta_kernel(phi, pr.phi_a, pr.phi_b);
-      lr += sv_log_norm(gam_old, 0.0, sg / sqrt(BVB_SV_B011INV)) - sv_log_norm(gam_prop, 0.0, sg / sqrt(BVB_SV_B011INV));
-      lr += sv_log_norm(phi, 0.0, sg / sqrt(BVB_SV_B022INV)) - sv_log_norm(phi_prop, 0.0, sg / sqrt(BVB_SV_B022INV));
-      if (log(u) < lr) { mu = mu_prop; phi = phi_prop; }
+      const double mu_o = mu, phi_o = phi;
+      const double lr = sv_sum_terms(10, lane, [&](int k) -> double {
+        switch (k) {
+          case 0: return (pr.h0_var <= 0.0) ? sv_log_norm(h0, mu_prop, sg / sqrt(1.0 - phi_prop * phi_prop))
+                                            : sv_log_norm(h0, mu_prop, sg * sqrt(pr.h0_var));
+          case 1: return (pr.h0_var <= 0.0) ? -sv_log_norm(h0, mu_o, sg / sqrt(1.0 - phi_o * phi_o))
+                                            : -sv_log_norm(h0, mu_o, sg * sqrt(pr.h0_var));
+          case 2: return sv_log_norm(gam_prop, pr.mu_mean * (1.0 - phi_prop), pr.mu_sd * (1.0 - phi_prop));
+          case 3: return -sv_log_norm(gam_old, pr.mu_mean * (1.0 - phi_o), pr.mu_sd * (1.0 - phi_o));
+          case 4: return sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b);
+          case 5: return -sv_log_beta_kernel(phi_o, pr.phi_a, pr.phi_b);
+          case 6: return sv_log_norm(gam_old, 0.0, sg / sqrt(BVB_SV_B011INV));
+          case 7: return -sv_log_norm(gam_prop, 0.0, sg / sqrt(BVB_SV_B011INV));
+          case 8: return sv_log_norm(phi_o, 0.0, sg / sqrt(BVB_SV_B022INV));
+          default: return -sv_log_norm(phi_prop, 0.0, sg / sqrt(BVB_SV_B022INV));
+        }
+      });
+      if (rv.lu_mh < lr) { mu = mu_prop; phi = phi_prop; }
     }
   } else {
     // mu fixed at 0: sigma^2 | phi, then phi | sigma^2
@@ -189,21 +236,25 @@ __host__ __device__ inline void sv_draw_centered(RngStream& g, int T, const SvCS
     double CT = (rss >= 0.0) ? 0.5 * (rss + stat0)
                              : 0.5 * (S.s_cur2 - 2.0 * phi * S.s_cross + phi * phi * S.s_prev2 + stat0);
     if (!(CT > 0.0)) CT = 1e-300;
-    const double cT = 0.5 * T;
     const double s2_old = sigma * sigma;
-    const double s2_prop = CT / g.gamma(cT);
-    if (log(g.uniform()) < (s2_old - s2_prop) * pr.s2_rate) sigma = sqrt(s2_prop);
+    const double s2_prop = CT / rv.gam;
+    if (rv.lu_s2 < (s2_old - s2_prop) * pr.s2_rate) sigma = sqrt(s2_prop);
     const double sg = sigma;
     const double den = S.s_prev2 + BVB_SV_B022INV;
-    const double phi_prop = S.s_cross / den + sg / sqrt(den) * g.normal();
-    const double u = g.uniform();
+    const double phi_prop = S.s_cross / den + sg / sqrt(den) * rv.z1;
     if (phi_prop > -1.0 && phi_prop < 1.0) {
-      double lr = 0.0;
-      if (pr.h0_var <= 0.0)
-        lr += sv_log_norm(h0, 0.0, sg / sqrt(1.0 - phi_prop * phi_prop)) - sv_log_norm(h0, 0.0, sg / sqrt(1.0 - phi * phi));
-      lr += sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b) - sv_log_beta_kernel(phi, pr.phi_a, pr.phi_b);
-      lr += sv_log_norm(phi, 0.0, sg / sqrt(BVB_SV_B022INV)) - sv_log_norm(phi_prop, 0.0, sg / sqrt(BVB_SV_B022INV));
-      if (log(u) < lr) phi = phi_prop;
+      const double phi_o = phi;
+      const double lr = sv_sum_terms(6, lane, [&](int k) -> double {
+        switch (k) {
+          case 0: return (pr.h0_var <= 0.0) ? sv_log_norm(h0, 0.0, sg / sqrt(1.0 - phi_prop * phi_prop)) : 0.0;
+          case 1: return (pr.h0_var <= 0.0) ? -sv_log_norm(h0, 0.0, sg / sqrt(1.0 - phi_o * phi_o)) : 0.0;
+          case 2: return sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b);
+          case 3: return -sv_log_beta_kernel(phi_o, pr.phi_a, pr.phi_b);
+          case 4: return sv_log_norm(phi_o, 0.0, sg / sqrt(BVB_SV_B022INV));
+          default: return -sv_log_norm(phi_prop, 0.0, sg / sqrt(BVB_SV_B022INV));
+        }
+      });
+      if (rv.lu_mh < lr) phi = phi_prop;
     }
   }
 }
@@ -223,8 +274,8 @@ __host__ __device__ inline void sv_nc_accumulate(SvNSums& S, double x_t, double 
 
 // Non-centered update: (mu, sigma) | htilde (Gaussian), then phi | htilde.
 // Returns the signed sigma draw in sg_n (h = mu + sigma*htilde is invariant to its sign).
-__host__ __device__ inline void sv_draw_noncentered(RngStream& g, const SvNSums& S, double ht0, double& mu_n,
-                                                    double& sg_n, double& phi, const SvPrior& pr) {
+__host__ __device__ inline void sv_draw_noncentered(const SvVariates& rv, const SvNSums& S, double ht0, double& mu_n,
+                                                    double& sg_n, double& phi, const SvPrior& pr, int lane = -1) {
   const double Bsig_inv = 2.0 * pr.s2_rate;   // sigma^2 ~ Gamma(1/2, rate) <=> sigma ~ N(0, 1/(2 rate))
   if (!pr.mu_const) {
     const double p00 = S.p00 + 1.0 / (pr.mu_sd * pr.mu_sd), p01 = S.p01, p11 = S.p11 + Bsig_inv;
@@ -232,26 +283,30 @@ __host__ __device__ inline void sv_draw_noncentered(RngStream& g, const SvNSums&
     const double det = p00 * p11 - p01 * p01;
     const double C00 = p11 / det, C01 = -p01 / det, C11 = p00 / det;
     const double m0 = C00 * l0 + C01 * l1, m1 = C01 * l0 + C11 * l1;
-    const double z1 = g.normal(), z0 = g.normal();
-    sg_n = m1 + sqrt(C11) * z1;
+    sg_n = m1 + sqrt(C11) * rv.nz1;
     double cv = C00 - C01 * C01 / C11;
     if (cv < 0.0) cv = 0.0;
-    mu_n = m0 + C01 / C11 * (sg_n - m1) + sqrt(cv) * z0;
+    mu_n = m0 + C01 / C11 * (sg_n - m1) + sqrt(cv) * rv.nz0;
   } else {
     const double p11 = S.p11 + Bsig_inv;
     mu_n = 0.0;
-    sg_n = S.l1 / p11 + g.normal() / sqrt(p11);
+    sg_n = S.l1 / p11 + rv.nz1 / sqrt(p11);
   }
   const double den = S.n_prev2 + BVB_SV_B022INV;
-  const double phi_prop = S.n_cross / den + g.normal() / sqrt(den);
-  const double u = g.uniform();
+  const double phi_prop = S.n_cross / den + rv.nzphi / sqrt(den);
   if (phi_prop > -1.0 && phi_prop < 1.0) {
-    double lr = 0.0;
-    if (pr.h0_var <= 0.0)
-      lr += sv_log_norm(ht0, 0.0, 1.0 / sqrt(1.0 - phi_prop * phi_prop)) - sv_log_norm(ht0, 0.0, 1.0 / sqrt(1.0 - phi * phi));
-    lr += sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b) - sv_log_beta_kernel(phi, pr.phi_a, pr.phi_b);
-    lr += sv_log_norm(phi, 0.0, 1.0 / sqrt(BVB_SV_B022INV)) - sv_log_norm(phi_prop, 0.0, 1.0 / sqrt(BVB_SV_B022INV));
-    if (log(u) < lr) phi = phi_prop;
+    const double phi_o = phi;
+    const double lr = sv_sum_terms(6, lane, [&](int k) -> double {
+      switch (k) {
+        case 0: return (pr.h0_var <= 0.0) ? sv_log_norm(ht0, 0.0, 1.0 / sqrt(1.0 - phi_prop * phi_prop)) : 0.0;
+        case 1: return (pr.h0_var <= 0.0) ? -sv_log_norm(ht0, 0.0, 1.0 / sqrt(1.0 - phi_o * phi_o)) : 0.0;
+        case 2: return sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b);
+        case 3: return -sv_log_beta_kernel(phi_o, pr.phi_a, pr.phi_b);
+        case 4: return sv_log_norm(phi_o, 0.0, 1.0 / sqrt(BVB_SV_B022INV));
+        default: return -sv_log_norm(phi_prop, 0.0, 1.0 / sqrt(BVB_SV_B022INV));
+      }
+    });
+    if (rv.nlu < lr) phi = phi_prop;
   }
 }
 
@@ -287,13 +342,15 @@ __host__ __device__ inline void sv_update_series(RngStream& g, int T, const doub
   } else {
     for (int t = 1; t <= T; ++t) { const double e = hh[t] - phi * hh[t - 1]; rss += e * e; }
   }
-  sv_draw_centered(g, T, cs, hh[0], mu, phi, sigma, pr, rss);
+  SvVariates rv;
+  sv_draw_variates(g, T, pr, rv);
+  sv_draw_centered(rv, T, cs, hh[0], mu, phi, sigma, pr, rss);
   const double mu_c = mu, sg_c = sigma;
   SvNSums ns = {0, 0, 0, 0, 0, 0, 0};
   for (int t = 1; t <= T; ++t)
     sv_nc_accumulate(ns, (hh[t] - mu_c) / sg_c, (hh[t - 1] - mu_c) / sg_c, ystar[t - 1], r[t - 1]);
   double mu_n, sg_n;
-  sv_draw_noncentered(g, ns, (hh[0] - mu_c) / sg_c, mu_n, sg_n, phi, pr);
+  sv_draw_noncentered(rv, ns, (hh[0] - mu_c) / sg_c, mu_n, sg_n, phi, pr);
   for (int t = 1; t <= T; ++t) h[t - 1] = mu_n + sg_n * ((hh[t] - mu_c) / sg_c);
   h0 = mu_n + sg_n * ((hh[0] - mu_c) / sg_c);
   mu = mu_n;
