@@ -14,7 +14,7 @@
 
 namespace bvb {
 
-constexpr int IRF_SC = 8;       // shocks per CTA
+constexpr int IRF_SC_MAX = 8;   // shocks per CTA: 1, 2, 4 or 8 (template parameter: a factor model has r shocks)
 constexpr int IRF_THREADS = 256;
 
 struct IrfParams {
@@ -28,6 +28,7 @@ struct IrfParams {
   int Kp, M, R, nf, hasU, ld, dim, n_shocks, ahead;
 };
 
+template <int IRF_SC>
 __global__ void __launch_bounds__(IRF_THREADS) irf_kernel(const IrfParams p) {
   extern __shared__ double sm[];
   const int M = p.M, Kp = p.Kp;
@@ -102,7 +103,20 @@ __global__ void __launch_bounds__(IRF_THREADS) irf_kernel(const IrfParams p) {
       double acc[IRF_SC];
 #pragma unroll
       for (int s = 0; s < IRF_SC; ++s) acc[s] = 0.0;
-      for (int k = lane; k < Kp; k += 32) {
+      // four independent loads in flight per lane: the PHI stream (L2 after the first horizon) is latency-bound
+      int k = lane;
+      for (; k + 96 < Kp; k += 128) {
+        const double c0 = col[k], c1 = col[k + 32], c2 = col[k + 64], c3 = col[k + 96];
+#pragma unroll
+        for (int s = 0; s < IRF_SC; ++s) {
+          const double* ps = pc + s * Kp + k;
+          acc[s] = fma(ps[0], c0, acc[s]);
+          acc[s] = fma(ps[32], c1, acc[s]);
+          acc[s] = fma(ps[64], c2, acc[s]);
+          acc[s] = fma(ps[96], c3, acc[s]);
+        }
+      }
+      for (; k < Kp; k += 32) {
         const double c = col[k];
 #pragma unroll
         for (int s = 0; s < IRF_SC; ++s) acc[s] = fma(pc[s * Kp + k], c, acc[s]);
@@ -127,14 +141,22 @@ __global__ void __launch_bounds__(IRF_THREADS) irf_kernel(const IrfParams p) {
   }
 }
 
-cudaError_t launch_irf(const IrfParams& p, cudaStream_t s) {
-  const size_t smem = ((size_t)2 * IRF_SC * p.Kp + (size_t)p.dim * IRF_SC + (size_t)p.M * IRF_SC) * sizeof(double);
+template <int SC>
+static cudaError_t launch_irf_sc(const IrfParams& p, cudaStream_t s) {
+  const size_t smem = ((size_t)2 * SC * p.Kp + (size_t)p.dim * SC + (size_t)p.M * SC) * sizeof(double);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(irf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(irf_kernel<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int chunks = (p.n_shocks + IRF_SC - 1) / IRF_SC;
-  irf_kernel<<<p.R * chunks, IRF_THREADS, smem, s>>>(p);
+  const int chunks = (p.n_shocks + SC - 1) / SC;
+  irf_kernel<SC><<<p.R * chunks, IRF_THREADS, smem, s>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_irf(const IrfParams& p, cudaStream_t s) {
+  if (p.n_shocks <= 1) return launch_irf_sc<1>(p, s);
+  if (p.n_shocks <= 2) return launch_irf_sc<2>(p, s);
+  if (p.n_shocks <= 4) return launch_irf_sc<4>(p, s);
+  return launch_irf_sc<IRF_SC_MAX>(p, s);
 }
 
 }  // namespace bvb

@@ -1,9 +1,10 @@
 """Turn the ncu artefacts brought back in gpurun_out/ into the tracked summaries under profiles/.
-usage: python tools/summarize_ncu.py <round-tag> <launches.csv> <prof.ncu-rep>"""
+usage: python tools/summarize_ncu.py <round-tag> <launches.csv> [<prof.ncu-rep>]"""
 import collections, csv, json, re, subprocess, sys
 from pathlib import Path
 
-tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+tag, launches = sys.argv[1], sys.argv[2]
+rep = sys.argv[3] if len(sys.argv) > 3 else None
 out = Path("profiles"); out.mkdir(exist_ok=True)
 
 rows = [r for r in csv.reader(open(launches)) if r and not r[0].startswith("==")]
@@ -23,6 +24,8 @@ for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     lines.append(f"| {k} | {len(v)} | {sum(v)/len(v)*1e-3:.1f} | {100*sum(v)/tot:.1f}% |")
 (out / f"launches_{tag}.md").write_text("\n".join(lines) + "\n")
 
+if rep is None:
+    sys.exit(0)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, units = rr[0], rr[1]
