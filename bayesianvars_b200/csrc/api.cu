@@ -579,10 +579,18 @@ int bvb_gig(bvb_handle* h, int n, const double* lambda, int len_lambda, const do
   cudaMemcpyAsync(dl.p, lambda, sizeof(double) * len_lambda, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(dc.p, chi, sizeof(double) * len_chi, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(dp.p, psi, sizeof(double) * len_psi, cudaMemcpyHostToDevice, s);
+  cudaEventRecord(h->ev[0], s);
   gig_vec_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(dout.p, n, m, dl.p, len_lambda, dc.p, len_chi, dp.p, len_psi, h->seed, stream);
+  cudaEventRecord(h->ev[1], s);
   cudaMemcpyAsync(out, dout.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, s);
   cudaError_t e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->last_ms[0] = h->last_ms[1] = h->last_ms[2] = 0; h->last_ms[3] = ms;
+    h->last_launches = 1;
+  }
   if (e != cudaSuccess) {
     bvb_set_error(h, BVB_ERR_CUDA, "bvb_gig: %s", cudaGetErrorString(e));
     return fin(BVB_ERR_CUDA);

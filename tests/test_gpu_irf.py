@@ -60,3 +60,47 @@ def test_irf_linearity_at_scale(handle):
     b = handle.irf_cpp(coef, fl, None, lv, w, 12)
     comb = np.einsum("mshr,s->mhr", a, w[:, 0])
     assert np.max(np.abs(comb - b[:, 0])) <= 1e-11 * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("M,p,R,nf,ahead", [
+    (100, 4, 40, 1, 12),    # config 3 slice (321 KB): cluster of 2 CTAs
+    (131, 4, 23, 2, 5),     # 4 CTAs, columns not divisible by the cluster size
+    (200, 4, 50, 1, 12),    # config 5 slice (1.28 MB): cluster of 8 CTAs, more draws than resident clusters
+    (200, 4, 9, 6, 3),      # 6 shocks: chunks of 4 so that the slice still fits next to the predictor rows
+    (50, 4, 700, 6, 4),     # one CTA per draw, persistent CTAs stride over many draws
+    (260, 4, 3, 1, 2),      # slice too large for 8 CTAs: many-CTA streaming kernel
+])
+def test_irf_cluster_forms_match_oracle(handle, M, p, R, nf, ahead):
+    """The cluster form of K6 (PHI slice resident in the shared memory of 1/2/4/8 CTAs, responses exchanged through
+    distributed shared memory) against the oracle recursion, every cluster size and the fallback."""
+    coef, fl, U, lv = draws(M, p, R, nf, 100 + M)
+    shocks = np.eye(nf)
+    ref = oracle_irf(coef, fl, None, lv, shocks, ahead)
+    out = handle.irf_cpp(coef, fl, None, lv, shocks, ahead)
+    assert out.shape == (M, nf, ahead + 1, R)
+    assert np.max(np.abs(out - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_irf_cluster_identity_shocks_no_factors_no_U(handle):
+    """dim == M shocks without factors or U (plain reduced-form responses), 13 shocks -> two chunks."""
+    M, p, R = 13, 2, 21
+    coef, fl, U, lv = draws(M, p, R, 0, 77)
+    shocks = np.eye(M)
+    ref = oracle_irf(coef, None, None, None, shocks, 6)
+    out = handle.irf_cpp(coef, None, None, None, shocks, 6)
+    assert np.max(np.abs(out - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_irf_forced_forms_agree_with_oracle(handle, monkeypatch, force):
+    """Both forms of K6 on the same small shapes (BVB_IRF_CLUSTER forces one): 1-CTA clusters, several shock chunks,
+    a rotation, no intercept."""
+    monkeypatch.setenv("BVB_IRF_CLUSTER", force)
+    for (M, p, R, nf, ahead, icpt) in [(50, 4, 300, 6, 4, True), (7, 3, 40, 3, 9, False), (24, 2, 17, 11, 3, True)]:
+        coef, fl, U, lv = draws(M, p, R, nf, 200 + M, intercept=icpt)
+        rng = np.random.default_rng(M)
+        rot = np.stack([np.linalg.qr(rng.standard_normal((nf, nf)))[0] for _ in range(R)], axis=2)
+        shocks = rng.standard_normal((nf, nf + 2))
+        ref = oracle_irf(coef, fl, None, lv, shocks, ahead, rot)
+        out = handle.irf_cpp(coef, fl, None, lv, shocks, ahead, rot)
+        assert np.max(np.abs(out - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))

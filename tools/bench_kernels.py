@@ -47,7 +47,7 @@ if "gig" in which:
     n = 4_000_000
     lam = np.full(n, -0.5); chi = rng.gamma(2.0, 1.0, n) * 1e-3 + 1e-8; psi = np.full(n, 2.0)
     for _ in range(3):
-        out = h.my_gig(n, lam, chi, psi)
+        out = h.my_gig(1, lam, chi, psi)
         ms = h.last_timing()["rest_ms"]
     gb = 4 * 8 * n / 1e9   # three parameters in, one variate out
     print(json.dumps(dict(kernel="bvb_gig", n=n, dev_ms=round(ms, 3), variates_per_us=round(n / ms / 1e3, 1),
