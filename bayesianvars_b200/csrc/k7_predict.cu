@@ -21,6 +21,7 @@ struct PredictParams {
   const double *x, *PHI, *U, *facload, *logvar_T, *sv_mu, *sv_phi, *sv_sigma, *Y_obs, *z_logvar, *z_pred;
   const int *ahead, *sv_ind, *voi;
   double *LPL, *PLu, *LPLs, *pred;
+  long long* prof;          // BVB_PREDICT_PROF=1: cycles of CTA 0 per phase
   double* scratch;          // per CTA slab
   size_t slab;              // doubles per CTA
   uint64_t seed;
@@ -31,11 +32,19 @@ struct PredictParams {
 // global memory.  64 x 64 output tile per pass, K chunks of 16 staged k-major in shared memory (row stride 68 == 4
 // mod 16: conflict-free m8n8k4 fragment loads), 8 warps as 4 (m) x 2 (n), each 16 x 32 of the tile on FP64 DMMA.
 constexpr int PR_LD = 68;
+constexpr int PR_ST = 3;                              // cp.async ring stages (one K chunk of 16 each)
+constexpr int PR_STAGE = 2 * 16 * PR_LD;              // doubles per stage: sA[16][PR_LD], sB[16][PR_LD]
+// The operands live in global scratch (L2): a 3-stage cp.async ring keeps two K chunks in flight under the DMMAs of the
+// current one, one CTA barrier per chunk (the first version loaded a chunk, synchronised, multiplied, synchronised: the
+// tensor pipe idled for a full L2 round trip per 32 DMMAs).  Accumulation order over k is unchanged.
+// transB: B is stored n x k (element (k, n) at B[k * ldb + n]); alpha scales the product (C = [C +] alpha * op(A) op(B)).
 __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool transA, const double* B, int ldb, double* C,
-                         int ldc, bool accumulate, double* sA /*[16][PR_LD]*/, double* sB /*[16][PR_LD]*/) {
+                         int ldc, bool accumulate, double* sbuf /*[PR_ST][PR_STAGE]*/, bool transB = false,
+                         double alpha = 1.0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
+  const int nk = (k + 15) >> 4;
   for (int m0 = 0; m0 < m; m0 += 64) {
     for (int n0 = 0; n0 < n; n0 += 64) {
       double acc[2][4][2];
@@ -43,23 +52,39 @@ __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool tra
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-      for (int k0 = 0; k0 < k; k0 += 16) {
+      auto issue = [&](int c) {
+        double* sA = sbuf + (size_t)(c % PR_ST) * PR_STAGE;
+        double* sB = sA + 16 * PR_LD;
+        const int k0 = c << 4;
         for (int i = tid; i < 16 * 64; i += PR_THREADS) {
           // sA[kk][mm] = op(A)[m0+mm, k0+kk];  sB[kk][nn] = B[k0+kk, n0+nn].  The fastest index follows the operand's
           // contiguous dimension so the global reads coalesce.
           int kk, mm;
           if (transA) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
           const int gm = m0 + mm, gk = k0 + kk;
-          double v = 0.0;
-          if (gm < m && gk < k) v = transA ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
-          sA[kk * PR_LD + mm] = v;
-          const int kb = i & 15, nn = i >> 4;
+          double* da = sA + kk * PR_LD + mm;
+          if (gm < m && gk < k) cp_async8(da, transA ? A + (size_t)gm * lda + gk : A + (size_t)gk * lda + gm);
+          else *da = 0.0;
+          int kb, nn;
+          if (transB) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
           const int gn = n0 + nn, gkb = k0 + kb;
-          double w = 0.0;
-          if (gn < n && gkb < k) w = B[(size_t)gn * ldb + gkb];
-          sB[kb * PR_LD + nn] = w;
+          double* db = sB + kb * PR_LD + nn;
+          if (gn < n && gkb < k) cp_async8(db, transB ? B + (size_t)gkb * ldb + gn : B + (size_t)gn * ldb + gkb);
+          else *db = 0.0;
         }
-        __syncthreads();
+      };
+#pragma unroll
+      for (int c = 0; c < PR_ST - 1; ++c) {
+        if (c < nk) issue(c);
+        cp_async_commit();
+      }
+      for (int c = 0; c < nk; ++c) {
+        cp_async_wait<PR_ST - 2>();
+        __syncthreads();                               // chunk c landed everywhere; the stage of chunk c-1 is free
+        if (c + PR_ST - 1 < nk) issue(c + PR_ST - 1);
+        cp_async_commit();
+        const double* sA = sbuf + (size_t)(c % PR_ST) * PR_STAGE;
+        const double* sB = sA + 16 * PR_LD;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const double* ap = sA + (4 * ks + fk) * PR_LD + 16 * wm + fr;
@@ -72,8 +97,9 @@ __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool tra
             dmma884(acc[1][b][0], acc[1][b][1], a1, bv);
           }
         }
-        __syncthreads();
       }
+      cp_async_wait<0>();
+      __syncthreads();                                 // the ring is free for the next tile
       // accumulator fragment: rows 8a + fr, columns 8b + 2 fk + {0, 1}
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -84,7 +110,7 @@ __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool tra
             const int gm = m0 + 16 * wm + 8 * a + fr, gn = n0 + 32 * wn + 8 * b + 2 * fk + e;
             if (gm < m && gn < n) {
               double* c = C + (size_t)gn * ldc + gm;
-              *c = accumulate ? *c + acc[a][b][e] : acc[a][b][e];
+              *c = accumulate ? *c + alpha * acc[a][b][e] : alpha * acc[a][b][e];
             }
           }
     }
@@ -114,6 +140,46 @@ __device__ bool cta_chol(int n, double* L, int ld, double* sh) {
   return ok;
 }
 
+// Blocked form: panels of 16 columns are factorised in shared memory (the GEMM ring, n <= 408 rows), the trailing
+// matrix takes a rank-16 update on the DMMA GEMM.  (The column-at-a-time version above goes through L2 three barriers
+// per column: 21 % of the kernel at M = 200.)  The strict upper triangle of L is scratch afterwards.
+constexpr int PR_CNB = 16;
+__device__ bool cta_chol_blocked(int n, double* L, int ld, double* sbuf) {
+  const int tid = threadIdx.x;
+  bool ok = true;
+  for (int k0 = 0; k0 < n; k0 += PR_CNB) {
+    const int nb = min(PR_CNB, n - k0), rows = n - k0;
+    const int RS = rows | 1;
+    double* P = sbuf;                                 // [nb][RS]
+    for (int c = 0; c < nb; ++c)
+      for (int r = tid; r < rows; r += PR_THREADS) P[c * RS + r] = L[(size_t)(k0 + c) * ld + k0 + r];
+    __syncthreads();
+    for (int c = 0; c < nb; ++c) {
+      const double d = P[c * RS + c];
+      if (!(d > 0.0)) ok = false;
+      const double piv = sqrt(d > 0.0 ? d : 1.0);
+      __syncthreads();
+      for (int r = c + tid; r < rows; r += PR_THREADS) P[c * RS + r] = (r == c) ? piv : P[c * RS + r] / piv;
+      __syncthreads();
+      for (int r = c + 1 + tid; r < rows; r += PR_THREADS) {
+        const double lr = P[c * RS + r];
+        const int cend = min(nb - 1, r);
+        for (int c2 = c + 1; c2 <= cend; ++c2) P[c2 * RS + r] -= lr * P[c * RS + c2];
+      }
+      __syncthreads();
+    }
+    for (int c = 0; c < nb; ++c)
+      for (int r = c + tid; r < rows; r += PR_THREADS) L[(size_t)(k0 + c) * ld + k0 + r] = P[c * RS + r];
+    __syncthreads();
+    const int rem = rows - nb;
+    if (rem > 0) {
+      const double* Ap = L + (size_t)k0 * ld + k0 + nb;  // rem x nb panel below the diagonal block
+      cta_gemm(rem, rem, nb, Ap, ld, false, Ap, ld, L + (size_t)(k0 + nb) * ld + k0 + nb, ld, true, sbuf, true, -1.0);
+    }
+  }
+  return __syncthreads_and(ok ? 1 : 0) != 0;
+}
+
 // log N(x; mean, L L') for the n-vector d = x - mean (overwritten with L^-1 d); thread 0 returns the value.
 __device__ double cta_mvn_logdens(int n, const double* L, int ld, double* d) {
   double out = 0.0;
@@ -134,12 +200,16 @@ __device__ double cta_mvn_logdens(int n, const double* L, int ld, double* d) {
 }
 
 __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams p) {
-  __shared__ double sA[16 * PR_LD], sB[16 * PR_LD];
+  extern __shared__ __align__(16) double sbuf[];   // [PR_ST][PR_STAGE] GEMM operand ring
   __shared__ double sres[2];
+  double* sA = sbuf;
+  const bool prof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = prof ? clock64() : 0;
+#define PR_TICK(slot) do { if (prof) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
   const int Kp = p.Kp, M = p.M, R = p.R, P = p.p, tid = threadIdx.x;
   double* base = p.scratch + (size_t)blockIdx.x * p.slab;
-  double* SL = base;                               // Kp x Kp
-  double* TMP = SL + (size_t)Kp * Kp;              // Kp x Kp
+  double* SL = base;                               // Kp x Kp   companion covariance (current)
+  double* TMP = SL + (size_t)Kp * Kp;              // Kp x Kp   companion covariance (next) / p = 1 temporary
   double* SIG = TMP + (size_t)Kp * Kp;             // M x M
   double* LCH = SIG + (size_t)M * M;               // M x M (also used for the VoI sub-matrix)
   double* UINV = LCH + (size_t)M * M;              // M x M
@@ -149,12 +219,14 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
   double* lvvar = lvp + (M + p.nf);                // [nsv]
   double* yp = lvvar + (p.nsv > 0 ? p.nsv : 1);    // [M]
   double* dv = yp + M;                             // [M]
+  double* GB = dv + M;                             // M x pM    PHI' SL
   const int nsave = R * p.each;
   for (int chain = blockIdx.x; chain < nsave; chain += gridDim.x) {
     const int r = chain % R, j = chain / R;
     const double* PHI = p.PHI + (size_t)r * Kp * M;
     const double* lvT = p.logvar_T + (size_t)r * p.ld_lv;
-    for (size_t i = tid; i < (size_t)Kp * Kp; i += PR_THREADS) SL[i] = 0.0;
+    SL = base; TMP = SL + (size_t)Kp * Kp;
+    for (size_t i = tid; i < (size_t)2 * Kp * Kp; i += PR_THREADS) SL[i] = 0.0;   // both buffers: the intercept row / column stay 0
     for (size_t i = tid; i < (size_t)Kp * M; i += PR_THREADS) PP0[i] = PHI[i];
     for (int i = tid; i < p.nsv; i += PR_THREADS) lvvar[i] = 0.0;
     if (!p.factor) {
@@ -189,9 +261,10 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
         else { RngStream g(p.seed, 0x700u, (uint32_t)(chain * p.max_ahead + i), (uint32_t)s); z = g.normal(); }
         lvp[idx] = mean + z * sqrt(var);
       }
+      PR_TICK(0);
       // ---- PHI to the power i+1 (:306-309, PHI_power0 :125-142)
       if (i > 0) {
-        cta_gemm(Kp, M, M, PHI, Kp, false, PPc, Kp, PPn, Kp, false, sA, sB);   // PHI * old[0:M, :]
+        cta_gemm(Kp, M, M, PHI, Kp, false, PPc, Kp, PPn, Kp, false, sbuf);   // PHI * old[0:M, :]
         for (size_t e = tid; e < (size_t)Kp * M; e += PR_THREADS) {
           const int row = (int)(e % Kp);
           double add = 0.0;
@@ -203,6 +276,7 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
         double* t = PPc; PPc = PPn; PPn = t;
       }
       __syncthreads();
+      PR_TICK(1);
       // ---- Sigma (build_sigma :45-67, return_chol = false)
       for (int e = tid; e < M * M; e += PR_THREADS) {
         const int a = e % M, b = e / M;
@@ -220,38 +294,50 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
         SIG[e] = v;
       }
       __syncthreads();
+      PR_TICK(2);
       // ---- companion covariance recursion (Sigma_pred_uncond :144-178), n_ahead = i
       if (P > 1) {
         if (i > 0) {
+          // The reference builds tmp = [PHI' SL ; SL.rows(0,(p-1)M-1)], then SL(0:M,0:M) = tmp PHI, SL.cols(M,pM-1) =
+          // tmp.cols(0,(p-1)M-1) and copies the upper triangle over the lower one.  The same values without the four
+          // Kp x Kp passes (zero, two block copies, transposed symmetrisation - 34 % of the kernel): the covariance
+          // ping-pongs between two buffers, new[M+a, M+c] = old[a, c] is one coalesced block copy (old is symmetric),
+          // G = PHI' old goes to a small M x pM buffer and lands in new[0:M, M+c] and, transposed, in new[M+c, 0:M].
           const int mn = (i < P ? i : P) * M;
-          for (size_t e = tid; e < (size_t)Kp * Kp; e += PR_THREADS) TMP[e] = 0.0;
-          __syncthreads();
-          cta_gemm(M, mn, mn, PHI, Kp, true, SL, Kp, TMP, Kp, false, sA, sB);      // tmp[0:M, 0:mn] = PHI[0:mn,:]' SL[0:mn,0:mn]
-          for (size_t e = tid; e < (size_t)(P - 1) * M * Kp; e += PR_THREADS) {     // tmp.rows(M, pM-1) = SL.rows(0, (p-1)M-1)
-            const int row = (int)(e % ((size_t)(P - 1) * M)), col = (int)(e / ((size_t)(P - 1) * M));
-            TMP[(size_t)col * Kp + M + row] = SL[(size_t)col * Kp + row];
+          const int sh = (P - 1) * M;
+          cta_gemm(M, mn, mn, PHI, Kp, true, SL, Kp, GB, M, false, sbuf);          // G[0:M, 0:mn] = PHI[0:mn,:]' SL[0:mn,0:mn]
+          PR_TICK(4);
+          cta_gemm(M, M, mn, GB, M, false, PHI, Kp, TMP, Kp, false, sbuf);         // new[0:M,0:M] = G[0:M,0:mn] PHI[0:mn,:]
+          PR_TICK(4);
+          for (size_t e = tid; e < (size_t)sh * sh; e += PR_THREADS) {              // new[M+a, M+c] = old[a, c]
+            const int a2 = (int)(e % sh), c2 = (int)(e / sh);
+            TMP[(size_t)(M + c2) * Kp + M + a2] = SL[(size_t)c2 * Kp + a2];
+          }
+          for (size_t e = tid; e < (size_t)M * sh; e += PR_THREADS) {               // new[0:M, M+c] = G[:, c] (0 beyond mn)
+            const int a2 = (int)(e % M), c2 = (int)(e / M);
+            TMP[(size_t)(M + c2) * Kp + a2] = (c2 < mn) ? GB[e] : 0.0;
+          }
+          for (size_t e = tid; e < (size_t)M * sh; e += PR_THREADS) {               // new[M+c, 0:M] = G[:, c]' (lower <- upper)
+            const int c2 = (int)(e % sh), a2 = (int)(e / sh);
+            TMP[(size_t)a2 * Kp + M + c2] = (c2 < mn) ? GB[(size_t)c2 * M + a2] : 0.0;
           }
           __syncthreads();
-          cta_gemm(M, M, mn, TMP, Kp, false, PHI, Kp, SL, Kp, false, sA, sB);      // SL[0:M,0:M] = tmp[0:M,0:mn] PHI[0:mn,:]
-          for (size_t e = tid; e < (size_t)Kp * (P - 1) * M; e += PR_THREADS) {     // SL.cols(M, pM-1) = tmp.cols(0, (p-1)M-1)
-            const int row = (int)(e % Kp), col = (int)(e / Kp);
-            SL[(size_t)(M + col) * Kp + row] = TMP[(size_t)col * Kp + row];
+          for (int e = tid; e < M * M; e += PR_THREADS) {                           // strict lower of the top-left block <- upper
+            const int row = e % M, col = e / M;
+            if (row > col) TMP[(size_t)col * Kp + row] = TMP[(size_t)row * Kp + col];
           }
           __syncthreads();
-          for (size_t e = tid; e < (size_t)Kp * Kp; e += PR_THREADS) {              // strict lower <- transposed upper
-            const int row = (int)(e % Kp), col = (int)(e / Kp);
-            if (row > col) SL[e] = SL[(size_t)row * Kp + col];
-          }
-          __syncthreads();
+          { double* t = SL; SL = TMP; TMP = t; }
         }
       } else if (P == 1) {
         if (i > 0) {
-          cta_gemm(M, M, M, PHI, Kp, true, SL, Kp, TMP, Kp, false, sA, sB);
-          cta_gemm(M, M, M, TMP, Kp, false, PHI, Kp, SL, Kp, false, sA, sB);
+          cta_gemm(M, M, M, PHI, Kp, true, SL, Kp, TMP, Kp, false, sbuf);
+          cta_gemm(M, M, M, TMP, Kp, false, PHI, Kp, SL, Kp, false, sbuf);
         }
       }
       for (int e = tid; e < M * M; e += PR_THREADS) SL[(size_t)(e / M) * Kp + (e % M)] += SIG[e];
       __syncthreads();
+      PR_TICK(3);
       // ---- requested horizon? (:346-380)
       if (counter < p.na && i == p.ahead[counter] - 1) {
         for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
@@ -261,7 +347,9 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
         }
         for (int e = tid; e < M * M; e += PR_THREADS) LCH[e] = SL[(size_t)(e / M) * Kp + (e % M)];
         __syncthreads();
-        const bool ok = cta_chol(M, LCH, M, sA);
+        PR_TICK(5);
+        const bool ok = (M <= PR_ST * PR_STAGE / PR_CNB - 1) ? cta_chol_blocked(M, LCH, M, sbuf) : cta_chol(M, LCH, M, sA);
+        PR_TICK(6);
         if (!ok && tid == 0) atomicCAS(p.status, 0, chain + 1);
         if (p.lpl) {
           for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
@@ -294,16 +382,20 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
           for (int e = tid; e < nv * nv; e += PR_THREADS) LCH[e] = SL[(size_t)p.voi[e / nv] * Kp + p.voi[e % nv]];
           for (int e = tid; e < nv; e += PR_THREADS) dv[e] = p.Y_obs[(size_t)p.voi[e] * p.na + counter] - yp[p.voi[e]];
           __syncthreads();
-          const bool ok2 = cta_chol(nv, LCH, nv, sA);
+          const bool ok2 = (nv <= PR_ST * PR_STAGE / PR_CNB - 1) ? cta_chol_blocked(nv, LCH, nv, sbuf) : cta_chol(nv, LCH, nv, sA);
           const double ll = cta_mvn_logdens(nv, LCH, nv, dv);
           if (tid == 0) p.LPLs[(size_t)chain * p.na + counter] = ok2 ? ll : nan("");
         }
         ++counter;   // every chain owns exactly one replicate j, so the horizon counter advances here
       }
       __syncthreads();
+      PR_TICK(7);
     }
     (void)sres;
   }
+  if (prof)
+    for (int i = 0; i < 8; ++i) p.prof[i] = tacc[i];
+#undef PR_TICK
 }
 
 cudaError_t launch_predict(PredictParams& p, int num_sms, cudaStream_t s, double** scratch_out) {
@@ -311,11 +403,14 @@ cudaError_t launch_predict(PredictParams& p, int num_sms, cudaStream_t s, double
   int grid = 2 * num_sms;
   if (grid > nsave) grid = nsave;
   p.slab = (size_t)2 * p.Kp * p.Kp + (size_t)3 * p.M * p.M + (size_t)2 * p.Kp * p.M + (size_t)(p.M + p.nf) +
-           (size_t)(p.nsv > 0 ? p.nsv : 1) + (size_t)2 * p.M + 8;
+           (size_t)(p.nsv > 0 ? p.nsv : 1) + (size_t)2 * p.M + (size_t)p.M * p.p * p.M + 8;
   cudaError_t e = cudaMalloc(scratch_out, p.slab * grid * sizeof(double));
   if (e != cudaSuccess) return e;
   p.scratch = *scratch_out;
-  predict_kernel<<<grid, PR_THREADS, 0, s>>>(p);
+  const size_t smem = (size_t)PR_ST * PR_STAGE * sizeof(double);
+  e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  predict_kernel<<<grid, PR_THREADS, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -393,6 +488,11 @@ extern "C" int bvb_predict(bvb_handle* h, int each, int Kp, int M, int R, int n_
   allocs.push_back(p.status);
   PR_TRY(cudaMemsetAsync(p.status, 0, sizeof(int), s));
   double* scratch = nullptr;
+  if (getenv("BVB_PREDICT_PROF")) {
+    PR_TRY(cudaMalloc(&p.prof, 8 * sizeof(long long)));
+    allocs.push_back(p.prof);
+    PR_TRY(cudaMemsetAsync(p.prof, 0, 8 * sizeof(long long), s));
+  }
   PR_TRY(cudaEventRecord(h->ev[0], s));
   cudaError_t le = launch_predict(p, h->num_sms, s, &scratch);
   if (scratch) allocs.push_back(scratch);
@@ -406,7 +506,12 @@ extern "C" int bvb_predict(bvb_handle* h, int each, int Kp, int M, int R, int n_
   if (simulate_predictive) PR_TRY(cudaMemcpyAsync(predictions, p.pred, d * n_ahead * M * nsave, cudaMemcpyDeviceToHost, s));
   int st = 0;
   PR_TRY(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  long long hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (p.prof) PR_TRY(cudaMemcpyAsync(hp, p.prof, sizeof(hp), cudaMemcpyDeviceToHost, s));
   PR_TRY(cudaStreamSynchronize(s));
+  if (p.prof)
+    fprintf(stderr, "predict ticks (CTA 0): logvar %lld phi-power %lld sigma %lld copies+sym %lld gemm %lld mean+copy %lld chol %lld density+draw %lld\n",
+            hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
   h->last_ms[0] = h->last_ms[1] = h->last_ms[2] = 0; h->last_ms[3] = ms;

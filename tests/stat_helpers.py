@@ -12,6 +12,21 @@ def batch_means_var(y, nbatch=40):
     return b.var(ddof=1) / nbatch
 
 
+def quantile_disagreement(a, b, levels=(0.1, 0.5, 0.9), nbatch=30):
+    """Posterior QUANTILES of two autocorrelated chains within Monte-Carlo error (north star: "posterior means and
+    quantiles must agree within Monte-Carlo standard error").  For each level the pooled quantile c is taken and the
+    two chains' frequencies of {draw <= c} are compared as means of indicator series (batch-means standard errors).
+    Returns the largest excess of |freq_a - freq_b| over 5 standard errors (<= slack means agreement)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    worst = -np.inf
+    for q in levels:
+        c = np.quantile(np.concatenate([a, b]), q)
+        ia, ib = (a <= c).astype(float), (b <= c).astype(float)
+        se = np.sqrt(batch_means_var(ia, nbatch) + batch_means_var(ib, nbatch))
+        worst = max(worst, abs(ia.mean() - ib.mean()) - 5 * se)
+    return worst
+
+
 def geweke_pvalue(x_iid, y_mcmc):
     """Two-sided p-value of mean(x) == mean(y), x iid, y autocorrelated
     (tests/testthat/test-bvar.R:23-35)."""

@@ -11,7 +11,7 @@ from scipy import stats
 
 from bayesianvars_b200 import bvar as B
 from oracle import gibbs as og
-from tests.stat_helpers import batch_means_var
+from tests.stat_helpers import batch_means_var, quantile_disagreement
 from tests.test_rng_host import gig_cdf_numeric
 
 pytestmark = pytest.mark.gpu
@@ -56,6 +56,8 @@ def test_posterior_matches_oracle_chain(handle, prior):
             a, b = gpu["PHI"][i, j], orc["PHI"][i, j]
             se = np.sqrt(batch_means_var(a, 30) + batch_means_var(b, 30))
             assert abs(a.mean() - b.mean()) < 5 * se + 0.02, (prior, i, j, a.mean(), b.mean(), se)
+            # 10 % / 50 % / 90 % posterior quantiles: frequencies below the pooled quantile within 5 MCSE (+0.02)
+            assert quantile_disagreement(a, b) < 0.02, (prior, "quantiles", i, j)
     # idiosyncratic log-variance level and SV parameters
     for k in range(3):
         a, b = gpu["sv_para"][k, :M].mean(axis=0), orc["sv_para"][k, :M].mean(axis=0)
@@ -174,6 +176,7 @@ def test_cholesky_posterior_matches_oracle_chain(handle, uprior):
             a, b = a_all[i], b_all[i]
             se = np.sqrt(batch_means_var(a, 30) + batch_means_var(b, 30))
             assert abs(a.mean() - b.mean()) < 5 * se + 0.02, (uprior, name, i, a.mean(), b.mean(), se)
+            assert quantile_disagreement(a, b) < 0.02, (uprior, name, "quantiles", i)
     for k in range(3):
         a, b = gpu["sv_para"][k].mean(axis=0), orc["sv_para"][k].mean(axis=0)
         se = np.sqrt(batch_means_var(a, 30) + batch_means_var(b, 30))

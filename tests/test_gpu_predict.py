@@ -74,6 +74,11 @@ def test_out_of_sample_tiles_cross_boundaries(handle):
     check(handle, make_case(seed=8, M=33, p=3, intercept=True, R=2, each=1, ahead=[3, 5], factor=False))
 
 
+def test_out_of_sample_config3_shape(handle):
+    # M = 100, p = 4 (Kp = 401): 7 Cholesky panels of 16 columns, ping-pong companion covariance over 6 horizons (> p)
+    check(handle, make_case(seed=11, M=100, p=4, intercept=True, R=2, each=1, ahead=[1, 4, 6], factor=True, nf=2))
+
+
 def test_many_chains_stride_over_ctas(handle):
     # more chains than resident CTAs (2 x 148): R*each = 700
     check(handle, make_case(seed=9, M=3, p=2, intercept=True, R=350, each=2, ahead=[1, 2], factor=True, nf=1))
