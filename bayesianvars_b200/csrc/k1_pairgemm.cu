@@ -549,7 +549,14 @@ static cudaError_t launch_k1_nt(const K1Params& p, cudaStream_t s) {
 cudaError_t launch_k1(const K1Params& p, cudaStream_t s) {
   const int m = p.M;
   // Smallest column block that covers M in the fewest CTA columns.
-  const int blocks = (m + K1_NMAX - 1) / K1_NMAX;
+  int blocks = (m + K1_NMAX - 1) / K1_NMAX;
+  {
+    // BVB_K1_NSPLIT=c: at least c CTA columns (narrower equation blocks, more and shorter CTAs: a smaller last wave at
+    // the price of re-reading A once per column)
+    static int nsplit = -1;
+    if (nsplit < 0) { const char* e = getenv("BVB_K1_NSPLIT"); nsplit = e ? atoi(e) : 0; }
+    if (nsplit > blocks && nsplit <= (m + 7) / 8) blocks = nsplit;
+  }
   const int per = (m + blocks - 1) / blocks;       // equations per CTA column
   const int nt = (per + 7) / 8;
   if (nt <= 1) return launch_k1_nt<1>(p, s);

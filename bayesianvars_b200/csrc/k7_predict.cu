@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
   double* SIG = TMP + (size_t)Kp * Kp;             // M x M
   double* LCH = SIG + (size_t)M * M;               // M x M (also used for the VoI sub-matrix)
   double* UINV = LCH + (size_t)M * M;              // M x M
-  double* PP0 = UINV + (size_t)M * M;              // Kp x M
-  double* PP1 = PP0 + (size_t)Kp * M;              // Kp x M
-  double* lvp = PP1 + (size_t)Kp * M;              // [M + nf]
+  double* xb0 = UINV + (size_t)M * M;              // [Kp] predictor row of the current horizon
+  double* xb1 = xb0 + Kp;                          // [Kp]
+  double* lvp = xb1 + Kp;                          // [M + nf]
   double* lvvar = lvp + (M + p.nf);                // [nsv]
   double* yp = lvvar + (p.nsv > 0 ? p.nsv : 1);    // [M]
   double* dv = yp + M;                             // [M]
@@ -227,7 +227,9 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
     const double* lvT = p.logvar_T + (size_t)r * p.ld_lv;
     SL = base; TMP = SL + (size_t)Kp * Kp;
     for (size_t i = tid; i < (size_t)2 * Kp * Kp; i += PR_THREADS) SL[i] = 0.0;   // both buffers: the intercept row / column stay 0
-    for (size_t i = tid; i < (size_t)Kp * M; i += PR_THREADS) PP0[i] = PHI[i];
+    double* xc = xb0;
+    double* xn = xb1;
+    for (int i = tid; i < Kp; i += PR_THREADS) xc[i] = p.x[i];
     for (int i = tid; i < p.nsv; i += PR_THREADS) lvvar[i] = 0.0;
     if (!p.factor) {
       // U_inv = inv(trimatu(Um)), one thread per column: back substitution on the unit upper triangle
@@ -242,8 +244,6 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
       }
     }
     __syncthreads();
-    double* PPc = PP0;
-    double* PPn = PP1;
     int counter = 0;
     for (int i = 0; i < p.max_ahead; ++i) {
       // ---- log-variance forecast (:300-304, :325-329)
@@ -262,20 +262,24 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
         lvp[idx] = mean + z * sqrt(var);
       }
       PR_TICK(0);
-      // ---- PHI to the power i+1 (:306-309, PHI_power0 :125-142)
-      if (i > 0) {
-        cta_gemm(Kp, M, M, PHI, Kp, false, PPc, Kp, PPn, Kp, false, sbuf);   // PHI * old[0:M, :]
-        for (size_t e = tid; e < (size_t)Kp * M; e += PR_THREADS) {
-          const int row = (int)(e % Kp);
-          double add = 0.0;
-          if (row < (P - 1) * M) add = PPc[e + M];                 // old rows of the next lag block
-          else if (row >= P * M) add = PPc[e];                     // intercept row
-          PPn[e] += add;
+      // ---- predictive mean.  The reference carries PHI^(i+1) (PHI_power0 :125-142, a Kp x M x M product per horizon)
+      // and forms X_T_plus_1 * PHI^(i+1) (:347); the same number is the iterated forecast yhat_i = x_i' PHI with the
+      // predictor row shifted by one lag per horizon (x_{i+1} = [yhat_i, x_i[0:(p-1)M], intercept]) - a Kp x M
+      // matrix-vector product instead of 18 % of the kernel; the two agree to 1e-16 relative (tests: 1e-9).
+      {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int m2 = warp; m2 < M; m2 += PR_THREADS / 32) {
+          const double* col = PHI + (size_t)m2 * Kp;
+          double v = 0.0;
+          for (int k = lane; k < Kp; k += 32) v = fma(xc[k], col[k], v);
+          v = warp_sum(v);
+          if (lane == 0) yp[m2] = v;
         }
         __syncthreads();
-        double* t = PPc; PPc = PPn; PPn = t;
+        for (int k = tid; k < Kp; k += PR_THREADS) xn[k] = (k < M) ? yp[k] : (k < P * M ? xc[k - M] : xc[k]);
+        __syncthreads();
+        double* t = xc; xc = xn; xn = t;
       }
-      __syncthreads();
       PR_TICK(1);
       // ---- Sigma (build_sigma :45-67, return_chol = false)
       for (int e = tid; e < M * M; e += PR_THREADS) {
@@ -309,17 +313,21 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
           PR_TICK(4);
           cta_gemm(M, M, mn, GB, M, false, PHI, Kp, TMP, Kp, false, sbuf);         // new[0:M,0:M] = G[0:M,0:mn] PHI[0:mn,:]
           PR_TICK(4);
-          for (size_t e = tid; e < (size_t)sh * sh; e += PR_THREADS) {              // new[M+a, M+c] = old[a, c]
-            const int a2 = (int)(e % sh), c2 = (int)(e / sh);
-            TMP[(size_t)(M + c2) * Kp + M + a2] = SL[(size_t)c2 * Kp + a2];
-          }
-          for (size_t e = tid; e < (size_t)M * sh; e += PR_THREADS) {               // new[0:M, M+c] = G[:, c] (0 beyond mn)
-            const int a2 = (int)(e % M), c2 = (int)(e / M);
-            TMP[(size_t)(M + c2) * Kp + a2] = (c2 < mn) ? GB[e] : 0.0;
-          }
-          for (size_t e = tid; e < (size_t)M * sh; e += PR_THREADS) {               // new[M+c, 0:M] = G[:, c]' (lower <- upper)
-            const int c2 = (int)(e % sh), a2 = (int)(e / sh);
-            TMP[(size_t)a2 * Kp + M + c2] = (c2 < mn) ? GB[(size_t)c2 * M + a2] : 0.0;
+          {
+            const int lane = tid & 31, warp = tid >> 5, nwp = PR_THREADS / 32;
+            for (int c2 = warp; c2 < sh; c2 += nwp) {                               // new[M+a, M+c] = old[a, c] (coalesced columns)
+              const double* src = SL + (size_t)c2 * Kp;
+              double* dst = TMP + (size_t)(M + c2) * Kp + M;
+#pragma unroll 4
+              for (int a2 = lane; a2 < sh; a2 += 32) dst[a2] = src[a2];
+              double* top = TMP + (size_t)(M + c2) * Kp;                            // new[0:M, M+c] = G[:, c] (0 beyond mn)
+              const double* g = GB + (size_t)c2 * M;
+              for (int a2 = lane; a2 < M; a2 += 32) top[a2] = (c2 < mn) ? g[a2] : 0.0;
+            }
+            for (int a2 = warp; a2 < M; a2 += nwp) {                                // new[M+c, 0:M] = G[:, c]' (lower <- upper)
+              double* dst = TMP + (size_t)a2 * Kp + M;
+              for (int c2 = lane; c2 < sh; c2 += 32) dst[c2] = (c2 < mn) ? GB[(size_t)c2 * M + a2] : 0.0;
+            }
           }
           __syncthreads();
           for (int e = tid; e < M * M; e += PR_THREADS) {                           // strict lower of the top-left block <- upper
@@ -340,11 +348,6 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
       PR_TICK(3);
       // ---- requested horizon? (:346-380)
       if (counter < p.na && i == p.ahead[counter] - 1) {
-        for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
-          double v = 0.0;
-          for (int k = 0; k < Kp; ++k) v = fma(p.x[k], PPc[(size_t)m2 * Kp + k], v);
-          yp[m2] = v;
-        }
         for (int e = tid; e < M * M; e += PR_THREADS) LCH[e] = SL[(size_t)(e / M) * Kp + (e % M)];
         __syncthreads();
         PR_TICK(5);
@@ -402,7 +405,7 @@ cudaError_t launch_predict(PredictParams& p, int num_sms, cudaStream_t s, double
   const int nsave = p.R * p.each;
   int grid = 2 * num_sms;
   if (grid > nsave) grid = nsave;
-  p.slab = (size_t)2 * p.Kp * p.Kp + (size_t)3 * p.M * p.M + (size_t)2 * p.Kp * p.M + (size_t)(p.M + p.nf) +
+  p.slab = (size_t)2 * p.Kp * p.Kp + (size_t)3 * p.M * p.M + (size_t)2 * p.Kp + (size_t)(p.M + p.nf) +
            (size_t)(p.nsv > 0 ? p.nsv : 1) + (size_t)2 * p.M + (size_t)p.M * p.p * p.M + 8;
   cudaError_t e = cudaMalloc(scratch_out, p.slab * grid * sizeof(double));
   if (e != cudaSuccess) return e;
