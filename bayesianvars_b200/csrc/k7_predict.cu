@@ -40,7 +40,7 @@ constexpr int PR_STAGE = 2 * 16 * PR_LD;              // doubles per stage: sA[1
 // transB: B is stored n x k (element (k, n) at B[k * ldb + n]); alpha scales the product (C = [C +] alpha * op(A) op(B)).
 __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool transA, const double* B, int ldb, double* C,
                          int ldc, bool accumulate, double* sbuf /*[PR_ST][PR_STAGE]*/, bool transB = false,
-                         double alpha = 1.0) {
+                         double alpha = 1.0, const int* bmap = nullptr /* B(k, n) lives at B[bmap[n] * ldb + bmap[k]] */) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
@@ -69,7 +69,9 @@ __device__ void cta_gemm(int m, int n, int k, const double* A, int lda, bool tra
           if (transB) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
           const int gn = n0 + nn, gkb = k0 + kb;
           double* db = sB + kb * PR_LD + nn;
-          if (gn < n && gkb < k) cp_async8(db, transB ? B + (size_t)gkb * ldb + gn : B + (size_t)gn * ldb + gkb);
+          if (gn < n && gkb < k)
+            cp_async8(db, bmap ? B + (size_t)bmap[gn] * ldb + bmap[gkb]
+                               : (transB ? B + (size_t)gkb * ldb + gn : B + (size_t)gn * ldb + gkb));
           else *db = 0.0;
         }
       };
@@ -200,7 +202,8 @@ __device__ double cta_mvn_logdens(int n, const double* L, int ld, double* d) {
 }
 
 __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams p) {
-  extern __shared__ __align__(16) double sbuf[];   // [PR_ST][PR_STAGE] GEMM operand ring
+  extern __shared__ __align__(16) double sbuf[];   // [PR_ST][PR_STAGE] GEMM operand ring, then int pmap[Kp]
+  int* pmap = reinterpret_cast<int*>(sbuf + PR_ST * PR_STAGE);
   __shared__ double sres[2];
   double* sA = sbuf;
   const bool prof = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -208,9 +211,8 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
 #define PR_TICK(slot) do { if (prof) { const long long tn = clock64(); tacc[slot] += tn - tprev; tprev = tn; } } while (0)
   const int Kp = p.Kp, M = p.M, R = p.R, P = p.p, tid = threadIdx.x;
   double* base = p.scratch + (size_t)blockIdx.x * p.slab;
-  double* SL = base;                               // Kp x Kp   companion covariance (current)
-  double* TMP = SL + (size_t)Kp * Kp;              // Kp x Kp   companion covariance (next) / p = 1 temporary
-  double* SIG = TMP + (size_t)Kp * Kp;             // M x M
+  double* SL = base;                               // Kp x Kp   companion covariance, lag blocks rotated by `off` (see below)
+  double* SIG = SL + (size_t)Kp * Kp;              // M x M
   double* LCH = SIG + (size_t)M * M;               // M x M (also used for the VoI sub-matrix)
   double* UINV = LCH + (size_t)M * M;              // M x M
   double* xb0 = UINV + (size_t)M * M;              // [Kp] predictor row of the current horizon
@@ -225,8 +227,9 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
     const int r = chain % R, j = chain / R;
     const double* PHI = p.PHI + (size_t)r * Kp * M;
     const double* lvT = p.logvar_T + (size_t)r * p.ld_lv;
-    SL = base; TMP = SL + (size_t)Kp * Kp;
-    for (size_t i = tid; i < (size_t)2 * Kp * Kp; i += PR_THREADS) SL[i] = 0.0;   // both buffers: the intercept row / column stay 0
+    for (size_t i = tid; i < (size_t)Kp * Kp; i += PR_THREADS) SL[i] = 0.0;       // the intercept row / column stay 0
+    int off = 0;                                                                  // logical lag block b lives in physical block (b + off) % P
+    for (int i = tid; i < Kp; i += PR_THREADS) pmap[i] = i;
     double* xc = xb0;
     double* xn = xb1;
     for (int i = tid; i < Kp; i += PR_THREADS) xc[i] = p.x[i];
@@ -303,52 +306,54 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
       if (P > 1) {
         if (i > 0) {
           // The reference builds tmp = [PHI' SL ; SL.rows(0,(p-1)M-1)], then SL(0:M,0:M) = tmp PHI, SL.cols(M,pM-1) =
-          // tmp.cols(0,(p-1)M-1) and copies the upper triangle over the lower one.  The same values without the four
-          // Kp x Kp passes (zero, two block copies, transposed symmetrisation - 34 % of the kernel): the covariance
-          // ping-pongs between two buffers, new[M+a, M+c] = old[a, c] is one coalesced block copy (old is symmetric),
-          // G = PHI' old goes to a small M x pM buffer and lands in new[0:M, M+c] and, transposed, in new[M+c, 0:M].
+          // tmp.cols(0,(p-1)M-1) and copies the upper triangle over the lower one: the covariance of the lags moves one
+          // block down the diagonal, new[b+1, c+1] = old[b, c].  Here that move is free: the lag blocks are addressed
+          // through a rotation (logical block b = physical block (b + off) % P, `pmap`), each horizon decrements `off`,
+          // and only the new first block row / column are written - into the physical block the oldest lag vacates.
+          // Same values as the reference (old is symmetric), none of its four Kp x Kp passes (34 % of the first version).
           const int mn = (i < P ? i : P) * M;
           const int sh = (P - 1) * M;
-          cta_gemm(M, mn, mn, PHI, Kp, true, SL, Kp, GB, M, false, sbuf);          // G[0:M, 0:mn] = PHI[0:mn,:]' SL[0:mn,0:mn]
+          cta_gemm(M, mn, mn, PHI, Kp, true, SL, Kp, GB, M, false, sbuf, false, 1.0, pmap);   // G = PHI[0:mn,:]' SL[0:mn,0:mn]
           PR_TICK(4);
-          cta_gemm(M, M, mn, GB, M, false, PHI, Kp, TMP, Kp, false, sbuf);         // new[0:M,0:M] = G[0:M,0:mn] PHI[0:mn,:]
+          off = (off + P - 1) % P;
+          __syncthreads();
+          for (int k = tid; k < P * M; k += PR_THREADS) pmap[k] = ((k / M + off) % P) * M + k % M;
+          __syncthreads();
+          double* TL = SL + (size_t)(off * M) * Kp + off * M;                        // new top-left block
+          cta_gemm(M, M, mn, GB, M, false, PHI, Kp, TL, Kp, false, sbuf);            // new[0:M,0:M] = G[0:M,0:mn] PHI[0:mn,:]
           PR_TICK(4);
           {
             const int lane = tid & 31, warp = tid >> 5, nwp = PR_THREADS / 32;
-            for (int c2 = warp; c2 < sh; c2 += nwp) {                               // new[M+a, M+c] = old[a, c] (coalesced columns)
-              const double* src = SL + (size_t)c2 * Kp;
-              double* dst = TMP + (size_t)(M + c2) * Kp + M;
-#pragma unroll 4
-              for (int a2 = lane; a2 < sh; a2 += 32) dst[a2] = src[a2];
-              double* top = TMP + (size_t)(M + c2) * Kp;                            // new[0:M, M+c] = G[:, c] (0 beyond mn)
+            for (int c2 = warp; c2 < sh; c2 += nwp) {                               // new[0:M, M+c] = G[:, c] (0 beyond mn)
+              double* top = SL + (size_t)pmap[M + c2] * Kp + off * M;
               const double* g = GB + (size_t)c2 * M;
               for (int a2 = lane; a2 < M; a2 += 32) top[a2] = (c2 < mn) ? g[a2] : 0.0;
             }
             for (int a2 = warp; a2 < M; a2 += nwp) {                                // new[M+c, 0:M] = G[:, c]' (lower <- upper)
-              double* dst = TMP + (size_t)a2 * Kp + M;
-              for (int c2 = lane; c2 < sh; c2 += 32) dst[c2] = (c2 < mn) ? GB[(size_t)c2 * M + a2] : 0.0;
+              double* dst = SL + (size_t)(off * M + a2) * Kp;
+              for (int c2 = lane; c2 < sh; c2 += 32) dst[pmap[M + c2]] = (c2 < mn) ? GB[(size_t)c2 * M + a2] : 0.0;
             }
           }
           __syncthreads();
           for (int e = tid; e < M * M; e += PR_THREADS) {                           // strict lower of the top-left block <- upper
             const int row = e % M, col = e / M;
-            if (row > col) TMP[(size_t)col * Kp + row] = TMP[(size_t)row * Kp + col];
+            if (row > col) TL[(size_t)col * Kp + row] = TL[(size_t)row * Kp + col];
           }
           __syncthreads();
-          { double* t = SL; SL = TMP; TMP = t; }
         }
       } else if (P == 1) {
         if (i > 0) {
-          cta_gemm(M, M, M, PHI, Kp, true, SL, Kp, TMP, Kp, false, sbuf);
-          cta_gemm(M, M, M, TMP, Kp, false, PHI, Kp, SL, Kp, false, sbuf);
+          cta_gemm(M, M, M, PHI, Kp, true, SL, Kp, GB, M, false, sbuf);
+          cta_gemm(M, M, M, GB, M, false, PHI, Kp, SL, Kp, false, sbuf);
         }
       }
-      for (int e = tid; e < M * M; e += PR_THREADS) SL[(size_t)(e / M) * Kp + (e % M)] += SIG[e];
+      const double* STL = SL + (size_t)(off * M) * Kp + off * M;   // top-left (current horizon) block
+      for (int e = tid; e < M * M; e += PR_THREADS) SL[(size_t)(off * M + e / M) * Kp + off * M + (e % M)] += SIG[e];
       __syncthreads();
       PR_TICK(3);
       // ---- requested horizon? (:346-380)
       if (counter < p.na && i == p.ahead[counter] - 1) {
-        for (int e = tid; e < M * M; e += PR_THREADS) LCH[e] = SL[(size_t)(e / M) * Kp + (e % M)];
+        for (int e = tid; e < M * M; e += PR_THREADS) LCH[e] = STL[(size_t)(e / M) * Kp + (e % M)];
         __syncthreads();
         PR_TICK(5);
         const bool ok = (M <= PR_ST * PR_STAGE / PR_CNB - 1) ? cta_chol_blocked(M, LCH, M, sbuf) : cta_chol(M, LCH, M, sA);
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
           for (int m2 = tid; m2 < M; m2 += PR_THREADS) {
             const double y = p.Y_obs[(size_t)m2 * p.na + counter];
             dv[m2] = y - yp[m2];
-            const double sd = sqrt(SL[(size_t)m2 * Kp + m2]);
+            const double sd = sqrt(STL[(size_t)m2 * Kp + m2]);
             const double zz = (y - yp[m2]) / sd;
             p.PLu[((size_t)chain * M + m2) * p.na + counter] = exp(-0.5 * zz * zz) / (sd * 2.5066282746310002);
           }
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(PR_THREADS) predict_kernel(const PredictParams
         __syncthreads();
         if (p.lpl && p.lpl_sub) {
           const int nv = p.nvoi;
-          for (int e = tid; e < nv * nv; e += PR_THREADS) LCH[e] = SL[(size_t)p.voi[e / nv] * Kp + p.voi[e % nv]];
+          for (int e = tid; e < nv * nv; e += PR_THREADS) LCH[e] = STL[(size_t)p.voi[e / nv] * Kp + p.voi[e % nv]];
           for (int e = tid; e < nv; e += PR_THREADS) dv[e] = p.Y_obs[(size_t)p.voi[e] * p.na + counter] - yp[p.voi[e]];
           __syncthreads();
           const bool ok2 = (nv <= PR_ST * PR_STAGE / PR_CNB - 1) ? cta_chol_blocked(nv, LCH, nv, sbuf) : cta_chol(nv, LCH, nv, sA);
@@ -405,12 +410,12 @@ cudaError_t launch_predict(PredictParams& p, int num_sms, cudaStream_t s, double
   const int nsave = p.R * p.each;
   int grid = 2 * num_sms;
   if (grid > nsave) grid = nsave;
-  p.slab = (size_t)2 * p.Kp * p.Kp + (size_t)3 * p.M * p.M + (size_t)2 * p.Kp + (size_t)(p.M + p.nf) +
+  p.slab = (size_t)p.Kp * p.Kp + (size_t)3 * p.M * p.M + (size_t)2 * p.Kp + (size_t)(p.M + p.nf) +
            (size_t)(p.nsv > 0 ? p.nsv : 1) + (size_t)2 * p.M + (size_t)p.M * p.p * p.M + 8;
   cudaError_t e = cudaMalloc(scratch_out, p.slab * grid * sizeof(double));
   if (e != cudaSuccess) return e;
   p.scratch = *scratch_out;
-  const size_t smem = (size_t)PR_ST * PR_STAGE * sizeof(double);
+  const size_t smem = (size_t)PR_ST * PR_STAGE * sizeof(double) + (size_t)(p.Kp + 2) * sizeof(int);
   e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   predict_kernel<<<grid, PR_THREADS, smem, s>>>(p);

@@ -53,3 +53,33 @@ if "gig" in which:
     print(json.dumps(dict(kernel="bvb_gig", n=n, dev_ms=round(ms, 3), variates_per_us=round(n / ms / 1e3, 1),
                           achieved_GBps=round(gb / (ms * 1e-3), 1), hbm_peak_GBps=hbm_peak,
                           frac=round(gb / (ms * 1e-3) / hbm_peak, 4))), flush=True)
+
+if "predict" in which:
+    # K7 at the config-5 shape with every SM busy (2 resident chains per SM): FP64 tensor roofline
+    M, p, nf, ahead = 200, 4, 1, np.arange(1, 13)
+    Rp = 296 if "--draws" not in sys.argv else R
+    Kp = M * p + 1
+    PHI = np.asfortranarray(rng.standard_normal((Kp, M, Rp)) * 0.3 / np.sqrt(M * p))
+    fl = rng.standard_normal((M, nf, Rp))
+    lv = rng.normal(-1.0, 0.3, (M + nf, Rp))
+    nsv = M + nf
+    mu = rng.normal(-1.0, 0.3, (nsv, Rp)); ph = rng.uniform(0.8, 0.98, (nsv, Rp)); sg = rng.uniform(0.05, 0.3, (nsv, Rp))
+    x = np.concatenate([rng.standard_normal(M * p), [1.0]])
+    yobs = rng.standard_normal((ahead.size, M))
+    t0 = time.perf_counter()
+    out = h.out_of_sample(1, x, PHI, None, fl, lv, ahead, mu, ph, sg, np.arange(nsv), True, True, yobs, False, None, True,
+                          None, None)
+    wall = time.perf_counter() - t0
+    ms = h.last_timing()["rest_ms"]
+    peak = h.measure_fp64_peak()
+    dmma = float(peak["dmma_tflops"] if isinstance(peak, dict) else peak[0])
+    # algorithmic flops per chain: horizons i >= 1: PHI' S (2 M mn^2) + (PHI' S) PHI (2 M^2 mn), mn = min(i, p) M; Cholesky M^3/3
+    fl_chain = 0.0
+    for i in range(int(ahead.max())):
+        mn = min(i, p) * M
+        fl_chain += 2.0 * M * mn * mn + 2.0 * M * M * mn + M ** 3 / 3.0
+    tf = fl_chain * Rp / (ms * 1e-3) / 1e12
+    print(json.dumps(dict(kernel="K7 predict", case="configs[4] M=200 p=4 r=1 ahead=1:12, LPL + predictive draws", draws=Rp,
+                          dev_ms=round(ms, 2), ms_per_draw=round(ms / Rp, 4), algorithmic_GFLOP_per_draw=round(fl_chain / 1e9, 3),
+                          achieved_TFLOPs=round(tf, 2), dmma_peak_TFLOPs=round(dmma, 1), frac=round(tf / dmma, 4),
+                          wall_s=round(wall, 3), finite=bool(np.isfinite(out["predictions"]).all()))), flush=True)
