@@ -409,11 +409,19 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   const bool has_hyper = !dbg_skip_hyper && G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING;
   static const bool dbg_fork_timing = getenv("BVB_DEBUG_FORK_TIMING") != nullptr;
   const bool forked = has_hyper && (!timing || dbg_fork_timing) && G.side != nullptr;
+  static const bool no_ng_side = getenv("BVB_NG_INLINE") != nullptr;
+  const bool ng_side = forked && !no_ng_side && G.sigma_type != BVB_SIGMA_CHOLESKY && fsv_has_ng(G.fsv) && G.ev_ng != nullptr;
   {
     cudaStream_t hs = forked ? G.side : s;
     if (forked) {
       GB_TRY(cudaEventRecord(G.ev_fork, s));
       GB_TRY(cudaStreamWaitEvent(hs, G.ev_fork, 0));
+      // the NG hyper-parameters of the factor loadings only read last sweep's loadings: first on the side stream, the
+      // Sigma_t branch waits for them in front of its loadings kernel (19 us off the critical path)
+      if (ng_side) {
+        GB_TRY(launch_fsv_ng(G.fsv, h->seed, sw, hs));
+        GB_TRY(cudaEventRecord(G.ev_ng, hs));
+      }
     }
     if (has_hyper) {
       GB_TRY(launch_hyper_update(G.hphi.d, h->seed, sw, G.burnin, hs));
@@ -444,7 +452,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     const size_t tm = (size_t)T * M;
     chol_dsq_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(G.dsq.p, G.logvar.p, tm);
   } else {
-    GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));
+    GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s, ng_side ? G.ev_ng : nullptr));
   }
   mark(7);
   if (forked) GB_TRY(cudaStreamWaitEvent(s, G.ev_join, 0));
@@ -462,6 +470,7 @@ static void gibbs_free(bvb_handle* h) {
   for (auto& e : G->ev) if (e) cudaEventDestroy(e);
   if (G->ev_fork) cudaEventDestroy(G->ev_fork);
   if (G->ev_join) cudaEventDestroy(G->ev_join);
+  if (G->ev_ng) cudaEventDestroy(G->ev_ng);
   if (G->side) cudaStreamDestroy(G->side);
   if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
   if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
@@ -894,6 +903,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     GB_TRY(cudaStreamCreateWithPriority(&G.side, cudaStreamNonBlocking, lo));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
+    GB_TRY(cudaEventCreateWithFlags(&G.ev_ng, cudaEventDisableTiming));
   }
   GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
   GB_TRY(cudaEventCreate(&G.ev_chunk[1]));

@@ -537,7 +537,16 @@ __global__ void __launch_bounds__(32 * FAC_SLICES) fsv_factors_kernel(const FsvD
   for (int p = 0; p < r; ++p) d.fac[(size_t)t * r + p] = b[p];
 }
 
-cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s) {
+// The NG hyper-parameters of the loadings only read the loadings of the previous sweep: the Gibbs loop may run them on
+// its side stream next to the SV series kernel (launch_fsv_ng there, `ng_done` here instead of the launch).
+bool fsv_has_ng(const FsvDev& d) { return d.r > 0 && d.ngprior; }
+cudaError_t launch_fsv_ng(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s) {
+  const int units = d.columnwise ? d.r : d.M;
+  fsv_ng_kernel<<<(units + 3) / 4, 128, 0, s>>>(d, seed, sweep);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done) {
   const int S = d.M + d.r;
   const size_t nel = (size_t)(d.T + 1) * S;
   fsv_elem_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(d, seed, sweep);
@@ -548,8 +557,13 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
   }
   if (d.r > 0) {
     if (d.ngprior) {
-      const int units = d.columnwise ? d.r : d.M;
-      fsv_ng_kernel<<<(units + 3) / 4, 128, 0, s>>>(d, seed, sweep);
+      if (ng_done) {
+        cudaError_t e = cudaStreamWaitEvent(s, ng_done, 0);
+        if (e != cudaSuccess) return e;
+      } else {
+        const int units = d.columnwise ? d.r : d.M;
+        fsv_ng_kernel<<<(units + 3) / 4, 128, 0, s>>>(d, seed, sweep);
+      }
     }
     fsv_loadings_kernel<<<(d.M + 3) / 4, 128, 0, s>>>(d, seed, sweep);
     if (d.interweaving != 0) fsv_interweave_kernel<<<d.r, IW_THREADS, 0, s>>>(d, seed, sweep);
