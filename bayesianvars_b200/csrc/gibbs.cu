@@ -208,9 +208,10 @@ __global__ void gibbs_store_kernel(const GibbsStore st, uint32_t* sweep, int* ns
     double* dst = st.ring + (size_t)slot * st.slot_doubles;
     for (int s = 0; s < st.nseg; ++s) {
       const GibbsSeg& sg = st.seg[s];
-      for (size_t i = tid; i < (size_t)sg.rows * sg.cols; i += nth) {
-        const size_t c = i / sg.rows, rr = i % sg.rows;
-        dst[sg.dst_off + i] = sg.src[c * sg.src_ld + sg.src_row0 + rr];
+      const unsigned n = (unsigned)sg.rows * (unsigned)sg.cols, rows = (unsigned)sg.rows;
+      for (unsigned i = (unsigned)tid; i < n; i += (unsigned)nth) {
+        const unsigned c = i / rows, rr = i - c * rows;
+        dst[sg.dst_off + i] = sg.src[(size_t)c * sg.src_ld + sg.src_row0 + rr];
       }
     }
     if (tid == 0) atomicMax(nstored, slot + 1);
@@ -457,7 +458,8 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   mark(7);
   if (forked) GB_TRY(cudaStreamWaitEvent(s, G.ev_join, 0));
   // ---- store + advance
-  gibbs_store_kernel<<<64, 256, 0, s>>>(G.store, G.sweep.p, G.nstored.p);   // also advances the sweep counter
+  // (two CTAs per SM: with 64 CTAs every thread copied ten elements one L2 round trip at a time, 14 us for 1.3 MB)
+  gibbs_store_kernel<<<2 * (h->num_sms > 0 ? h->num_sms : 148), 256, 0, s>>>(G.store, G.sweep.p, G.nstored.p);   // also advances the sweep counter
   mark(8);
   GB_TRY(cudaGetLastError());
   return BVB_OK;
