@@ -43,6 +43,8 @@ struct FsvDev {
 };
 
 cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done = nullptr);
+cudaError_t launch_fsv_series(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s);
+cudaError_t launch_fsv_rest(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done = nullptr);
 bool fsv_has_ng(const FsvDev& d);
 cudaError_t launch_fsv_ng(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s);
 

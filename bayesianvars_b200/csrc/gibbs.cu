@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) gibbs_prep_normals_kernel(double* __restr
                                                                  const double* __restrict__ Y, const double* __restrict__ logvar,
                                                                  const double* __restrict__ facload, const double* __restrict__ fac,
                                                                  int T, int Tp, int M, int r, double* zout, int n, int Mloc,
-                                                                 int j0, uint64_t seed, const uint32_t* sweep) {
+                                                                 int j0, uint64_t seed, const uint32_t* sweep, int write_w) {
   if ((int)blockIdx.x < M) {
     const int j = blockIdx.x;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) gibbs_prep_normals_kernel(double* __restr
       for (int k = 0; k < r; ++k) yh -= facload[(size_t)k * M + j] * fac[(size_t)t * r + k];
       const double nrm = exp(-0.5 * logvar[(size_t)j * T + t]);   // squared like the reference's X_norm'X_norm
       const double w = nrm * nrm;
-      W[(size_t)j * Tp + t] = w;
+      if (write_w) W[(size_t)j * Tp + t] = w;   // (0: gibbs_prep_w_kernel wrote it and the Z tiles may be reading it)
       WY[(size_t)j * Tp + t] = w * yh;
     }
     return;
@@ -185,6 +185,83 @@ __global__ void __launch_bounds__(32 * RESID_SPLIT) gibbs_resid_kernel(double* _
       for (int w = 0; w < RESID_SPLIT; ++w) v += part[w][idx];
       const int t = t0 + fr, j = j0 + 2 * fk + e;
       if (t < T && j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - v;
+    }
+  }
+}
+
+// W = exp(-h) for every equation (the part of gibbs_prep_normals_kernel the pair-GEMM's Z tiles need): launched right
+// after the SV series kernel when the next sweep's Z tiles are computed under the tail of this one.
+__global__ void __launch_bounds__(256) gibbs_prep_w_kernel(double* __restrict__ W, const double* __restrict__ logvar, int T, int Tp) {
+  const int j = blockIdx.x;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const double nrm = exp(-0.5 * logvar[(size_t)j * T + t]);   // same expression as gibbs_prep_normals_kernel
+    W[(size_t)j * Tp + t] = nrm * nrm;
+  }
+}
+
+// Right-hand sides b_j = X'(w_j . yhat_j) + PHI0_j / v_j of the local equations, scattered into the packed systems
+// (what K1 does with its X tiles).  A separate small contraction so that K1's Z tiles - 99.5 % of its work, which only
+// depend on W - can be computed before yhat of the next sweep exists.  Same layout as the residual kernel: one CTA per
+// 8 x 8 output tile, four warps split the contraction over t (both operands are t-contiguous and L2-resident).
+constexpr int RHS_SPLIT = 4;
+__global__ void __launch_bounds__(32 * RHS_SPLIT) gibbs_k1_rhs_kernel(const double* __restrict__ AX, const int2* __restrict__ lutX,
+                                                                     const double* __restrict__ WY, const double* __restrict__ V,
+                                                                     const double* __restrict__ PHI0, double* __restrict__ omega,
+                                                                     int nrows, int Tp, int Mloc, int n, long ldo) {
+  __shared__ double part[RHS_SPLIT][64];
+  const int lane = threadIdx.x & 31, wk = threadIdx.x >> 5;
+  const int ntj = (Mloc + 7) / 8;
+  const int tile = blockIdx.x;
+  const int r0 = (tile / ntj) * 8, j0 = (tile % ntj) * 8;
+  const int fr = lane >> 2, fk = lane & 3;
+  const double* xa = AX + (size_t)min(r0 + fr, nrows - 1) * Tp;
+  const double* pb = WY + (size_t)min(j0 + fr, Mloc - 1) * Tp;
+  const int steps = (Tp + 3) / 4, per = (steps + RHS_SPLIT - 1) / RHS_SPLIT;
+  const int kbeg = min(Tp, 4 * per * wk), kend = min(Tp, 4 * per * (wk + 1));
+  double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+  int k = kbeg;
+  for (; k + 32 <= kend; k += 32) {
+    double av[8], bv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { av[q] = xa[k + 4 * q + fk]; bv[q] = pb[k + 4 * q + fk]; }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      dmma884(c0, c1, av[q], bv[q]);
+      dmma884(d0, d1, av[q + 1], bv[q + 1]);
+    }
+  }
+  {
+    double av[8], bv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int kk = k + 4 * q + fk;
+      av[q] = kk < kend ? xa[kk] : 0.0;
+      bv[q] = kk < kend ? pb[kk] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      dmma884(c0, c1, av[q], bv[q]);
+      dmma884(d0, d1, av[q + 1], bv[q + 1]);
+    }
+  }
+  c0 += d0; c1 += d1;
+  part[wk][fr * 8 + 2 * fk] = c0;
+  part[wk][fr * 8 + 2 * fk + 1] = c1;
+  __syncthreads();
+  if (wk == 0) {
+    const int row = r0 + fr;
+    const int2 l = row < nrows ? lutX[row] : make_int2(-1, -1);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int idx = fr * 8 + 2 * fk + e;
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < RHS_SPLIT; ++w) v += part[w][idx];
+      const int j = j0 + 2 * fk + e;
+      if (l.x >= 0 && j < Mloc) {
+        if (l.y >= 0 && PHI0) v += PHI0[(size_t)j * n + l.y] / V[(size_t)j * n + l.y];
+        omega[(size_t)j * ldo + l.x] = v;
+      }
     }
   }
 }
@@ -337,6 +414,38 @@ void add_seg(GibbsStore& st, const double* src, int rows, int cols, int src_ld, 
 
 }  // namespace
 
+// Z tiles of the pair-GEMM (Omega_j = Z W_j + diag(1/v_j)) of the local equations from the current W and V_prior.
+static cudaError_t enqueue_k1z(Gibbs& G, cudaStream_t s) {
+  const int Kp = G.Kp;
+  K1Params k1{};
+  k1.A = G.A.p; k1.W = G.W.p + (size_t)G.j0 * G.geom.Tp; k1.WY = G.WY.p + (size_t)G.j0 * G.geom.Tp; k1.lut = G.lut.p;
+  k1.V = G.Vprior.p + (size_t)G.j0 * Kp; k1.PHI0 = G.PHI0.p + (size_t)G.j0 * Kp; k1.omega = G.omega.p;
+  k1.Tp = G.geom.Tp; k1.nZtiles = G.geom.nZtiles; k1.ntiles = G.geom.nZtiles;     // no X tiles: gibbs_k1_rhs_kernel
+  k1.M = G.nloc; k1.n = Kp; k1.ldo = G.geom.ldo;
+  return launch_k1(k1, s);
+}
+
+// Normals of the local equations, WY = w * yhat (and W unless the Z tiles already own it) for the next PHI draw.
+static cudaError_t enqueue_prep(bvb_handle* h, Gibbs& G, cudaStream_t s, int write_w) {
+  const size_t nz = (size_t)G.Kp * G.nloc;
+  gibbs_prep_normals_kernel<<<(unsigned)(G.M + (nz + 255) / 256), 256, 0, s>>>(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p,
+                                                                              G.fac.p, G.T, G.geom.Tp, G.M, G.r, G.Zn.p, G.Kp,
+                                                                              G.nloc, G.j0, h->seed, G.sweep.p, write_w);
+  return cudaGetLastError();
+}
+
+// Right-hand sides of the local systems from WY (K1's X tiles as a separate small contraction).
+static cudaError_t enqueue_k1rhs(Gibbs& G, cudaStream_t s) {
+  const int Kp = G.Kp, nrows = G.geom.nXtiles * K1_BM;
+  const int tiles = ((nrows + 7) / 8) * ((G.nloc + 7) / 8);
+  gibbs_k1_rhs_kernel<<<tiles, 32 * RHS_SPLIT, 0, s>>>(G.A.p + (size_t)G.geom.nZtiles * K1_BM * G.geom.Tp,
+                                                      G.lut.p + (size_t)G.geom.nZtiles * K1_BM,
+                                                      G.WY.p + (size_t)G.j0 * G.geom.Tp, G.Vprior.p + (size_t)G.j0 * Kp,
+                                                      G.PHI0.p + (size_t)G.j0 * Kp, G.omega.p, nrows, G.geom.Tp, G.nloc, Kp,
+                                                      G.geom.ldo);
+  return cudaGetLastError();
+}
+
 // One sweep's worth of launches on h->stream (captured into a graph by the caller).
 static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   cudaStream_t s = h->stream;
@@ -369,19 +478,18 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
                                                                    G.PHI_tol, h->seed, sw, G.status.p);
   } else if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
     // ---- 1) PHI | .  (factor structure: equations independent)
-    {
-      const size_t nz = (size_t)Kp * G.nloc;
-      gibbs_prep_normals_kernel<<<(unsigned)(M + (nz + 255) / 256), 256, 0, s>>>(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p,
-                                                                                G.fac.p, T, G.geom.Tp, M, G.r, G.Zn.p, Kp,
-                                                                                G.nloc, G.j0, h->seed, sw);
+    // K1 is split.  The Z tiles (X'diag(w)X, 99.5 % of its work) only need W = exp(-h), which is final once the SV series
+    // kernel of the PREVIOUS sweep has run, so that sweep computed them on the side stream under its own tail, and its
+    // main stream finished with this sweep's normals, WY and right-hand sides (enqueue_assemble below).  Only the first
+    // sweep of a chain (and the timing pass, so that phases "prep" and "k1" show their cost) assemble here.
+    if (!G.k1z_valid || timing) {
+      GB_TRY(enqueue_prep(h, G, s, 1));
+      mark(1);
+      GB_TRY(enqueue_k1z(G, s));
+      GB_TRY(enqueue_k1rhs(G, s));
+    } else {
+      mark(1);
     }
-    mark(1);
-    K1Params k1{};
-    k1.A = G.A.p; k1.W = G.W.p + (size_t)G.j0 * G.geom.Tp; k1.WY = G.WY.p + (size_t)G.j0 * G.geom.Tp; k1.lut = G.lut.p;
-    k1.V = G.Vprior.p + (size_t)G.j0 * Kp; k1.PHI0 = G.PHI0.p + (size_t)G.j0 * Kp; k1.omega = G.omega.p;
-    k1.Tp = G.geom.Tp; k1.nZtiles = G.geom.nZtiles; k1.ntiles = G.geom.nZtiles + G.geom.nXtiles;
-    k1.M = G.nloc; k1.n = Kp; k1.ldo = G.geom.ldo;
-    GB_TRY(launch_k1(k1, s));
     mark(2);
     K2Params k2{};
     k2.omega = G.omega.p; k2.colbase = G.colbase.p; k2.z = G.Zn.p; k2.phi = G.PHI.p + (size_t)G.j0 * Kp;
@@ -410,7 +518,10 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   const bool has_hyper = !dbg_skip_hyper && G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING;
   static const bool dbg_fork_timing = getenv("BVB_DEBUG_FORK_TIMING") != nullptr;
   const bool forked = has_hyper && (!timing || dbg_fork_timing) && G.side != nullptr;
-  static const bool no_ng_side = getenv("BVB_NG_INLINE") != nullptr;
+  const bool no_rotate = getenv("BVB_NO_ROTATE") != nullptr;     // (read per enqueue: tests compare both forms)
+  const bool rotate = !no_rotate && K > 0 && G.sigma_type != BVB_SIGMA_CHOLESKY && !G.huge && G.side != nullptr &&
+                      G.ev_series != nullptr && G.ev_k1z != nullptr;
+  const bool no_ng_side = getenv("BVB_NG_INLINE") != nullptr;
   const bool ng_side = forked && !no_ng_side && G.sigma_type != BVB_SIGMA_CHOLESKY && fsv_has_ng(G.fsv) && G.ev_ng != nullptr;
   {
     cudaStream_t hs = forked ? G.side : s;
@@ -453,7 +564,17 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     const size_t tm = (size_t)T * M;
     chol_dsq_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(G.dsq.p, G.logvar.p, tm);
   } else {
-    GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s, ng_side ? G.ev_ng : nullptr));
+    GB_TRY(launch_fsv_series(G.fsv, h->seed, sw, s));
+    if (rotate && !timing) {
+      // the idiosyncratic log-variances are final: the next sweep's Z tiles run on the (low-priority) side stream,
+      // behind the hyper-parameters (V_prior), under loadings -> interweaving -> factors -> store
+      GB_TRY(cudaEventRecord(G.ev_series, s));
+      GB_TRY(cudaStreamWaitEvent(G.side, G.ev_series, 0));
+      gibbs_prep_w_kernel<<<M, 256, 0, G.side>>>(G.W.p, G.logvar.p, T, G.geom.Tp);
+      GB_TRY(enqueue_k1z(G, G.side));
+      GB_TRY(cudaEventRecord(G.ev_k1z, G.side));
+    }
+    GB_TRY(launch_fsv_rest(G.fsv, h->seed, sw, s, ng_side ? G.ev_ng : nullptr));
   }
   mark(7);
   if (forked) GB_TRY(cudaStreamWaitEvent(s, G.ev_join, 0));
@@ -461,6 +582,18 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   // (two CTAs per SM: with 64 CTAs every thread copied ten elements one L2 round trip at a time, 14 us for 1.3 MB)
   gibbs_store_kernel<<<2 * (h->num_sms > 0 ? h->num_sms : 148), 256, 0, s>>>(G.store, G.sweep.p, G.nstored.p);   // also advances the sweep counter
   mark(8);
+  if (rotate) {
+    // the store advanced the sweep counter: normals, WY and right-hand sides of the NEXT sweep (disjoint from the entries
+    // of `omega` the Z tiles are writing), then the join with the Z tiles
+    if (timing) {   // serial form of the same tail (the timing pass measures the phases one after the other)
+      gibbs_prep_w_kernel<<<M, 256, 0, s>>>(G.W.p, G.logvar.p, T, G.geom.Tp);
+      GB_TRY(enqueue_k1z(G, s));
+    }
+    GB_TRY(enqueue_prep(h, G, s, 0));
+    GB_TRY(enqueue_k1rhs(G, s));
+    if (!timing) GB_TRY(cudaStreamWaitEvent(s, G.ev_k1z, 0));
+  }
+  G.k1z_valid = rotate;
   GB_TRY(cudaGetLastError());
   return BVB_OK;
 }
@@ -473,6 +606,8 @@ static void gibbs_free(bvb_handle* h) {
   if (G->ev_fork) cudaEventDestroy(G->ev_fork);
   if (G->ev_join) cudaEventDestroy(G->ev_join);
   if (G->ev_ng) cudaEventDestroy(G->ev_ng);
+  if (G->ev_series) cudaEventDestroy(G->ev_series);
+  if (G->ev_k1z) cudaEventDestroy(G->ev_k1z);
   if (G->side) cudaStreamDestroy(G->side);
   if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
   if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
@@ -906,6 +1041,8 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     GB_TRY(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_ng, cudaEventDisableTiming));
+    GB_TRY(cudaEventCreateWithFlags(&G.ev_series, cudaEventDisableTiming));
+    GB_TRY(cudaEventCreateWithFlags(&G.ev_k1z, cudaEventDisableTiming));
   }
   GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
   GB_TRY(cudaEventCreate(&G.ev_chunk[1]));

@@ -101,7 +101,8 @@ struct Gibbs {
   GBuf<double> ring;
   double* pinned[2] = {nullptr, nullptr};
   cudaStream_t side = nullptr;                 // hyper-parameter branch of the sweep graph
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ng = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ng = nullptr, ev_series = nullptr, ev_k1z = nullptr;
+  bool k1z_valid = false;                      // the Z tiles of the NEXT PHI draw are already in `omega` (see enqueue_sweep)
   cudaEvent_t ev_pin[2] = {nullptr, nullptr};
   bvb_draws out{};
   size_t off_PHI = 0, off_Vprior = 0, off_logvar = 0, off_svpara = 0, off_hyper = 0, off_facload = 0, off_fac = 0;

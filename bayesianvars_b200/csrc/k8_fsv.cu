@@ -546,15 +546,21 @@ cudaError_t launch_fsv_ng(const FsvDev& d, uint64_t seed, const uint32_t* sweep,
   return cudaGetLastError();
 }
 
-cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done) {
+// First half of the update: mixture indicators + AWOL normals, then h and (mu, phi, sigma) of every series.  The
+// idiosyncratic log-variances are FINAL after this (the interweaving step only moves the factor log-variances), which is
+// what lets the Gibbs loop start the next sweep's pair-GEMM here.
+cudaError_t launch_fsv_series(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s) {
   const int S = d.M + d.r;
   const size_t nel = (size_t)(d.T + 1) * S;
   fsv_elem_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(d, seed, sweep);
-  {
-    const size_t smem = (size_t)(6 * (d.T + 1)) * sizeof(double) + (size_t)d.T + 16;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(fsv_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fsv_series_kernel<<<S, SV_THREADS, smem, s>>>(d, seed, sweep);
-  }
+  const size_t smem = (size_t)(6 * (d.T + 1)) * sizeof(double) + (size_t)d.T + 16;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fsv_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fsv_series_kernel<<<S, SV_THREADS, smem, s>>>(d, seed, sweep);
+  return cudaGetLastError();
+}
+
+// Second half: NG hyper-parameters (or the event of their side-stream launch), loadings, interweaving, factors.
+cudaError_t launch_fsv_rest(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done) {
   if (d.r > 0) {
     if (d.ngprior) {
       if (ng_done) {
@@ -577,6 +583,12 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
     }
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done) {
+  cudaError_t e = launch_fsv_series(d, seed, sweep, s);
+  if (e != cudaSuccess) return e;
+  return launch_fsv_rest(d, seed, sweep, s, ng_done);
 }
 
 }  // namespace bvb
