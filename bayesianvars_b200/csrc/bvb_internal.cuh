@@ -88,6 +88,7 @@ struct K2Params {
   long long* prof = nullptr;  // optional [8] phase cycle counters (debug)
   int mode = 0;               // 0: factor + forward solve (rhs row) + back-solve/draw; 1: factor only
   int debug_mode = 0;         // 1: skip the DMMA of the update loop, 2: skip its loads (timing experiments only)
+  int direct = 1;             // look-ahead kernel: operands of the update straight from L2 into registers (BVB_K2_DIRECT)
 };
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s);
 cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s);

@@ -645,6 +645,48 @@ __device__ __forceinline__ void k2v_stage(int nq, double (&acc)[K2_MAXQ][4][2], 
   }
 }
 
+// Part A without the shared-memory ring (p.direct, BVB_K2_DIRECT=0 switches it off): every A element of the update is
+// used by exactly one warp (the owner of its m8 tile), so staging it through shared memory buys no reuse - each GEMM
+// warp loads its own fragments straight from L2 (8 rows x 4 columns per load: four 64-byte segments), two k4-steps in
+// flight, no barrier in the loop.  The B fragments (the 32 rows of block k+1) are the same for all 15 warps and come
+// through L1.  Same k order, same accumulators: bit-identical to the ring form.  Measured 333.8 -> 328.6 us: the
+// stream through shared memory was NOT what held part A at 8.5 B/clk/SM.  (Also measured: dealing the n8 units of the
+// last, mostly empty round of m8 tiles one at a time over the warps - 47 tiles are 3 full rounds + 2 tiles - is SLOWER,
+// 408 us: the extra units have no operand reuse and their second pass over k runs at two loads per DMMA.)
+template <int NQ>
+__device__ __forceinline__ void k2v_direct_mma(double (&acc)[K2_MAXQ][4][2], const double* __restrict__ om,
+                                               const int* colb, int c0n, int c0, int g, int fr, int fk) {
+  const double* rowbase = om + c0n + fr;
+#pragma unroll 1
+  for (int c = 0; c < c0; c += 8) {
+    double av[2][NQ], bv[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const double* base = rowbase + colb[c + 4 * ks + fk];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) av[ks][q] = __ldcg(base + 8 * (g + K2V_G * q));
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bv[ks][nt] = __ldca(base + 8 * nt);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], av[ks][q], bv[ks][nt]);
+  }
+}
+__device__ __forceinline__ void k2v_direct(int nq, double (&acc)[K2_MAXQ][4][2], const double* om, const int* colb, int c0n,
+                                           int c0, int g, int fr, int fk) {
+  switch (nq) {
+    case 1: k2v_direct_mma<1>(acc, om, colb, c0n, c0, g, fr, fk); break;
+    case 2: k2v_direct_mma<2>(acc, om, colb, c0n, c0, g, fr, fk); break;
+    case 3: k2v_direct_mma<3>(acc, om, colb, c0n, c0, g, fr, fk); break;
+    case 4: k2v_direct_mma<4>(acc, om, colb, c0n, c0, g, fr, fk); break;
+    default: break;
+  }
+}
+
 __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Params p, double* __restrict__ linv_ws, int ring_doubles) {
   constexpr int NWARPS = K2_NWARPS, MAXQ = K2_MAXQ, NTHREADS = K2_NWARPS * 32;
   extern __shared__ __align__(16) double smem[];
@@ -897,6 +939,9 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
             }
           }
         };
+        if (p.direct && fulln) {
+          k2v_direct(nqn, acc, om, colb, c0n, c0, g, fr, fk);
+        } else {
         for (int s = 0; s < S - 1; ++s) {
           if (s < nchunks) load_chunk(s, s);
           cp_async_commit();
@@ -914,6 +959,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
             k2v_stage(nqn, acc, ring + (size_t)(ch % S) * stage_cd + (size_t)u * sub_d, RSl, g, fr, fk);
         }
         cp_async_wait<0>();
+        }
         k2v_bar_gemm();                                      // ring is free
       }
       if (prof && real && k + 1 < 16) p.prof[8 + k + 1] += clock64() - tprev;
@@ -1089,7 +1135,9 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     const size_t smem2 = k2v_smem_bytes(p.n, &ring);
     cudaError_t e2 = cudaFuncSetAttribute(k2_cholsolve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e2 != cudaSuccess) return e2;
-    k2_cholsolve_v2<<<p.M, K2_NWARPS * 32, smem2, s>>>(p, g_linv_ws, (int)ring);
+    K2Params q = p;
+    { const char* ed = getenv("BVB_K2_DIRECT"); if (ed) q.direct = atoi(ed); }
+    k2_cholsolve_v2<<<q.M, K2_NWARPS * 32, smem2, s>>>(q, g_linv_ws, (int)ring);
     return cudaGetLastError();
   }
   const int rt = k2_pick_rt(p.n);
