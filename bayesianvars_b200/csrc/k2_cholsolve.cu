@@ -833,6 +833,8 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
   } else {
     // =================================== GEMM warps ===================================
     const int fr = lane >> 2, fk = lane & 3;
+    // (measured: handing the tiles of the last, partial round to the GEMM warps that share a sub-partition with the panel
+    // warp - warps 4, 8, 12 as g = 0, 1, 2 - costs 5 us: the panel warp's pivot chain is slowed more than the tiles gain)
     const int g = warp - 1;                                  // 0..14, owns m8 tiles g + 15 q
     const int tg = tid - 32;                                 // 0..479
     // original entries of a FULL block column kk (rows c0.., 32 columns) -> ring as [c][RSl]
