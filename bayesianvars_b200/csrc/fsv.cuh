@@ -27,6 +27,8 @@ struct FsvDev {
   double* scratch = nullptr;        // unused by the CTA-per-series kernel
   double* eidi = nullptr;           // T x M idiosyncratic residuals (series-major)
   double* wexp = nullptr;           // T x M exp(-h) of the idiosyncratic series (refreshed by the series kernel)
+  double* Wk1 = nullptr;            // [M][Tp] weight operand of the pair-GEMM (written by the series kernel when set)
+  int Tp = 0;
   int* status = nullptr;
   // configuration
   const int* hetero = nullptr;      // [M+r]

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) gibbs_prep_normals_kernel(double* __restr
       for (int k = 0; k < r; ++k) yh -= facload[(size_t)k * M + j] * fac[(size_t)t * r + k];
       const double nrm = exp(-0.5 * logvar[(size_t)j * T + t]);   // squared like the reference's X_norm'X_norm
       const double w = nrm * nrm;
-      if (write_w) W[(size_t)j * Tp + t] = w;   // (0: gibbs_prep_w_kernel wrote it and the Z tiles may be reading it)
+      if (write_w) W[(size_t)j * Tp + t] = w;   // (0: the SV series kernel wrote it and the Z tiles may be reading it)
       WY[(size_t)j * Tp + t] = w * yh;
     }
     return;
@@ -186,16 +186,6 @@ __global__ void __launch_bounds__(32 * RESID_SPLIT) gibbs_resid_kernel(double* _
       const int t = t0 + fr, j = j0 + 2 * fk + e;
       if (t < T && j < M) resid[(size_t)j * T + t] = Y[(size_t)j * T + t] - v;
     }
-  }
-}
-
-// W = exp(-h) for every equation (the part of gibbs_prep_normals_kernel the pair-GEMM's Z tiles need): launched right
-// after the SV series kernel when the next sweep's Z tiles are computed under the tail of this one.
-__global__ void __launch_bounds__(256) gibbs_prep_w_kernel(double* __restrict__ W, const double* __restrict__ logvar, int T, int Tp) {
-  const int j = blockIdx.x;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const double nrm = exp(-0.5 * logvar[(size_t)j * T + t]);   // same expression as gibbs_prep_normals_kernel
-    W[(size_t)j * Tp + t] = nrm * nrm;
   }
 }
 
@@ -564,13 +554,17 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     const size_t tm = (size_t)T * M;
     chol_dsq_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(G.dsq.p, G.logvar.p, tm);
   } else {
-    GB_TRY(launch_fsv_series(G.fsv, h->seed, sw, s));
+    {
+      // rotated graph: the series kernel writes next sweep's W itself (every idiosyncratic series passes through it)
+      FsvDev fs = G.fsv;
+      if (rotate) { fs.Wk1 = G.W.p; fs.Tp = G.geom.Tp; }
+      GB_TRY(launch_fsv_series(fs, h->seed, sw, s));
+    }
     if (rotate && !timing) {
       // the idiosyncratic log-variances are final: the next sweep's Z tiles run on the (low-priority) side stream,
       // behind the hyper-parameters (V_prior), under loadings -> interweaving -> factors -> store
       GB_TRY(cudaEventRecord(G.ev_series, s));
       GB_TRY(cudaStreamWaitEvent(G.side, G.ev_series, 0));
-      gibbs_prep_w_kernel<<<M, 256, 0, G.side>>>(G.W.p, G.logvar.p, T, G.geom.Tp);
       GB_TRY(enqueue_k1z(G, G.side));
       GB_TRY(cudaEventRecord(G.ev_k1z, G.side));
     }
@@ -585,10 +579,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   if (rotate) {
     // the store advanced the sweep counter: normals, WY and right-hand sides of the NEXT sweep (disjoint from the entries
     // of `omega` the Z tiles are writing), then the join with the Z tiles
-    if (timing) {   // serial form of the same tail (the timing pass measures the phases one after the other)
-      gibbs_prep_w_kernel<<<M, 256, 0, s>>>(G.W.p, G.logvar.p, T, G.geom.Tp);
-      GB_TRY(enqueue_k1z(G, s));
-    }
+    if (timing) GB_TRY(enqueue_k1z(G, s));   // serial form of the same tail (the timing pass measures phase by phase)
     GB_TRY(enqueue_prep(h, G, s, 0));
     GB_TRY(enqueue_k1rhs(G, s));
     if (!timing) GB_TRY(cudaStreamWaitEvent(s, G.ev_k1z, 0));

@@ -94,7 +94,11 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
         bc[0] = log((d.priorhomo[d.M + s] + 0.5 * ss[0]) / rng.gamma(d.priorhomo[s] + 0.5 * T));
       }
       __syncthreads();
-      for (int t = tid; t < T; t += SV_THREADS) { h[t] = bc[0]; d.wexp[(size_t)s * T + t] = exp(-bc[0]); }
+      for (int t = tid; t < T; t += SV_THREADS) {
+        h[t] = bc[0];
+        d.wexp[(size_t)s * T + t] = exp(-bc[0]);
+        if (d.Wk1) { const double nrm = exp(-0.5 * bc[0]); d.Wk1[(size_t)s * d.Tp + t] = nrm * nrm; }
+      }
     }  // homoskedastic factors keep h == 0
     return;
   }
@@ -251,7 +255,11 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
     for (int t = 1 + tid; t <= T; t += SV_THREADS) {
       const double hv = mu_n + sg_n * ((hh[t] - mu_c) / sg_c);
       h[t - 1] = hv;
-      if (s < d.M) d.wexp[(size_t)s * T + t - 1] = exp(-hv);
+      if (s < d.M) {
+        d.wexp[(size_t)s * T + t - 1] = exp(-hv);
+        // the pair-GEMM's weight operand of the NEXT sweep, same expression as gibbs_prep_normals_kernel (bit-identical)
+        if (d.Wk1) { const double nrm = exp(-0.5 * hv); d.Wk1[(size_t)s * d.Tp + t - 1] = nrm * nrm; }
+      }
     }
     if (tid == 0) {
       d.logvar0[s] = mu_n + sg_n * ((hh[0] - mu_c) / sg_c);
