@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(MAXT, 1) irf_cluster_kernel(const IrfParams p,
               }
             }
           }
-          for (int u = 0; k < Kp; k += 32, ++u) {
+          for (; k < Kp; k += 32) {
             double cv[CPW];
             cv[0] = col[k];
             if (CPW > 1) cv[CPW - 1] = colb[k];
