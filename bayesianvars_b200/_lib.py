@@ -33,6 +33,8 @@ SIGNATURES = {
     "bvb_irf": (C.c_int, [_vp] + [C.c_int] * 9 + [_dp] * 7),
     "bvb_predict": (C.c_int, [_vp] + [C.c_int] * 7 + [_dp] * 5 + [_ip, C.c_int, _dp, _dp, _dp, _ip, C.c_int, C.c_int, _dp,
                                               C.c_int, _ip, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "bvb_predh": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "bvb_vcov": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
     "bvb_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "bvb_last_timing": (C.c_int, [_vp, _dp]),
 }

@@ -138,6 +138,39 @@ class Handle:
         self._check(rc)
         return out
 
+    # -- section 8(f) rank 2: predh / vcov_cpp (src/utilities_cpp.cpp:181-212, 436-472) --
+    def predh(self, logvar_T, ahead, each, sv_mu, sv_phi, sv_sigma, z=None):
+        """Same arguments as the Rcpp export (R/RcppExports.R:54); returns (len(ahead), M, R*each).
+        z (optional, parity tests): the injected standard normals, shape (len(ahead), each, M, R)."""
+        lv = np.asfortranarray(logvar_T, dtype=np.float64)
+        M, R = lv.shape
+        ahead = np.ascontiguousarray(ahead, dtype=np.int32)
+        out = np.empty((ahead.size, M, R * int(each)), order="F")
+        F = lambda a: fptr(np.asfortranarray(a, dtype=np.float64).reshape(-1, order="F"))
+        zz = None
+        if z is not None:   # (na, each, M, R) -> C-ordered [na][each][R][M]
+            zz = np.ascontiguousarray(np.transpose(np.asarray(z, dtype=np.float64), (0, 1, 3, 2)))
+        rc = self._lib.bvb_predh(self._h, M, R, int(each), ahead.ctypes.data_as(C.POINTER(C.c_int)), int(ahead.size), F(lv),
+                                 F(sv_mu), F(sv_phi), F(sv_sigma), fptr(zz.reshape(-1)) if zz is not None else None,
+                                 fptr(out.reshape(-1, order="F")))
+        self._check(rc)
+        return out
+
+    def vcov_cpp(self, factor, facload, logvar, U, M, factors):
+        """Same arguments as the Rcpp export (R/RcppExports.R:66); returns (T*M, M, nsave)."""
+        lv = np.asfortranarray(logvar, dtype=np.float64)
+        T, S, R = lv.shape
+        factor = bool(factor)
+        nf = int(factors) if factor else 0
+        fl = np.asfortranarray(facload, dtype=np.float64) if factor and nf > 0 else None
+        uv = np.asfortranarray(U, dtype=np.float64) if not factor and M > 1 else None
+        out = np.empty((T * M, M, R), order="F")
+        rc = self._lib.bvb_vcov(self._h, int(factor), T, int(M), nf, R, fptr(fl.reshape(-1, order="F")) if fl is not None else None,
+                                fptr(lv.reshape(-1, order="F")), fptr(uv.reshape(-1, order="F")) if uv is not None else None,
+                                fptr(out.reshape(-1, order="F")))
+        self._check(rc)
+        return out
+
     # -- a15: out_of_sample (src/utilities_cpp.cpp:216-393) ----------------------------
     def out_of_sample(self, each, X_T_plus_1, PHI, U, facload, logvar_T, ahead, sv_mu, sv_phi, sv_sigma,
                       sv_indicator, factor, LPL, Y_obs, LPL_subset, VoI, simulate_predictive,

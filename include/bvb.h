@@ -274,6 +274,21 @@ int bvb_predict(bvb_handle* h, int each, int Kp, int M, int R, int n_factors, in
                 const double* z_logvar, const double* z_pred, double* LPL_draws,
                 double* PL_univariate_draws, double* LPL_sub_draws, double* predictions);
 
+/* ---- section 8(f) rank 2: predh (src/utilities_cpp.cpp:181-212) ----------------------
+ * Log-variance forecasts h_{T+ahead} | h_T of the AR(1) SV processes.  logvar_T, sv_mu, sv_phi, sv_sigma M x R
+ * (column-major, one column per stored draw); ahead[n_ahead] strictly increasing (1-based).  z: NULL = counter-based
+ * device normals, otherwise the normals of `norm_rand.imbue(R::norm_rand)` (:202-203), C-ordered
+ * [n_ahead][each][R][M].  out: n_ahead x M x (R*each) column-major; replicate j fills slices j*R .. (j+1)*R-1 (:205). */
+int bvb_predh(bvb_handle* h, int M, int R, int each, const int* ahead, int n_ahead, const double* logvar_T,
+              const double* sv_mu, const double* sv_phi, const double* sv_sigma, const double* z, double* out);
+
+/* ---- section 8(f) rank 2: vcov_cpp (src/utilities_cpp.cpp:436-472) -------------------
+ * Posterior draws of Sigma_t.  logvar T x (M + n_factors) x R (factor) or T x M x R (cholesky); facload
+ * M x n_factors x R; U n_U x R (upper-triangular elements in trimatu_ind order).  out: (T*M) x M x R column-major,
+ * slice i = the cube (T, M, M) flattened as the reference does (:448-449): element (t, a, b) at row t + T*a, column b. */
+int bvb_vcov(bvb_handle* h, int factor, int T, int M, int n_factors, int R, const double* facload,
+             const double* logvar, const double* U, double* out);
+
 /* ---- diagnostics -------------------------------------------------------------
  * Measured FP64 peaks on this device (own micro-kernels, register-resident):
  * out[0] = DMMA m8n8k4 TFLOP/s, out[1] = DFMA TFLOP/s, out[2] = SM clock MHz
