@@ -181,3 +181,29 @@ NumericMatrix sample_PHI_cholesky(const NumericMatrix PHI, const NumericMatrix& 
                                    X.begin(), U.begin(), d_sqrt.begin(), V_prior.begin(), z.begin(), out.begin()));
   return out;
 }
+
+// src/utilities_cpp.cpp:436-472 -> bvb_vcov (same arguments, same (T*M, M, nsave) result)
+// [[Rcpp::export]]
+NumericVector vcov_cpp(const bool& factor, const NumericVector& facload, const NumericVector& logvar, const NumericMatrix& U,
+                       const int& M, const int& factors) {
+  Handle H;
+  const IntegerVector dl = logvar.attr("dim");          // (T, M + factors | M, nsave)
+  const int T = dl[0], nsave = dl[2];
+  NumericVector out((size_t)T * M * M * nsave);
+  out.attr("dim") = Dimension(T * M, M, nsave);
+  check(H.h, bvb_vcov(H.h, factor ? 1 : 0, T, M, factors, nsave, facload.begin(), logvar.begin(), U.begin(), out.begin()));
+  return out;
+}
+
+// src/utilities_cpp.cpp:181-212 -> bvb_predh (device Philox normals; the key comes from R's RNG through Handle)
+// [[Rcpp::export]]
+NumericVector predh(const NumericMatrix& logvar_T, const IntegerVector& ahead, const int& each, const NumericMatrix& sv_mu,
+                    const NumericMatrix& sv_phi, const NumericMatrix& sv_sigma) {
+  Handle H;
+  const int M = logvar_T.nrow(), R = logvar_T.ncol();
+  NumericVector out((size_t)ahead.size() * M * R * each);
+  out.attr("dim") = Dimension(ahead.size(), M, R * each);
+  check(H.h, bvb_predh(H.h, M, R, each, ahead.begin(), ahead.size(), logvar_T.begin(), sv_mu.begin(), sv_phi.begin(),
+                       sv_sigma.begin(), /*z*/ nullptr, out.begin()));
+  return out;
+}
