@@ -7,8 +7,8 @@ sys.path.insert(0, ".")
 import numpy as np
 from bayesianvars_b200 import Handle
 
-args = [a for a in sys.argv[1:] if a in ("irf", "gig", "predict")]
-which = args or ["irf", "gig", "predict"]
+args = [a for a in sys.argv[1:] if a in ("irf", "gig", "predict", "vcov")]
+which = args or ["irf", "gig", "predict", "vcov"]
 R = int(sys.argv[sys.argv.index("--draws") + 1]) if "--draws" in sys.argv else 1000
 try:
     peaks = json.load(open("MEASURED_PEAKS.json"))
@@ -83,3 +83,18 @@ if "predict" in which:
                           dev_ms=round(ms, 2), ms_per_draw=round(ms / Rp, 4), algorithmic_GFLOP_per_draw=round(fl_chain / 1e9, 3),
                           achieved_TFLOPs=round(tf, 2), dmma_peak_TFLOPs=round(dmma, 1), frac=round(tf / dmma, 4),
                           wall_s=round(wall, 3), finite=bool(np.isfinite(out["predictions"]).all()))), flush=True)
+
+if "vcov" in which:
+    # K9 vcov at the config-3 shape: output-write bound (T * M * M doubles per draw)
+    T, M, nf, Rv = 500, 100, 1, 40
+    fl = rng.standard_normal((M, nf, Rv))
+    lv = rng.normal(-1.0, 0.3, (T, M + nf, Rv))
+    best = 1e30
+    for _ in range(2):
+        out = h.vcov_cpp(True, fl, lv, None, M, nf)
+        best = min(best, h.last_timing()["rest_ms"])
+    gb = out.nbytes / 1e9
+    print(json.dumps(dict(kernel="K9 vcov", case="configs[2] T=500 M=100 r=1 (factor)", draws=Rv, dev_ms=round(best, 3),
+                          algorithmic_GB_written=round(gb, 3), achieved_GBps=round(gb / (best * 1e-3), 1),
+                          hbm_peak_GBps=hbm_peak, frac=round(gb / (best * 1e-3) / hbm_peak, 4),
+                          finite=bool(np.isfinite(out).all()))), flush=True)
