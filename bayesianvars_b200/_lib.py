@@ -25,6 +25,7 @@ SIGNATURES = {
     "bvb_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_uint64]),
     "bvb_destroy": (None, [_vp]),
     "bvb_version": (C.c_char_p, []),
+    "bvb_set_seed": (C.c_int, [_vp, C.c_uint64]),
     "bvb_last_error": (C.c_int, [_vp, _ip, _ip, _ip, C.c_char_p, C.c_int]),
     "bvb_phi_draw_factor": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp]),
     "bvb_phi_draw_cholesky": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

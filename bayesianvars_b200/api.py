@@ -26,6 +26,12 @@ class Handle:
             raise BvbError(rc, "bvb_create failed: no usable sm_100a CUDA device (there is no CPU fallback)")
         self._h = h
         self.device = device
+        self.seed = int(seed)
+
+    def reseed(self, seed: int):
+        """New Philox key for the calls that follow (bvb_set_seed)."""
+        self._check(self._lib.bvb_set_seed(self._h, C.c_uint64(int(seed))))
+        self.seed = int(seed)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -115,6 +121,16 @@ class Handle:
         rc = self._lib.bvb_gig(self._h, int(n), fptr(lam), lam.size, fptr(chi), chi.size, fptr(psi), psi.size,
                                C.c_uint64(stream), fptr(out))
         self._check(rc)
+        return out
+
+    # -- a12: tolerance clamp (src/bvar_cpp.cpp:534-559) ---------------------------
+    def tolerance_clamp(self, PHI, PHI0, K, tol, sweep=0):
+        """|PHI - PHI0| >= tol on the first K rows; exact zeros get a random sign.  Returns the clamped copy."""
+        from . import bvar as _b  # registers the signature
+        out = np.asfortranarray(PHI, dtype=np.float64).copy(order="F")
+        P0 = np.asfortranarray(PHI0, dtype=np.float64)
+        Kp, M = out.shape
+        self._check(self._lib.bvb_tolerance_clamp(self._h, int(K), Kp, M, fptr(out), fptr(P0), float(tol), int(sweep)))
         return out
 
     # -- a14: irf_cpp (src/irf.cpp:468-524) ---------------------------------------

@@ -74,6 +74,9 @@ def _register_gibbs_signatures():
                                      C.POINTER(StartVals), _ip, C.c_double, C.c_double, C.c_int, C.POINTER(Draws)]),
         "bvb_gibbs_run": (C.c_int, [vp, C.c_int, _ip]),
         "bvb_gibbs_timing": (C.c_int, [vp, _dp]),
+        "bvb_gibbs_profile_sweep": (C.c_int, [vp, _dp, _ip]),
+        "bvb_gibbs_kernel_times": (C.c_int, [vp, _dp, C.c_int]),
+        "bvb_tolerance_clamp": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_uint32]),
         "bvb_gibbs_state": (C.c_int, [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
         "bvb_comm_unique_id": (C.c_int, [C.c_char_p]),
         "bvb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
@@ -617,6 +620,21 @@ class Sampler:
         self.h._check(rc)
         self.done = done.value
         return self.done
+
+    def profile_sweep(self):
+        """One further sweep in its serial, event-instrumented form; returns ms per phase."""
+        out = np.zeros(8)
+        done = C.c_int(0)
+        self.h._check(self.lib.bvb_gibbs_profile_sweep(self.h._h, fptr(out), C.byref(done)))
+        self.done = done.value
+        return dict(zip(["prep", "k1", "k2", "comm", "clamp_hyper", "resid", "sv", "store"], out))
+
+    def kernel_times(self, reset=False):
+        """Live %globaltimer spans of K1 (Z tiles) and K2 accumulated by the sweeps since the last reset."""
+        out = np.zeros(3)
+        self.h._check(self.lib.bvb_gibbs_kernel_times(self.h._h, fptr(out), 1 if reset else 0))
+        n = int(out[2])
+        return dict(sweeps=n, k1_ms=out[0] / n if n else 0.0, k2_ms=out[1] / n if n else 0.0)
 
     def timing(self):
         out = np.zeros(10)

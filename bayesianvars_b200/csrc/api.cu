@@ -276,6 +276,14 @@ int bvb_create(bvb_handle** out, int device, uint64_t seed) {
   return BVB_OK;
 }
 
+// New Philox key for the calls that follow (a chain set up by bvb_gibbs_init keeps using the handle's key, so call it
+// before bvb_gibbs_init).  The Rcpp shim keeps ONE process-wide handle and re-keys it from R's RNG at every entry point.
+int bvb_set_seed(bvb_handle* h, uint64_t seed) {
+  if (!h) return BVB_ERR_ARG;
+  h->seed = seed;
+  return BVB_OK;
+}
+
 void bvb_destroy(bvb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);

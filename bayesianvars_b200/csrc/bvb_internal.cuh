@@ -73,6 +73,7 @@ struct K1Params {
   //   acc * rowscale[t, j] * rowscale[s, j] + (t == s)       (= X_norm V X_norm' + I_T)
   const int2* pairs = nullptr;      // [nArows] {t, s}
   const double* rowscale = nullptr; // [n][M] normaliser exp(-h/2); non-null selects the mode
+  unsigned long long* tstamp = nullptr;  // optional [2]: %globaltimer of the first CTA start (atomicMin) / last CTA end (atomicMax)
 };
 cudaError_t launch_k1(const K1Params& p, cudaStream_t s);
 
@@ -89,6 +90,7 @@ struct K2Params {
   int mode = 0;               // 0: factor + forward solve (rhs row) + back-solve/draw; 1: factor only
   int debug_mode = 0;         // 1: skip the DMMA of the update loop, 2: skip its loads (timing experiments only)
   int direct = 1;             // look-ahead kernel: operands of the update straight from L2 into registers (BVB_K2_DIRECT)
+  unsigned long long* tstamp = nullptr;  // optional [2]: %globaltimer of the first CTA start / last CTA end
 };
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s);
 cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s);

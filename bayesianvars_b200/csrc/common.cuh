@@ -87,6 +87,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 // order generic-proxy accesses (plain ld/st) against later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
+// ------------------------------------------------------- live kernel timers --
+// Device-wide nanosecond timer; a kernel stamps its span into ts[0] (min over CTA starts) / ts[1] (max over CTA ends).
+__device__ __forceinline__ unsigned long long bvb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void bvb_stamp_begin(unsigned long long* ts) { if (ts) atomicMin(ts, bvb_globaltimer()); }
+__device__ __forceinline__ void bvb_stamp_end(unsigned long long* ts) { if (ts) atomicMax(ts + 1, bvb_globaltimer()); }
+
 // --------------------------------------------------------------- warp ------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -6,7 +6,9 @@
 
 namespace bvb {
 
-constexpr int FSV_RMAX = 16;  // max number of factors handled by the per-thread small systems
+constexpr int FSV_RMAX = 16;     // factors handled by the per-thread (register / local) small systems
+constexpr int FSV_RMAX_BIG = 64; // beyond FSV_RMAX the r x r systems live in shared memory, one CTA per row / time point
+                                 // (the reference's own benchmark runs r = 50, vignettes/scalability-vignette.qmd:95)
 
 struct FsvDev {
   int M = 0, T = 0, r = 0;

@@ -53,7 +53,9 @@ NcclApi& nccl_api() {
 
 namespace bvb {
 
-constexpr uint32_t STREAM_PHI_Z = 0x10, STREAM_CLAMP = 0x11, STREAM_U_Z = 0x13, STREAM_PHI_HYPER = 0x20, STREAM_U_HYPER = 0x30;
+// Philox stream ids: one named constant per purpose (hyper-parameter blocks use base .. base + 3)
+constexpr uint32_t STREAM_PHI_Z = 0x10, STREAM_CLAMP = 0x11, STREAM_U_Z = 0x13, STREAM_HUGE_DELTA = 0x14, STREAM_CLAMP_U = 0x15,
+                   STREAM_PHI_HYPER = 0x20, STREAM_U_HYPER = 0x30;
 
 // ------------------------------------------------------------------ kernels
 __global__ void gibbs_normals_kernel(double* out, int n, int M, int ld, int j0, uint64_t seed, const uint32_t* sweep) {
@@ -94,9 +96,20 @@ __global__ void __launch_bounds__(256) gibbs_prep_normals_kernel(double* __restr
 
 // PHI_diff = PHI - PHI0 on the K lag rows, pushed away from zero for DL / GT
 // (bvar_cpp.cpp:534-559); also the non-finite check of :529-531.
+//
+// Thread 0 also closes the live kernel timers of this sweep: K1 (Z tiles) and K2 stamped the device-wide
+// %globaltimer of their first CTA start / last CTA end into kt[0..3] (atomicMin / atomicMax); both are complete here
+// and the next Z tiles cannot start before the SV series kernel, so the spans are added to kt[4] / kt[5] and re-armed.
 __global__ void gibbs_clamp_kernel(double* PHI, const double* PHI0, double* coef, int K, int Kp, int M,
-                                   int do_clamp, double tol, uint64_t seed, const uint32_t* sweep, int* status) {
+                                   int do_clamp, double tol, uint64_t seed, const uint32_t* sweep, int* status,
+                                   unsigned long long* kt) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0 && kt) {
+    if (kt[1] > kt[0]) kt[4] += kt[1] - kt[0];
+    if (kt[3] > kt[2]) kt[5] += kt[3] - kt[2];
+    if (kt[3] > kt[2]) kt[6] += 1;
+    kt[0] = ~0ull; kt[1] = 0; kt[2] = ~0ull; kt[3] = 0;
+  }
   if (idx >= (size_t)Kp * M) return;
   const int j = (int)(idx / Kp), k = (int)(idx % Kp);
   double v = PHI[idx];
@@ -304,7 +317,7 @@ __global__ void chol_clamp_u_kernel(double* U, double* uvec, int M, int do_clamp
   double v = U[idx];
   if (do_clamp) {
     if (v == 0.0) {
-      RngStream rng(seed, STREAM_CLAMP + 1, (uint32_t)idx, *sweep);
+      RngStream rng(seed, STREAM_CLAMP_U, (uint32_t)idx, *sweep);
       v = (rng.uniform() < 0.5) ? tol : -tol;
     } else if (v < tol && v > 0.0) v = tol;
     else if (v > -tol && v < 0.0) v = -tol;
@@ -368,15 +381,26 @@ int setup_hyper(bvb_handle* h, GibbsHyper& H, int prior, int n, const std::vecto
   d.tol = tol; d.vs = vs; d.hyper = hyper; d.dl_plus = dl_plus; d.c_rel_a = c_rel_a; d.kernel_exp = kernel_exp;
   d.s_a = s_a; d.s_b = s_b; d.grid_len = grid_len; d.stream_base = stream_base;
   if (n == 0) return BVB_OK;
-  if (G > HYP_MAXG) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "more than %d coefficient groups", HYP_MAXG); return BVB_ERR_UNSUPPORTED; }
   int rc;
   if ((rc = upload(h, H.grp, grp.data(), n))) return rc;
+  {
+    // member lists of the groups (CSR, ascending coefficient index): one CTA per group reduces them in a fixed order
+    const int Gs = std::max(G, 1);
+    std::vector<int> gstart((size_t)Gs + 1, 0), gmem;
+    for (int i = 0; i < n; ++i) if (grp[i] >= 0 && grp[i] < Gs) gstart[grp[i] + 1] += 1;
+    for (int g = 0; g < Gs; ++g) gstart[g + 1] += gstart[g];
+    gmem.assign((size_t)std::max(gstart[Gs], 1), 0);
+    std::vector<int> fill(gstart.begin(), gstart.end() - 1);
+    for (int i = 0; i < n; ++i) if (grp[i] >= 0 && grp[i] < Gs) gmem[fill[grp[i]]++] = i;
+    if ((rc = upload(h, H.gstart, gstart.data(), gstart.size()))) return rc;
+    if ((rc = upload(h, H.gmem, gmem.data(), gmem.size()))) return rc;
+  }
   if ((rc = upload(h, H.gpar, gpar.data(), (size_t)std::max(G, 1) * HYP_GP))) return rc;
   GB_TRY(H.coef.ensure(n));
   if ((rc = upload(h, H.V_i, V_init.data(), n))) return rc;
   if ((rc = upload(h, H.loc1, loc1_init.data(), n))) return rc;
   if ((rc = upload(h, H.loc2, loc2_init.data(), n))) return rc;
-  GB_TRY(H.partial.ensure((size_t)d.nblocks * std::max(G, 1) * HYP_NRED));
+  GB_TRY(H.red.ensure((size_t)n * HYP_NRED));
   GB_TRY(H.gsum.ensure((size_t)std::max(G, 1) * HYP_NRED));
   if (grid_len > 0) {
     if ((rc = upload(h, H.a_vec, a_vec, grid_len))) return rc;
@@ -391,7 +415,7 @@ int setup_hyper(bvb_handle* h, GibbsHyper& H, int prior, int n, const std::vecto
   if (prior == BVB_PRIOR_HMP) if ((rc = upload(h, H.V_prep, V_prep.data(), n))) return rc;
   (void)V_i_fixed; (void)p_init;
   d.grp = H.grp.p; d.coef = H.coef.p; d.V_i = H.V_i.p; d.loc1 = H.loc1.p; d.loc2 = H.loc2.p; d.gpar = H.gpar.p;
-  d.partial = H.partial.p; d.gsum = H.gsum.p; d.a_vec = H.a_vec.p; d.a_weight = H.a_weight.p;
+  d.gstart = H.gstart.p; d.gmem = H.gmem.p; d.red = H.red.p; d.gsum = H.gsum.p; d.a_vec = H.a_vec.p; d.a_weight = H.a_weight.p;
   d.norm_consts = H.norm_consts.p; d.c_vec = H.c_vec.p; d.tau0 = H.tau0.p; d.tau1 = H.tau1.p; d.V_prep = H.V_prep.p;
   return BVB_OK;
 }
@@ -412,6 +436,7 @@ static cudaError_t enqueue_k1z(Gibbs& G, cudaStream_t s) {
   k1.V = G.Vprior.p + (size_t)G.j0 * Kp; k1.PHI0 = G.PHI0.p + (size_t)G.j0 * Kp; k1.omega = G.omega.p;
   k1.Tp = G.geom.Tp; k1.nZtiles = G.geom.nZtiles; k1.ntiles = G.geom.nZtiles;     // no X tiles: gibbs_k1_rhs_kernel
   k1.M = G.nloc; k1.n = Kp; k1.ldo = G.geom.ldo;
+  k1.tstamp = G.ktime.p;
   return launch_k1(k1, s);
 }
 
@@ -420,7 +445,7 @@ static cudaError_t enqueue_prep(bvb_handle* h, Gibbs& G, cudaStream_t s, int wri
   const size_t nz = (size_t)G.Kp * G.nloc;
   gibbs_prep_normals_kernel<<<(unsigned)(G.M + (nz + 255) / 256), 256, 0, s>>>(G.W.p, G.WY.p, G.Y.p, G.logvar.p, G.facload.p,
                                                                               G.fac.p, G.T, G.geom.Tp, G.M, G.r, G.Zn.p, G.Kp,
-                                                                              G.nloc, G.j0, h->seed, G.sweep.p, write_w);
+                                                                              G.nloc, G.j0, G.seed, G.sweep.p, write_w);
   return cudaGetLastError();
 }
 
@@ -448,24 +473,24 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   if (K > 0 && G.sigma_type == BVB_SIGMA_CHOLESKY) {
     // ---- 1) PHI | .  (cholesky structure: corrected triangular algorithm, bvar_cpp.cpp:510)
     const size_t nz = (size_t)Kp * M;
-    gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, M, Kp, 0, h->seed, sw);
+    gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, M, Kp, 0, G.seed, sw);
     mark(1);
     GB_TRY(launch_chol_phi(G.cphi, s));
     mark(2); mark(3); mark(4);
     const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
     gibbs_clamp_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
-                                                                   G.PHI_tol, h->seed, sw, G.status.p);
+                                                                   G.PHI_tol, G.seed, sw, G.status.p, nullptr);
   } else if (K > 0 && G.huge) {
     // ---- 1) PHI | .  (factor structure, expert_huge: T x T systems; every rank draws all equations)
     const size_t nz = (size_t)Kp * M, nd = (size_t)T * M;
-    gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, M, Kp, 0, h->seed, sw);
-    gibbs_flat_normals_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, s>>>(G.hdelta.p, nd, h->seed, STREAM_PHI_Z + 2, sw);
+    gibbs_normals_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.Zn.p, Kp, M, Kp, 0, G.seed, sw);
+    gibbs_flat_normals_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, s>>>(G.hdelta.p, nd, G.seed, STREAM_HUGE_DELTA, sw);
     mark(1);
     GB_TRY(launch_phi_huge(G.chuge, s));
     mark(2); mark(3); mark(4);
     const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
     gibbs_clamp_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
-                                                                   G.PHI_tol, h->seed, sw, G.status.p);
+                                                                   G.PHI_tol, G.seed, sw, G.status.p, nullptr);
   } else if (K > 0) {  // bvar_cpp.cpp:507: PHI is only drawn when there are lagged regressors
     // ---- 1) PHI | .  (factor structure: equations independent)
     // K1 is split.  The Z tiles (X'diag(w)X, 99.5 % of its work) only need W = exp(-h), which is final once the SV series
@@ -484,6 +509,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     K2Params k2{};
     k2.omega = G.omega.p; k2.colbase = G.colbase.p; k2.z = G.Zn.p; k2.phi = G.PHI.p + (size_t)G.j0 * Kp;
     k2.status = G.eqstatus.p + G.j0; k2.n = Kp; k2.M = G.nloc; k2.ldo = G.geom.ldo; k2.ldz = Kp; k2.ldphi = Kp;
+    k2.tstamp = G.ktime.p + 2;
     GB_TRY(launch_k2(k2, s));
     mark(3);
     if (G.world > 1) {
@@ -497,14 +523,18 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     const size_t nphi = (size_t)Kp * M;
     const int do_clamp = (G.hphi.d.prior == BVB_PRIOR_DL || G.hphi.d.prior == BVB_PRIOR_GT) ? 1 : 0;
     gibbs_clamp_kernel<<<(unsigned)((nphi + 255) / 256), 256, 0, s>>>(G.PHI.p, G.PHI0.p, G.hphi.d.coef, K, Kp, M, do_clamp,
-                                                                     G.PHI_tol, h->seed, sw, G.status.p);
+                                                                     G.PHI_tol, G.seed, sw, G.status.p, G.ktime.p);
   } else {
     mark(1); mark(2); mark(3); mark(4);
   }
   // ---- 2) hyper-parameters of the prior on PHI.  They only read PHI and write V_prior / their own state, which
   // nothing below touches, so outside the timing pass they run on a side stream next to resid + Sigma_t (a fork /
   // join in the captured graph); the join is before the store.
+#ifdef BVB_DEBUG_SWITCHES
   static const bool dbg_skip_hyper = getenv("BVB_DEBUG_SKIP_HYPER") != nullptr;   // timing experiments only (wrong draws)
+#else
+  constexpr bool dbg_skip_hyper = false;   // (switches that change the draws are compiled out of release builds)
+#endif
   const bool has_hyper = !dbg_skip_hyper && G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING;
   static const bool dbg_fork_timing = getenv("BVB_DEBUG_FORK_TIMING") != nullptr;
   const bool forked = has_hyper && (!timing || dbg_fork_timing) && G.side != nullptr;
@@ -521,12 +551,12 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
       // the NG hyper-parameters of the factor loadings only read last sweep's loadings: first on the side stream, the
       // Sigma_t branch waits for them in front of its loadings kernel (19 us off the critical path)
       if (ng_side) {
-        GB_TRY(launch_fsv_ng(G.fsv, h->seed, sw, hs));
+        GB_TRY(launch_fsv_ng(G.fsv, G.seed, sw, hs));
         GB_TRY(cudaEventRecord(G.ev_ng, hs));
       }
     }
     if (has_hyper) {
-      GB_TRY(launch_hyper_update(G.hphi.d, h->seed, sw, G.burnin, hs));
+      GB_TRY(launch_hyper_update(G.hphi.d, G.seed, sw, G.burnin, hs));
       const size_t nk = (size_t)K * M;
       gibbs_scatter_V_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, hs>>>(G.Vprior.p, G.hphi.d.V_i, K, Kp, M);
     }
@@ -543,14 +573,14 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   if (G.sigma_type == BVB_SIGMA_CHOLESKY) {
     const int M2 = M * M;
     if (G.nU > 0) {
-      gibbs_flat_normals_kernel<<<(G.nU + 255) / 256, 256, 0, s>>>(G.zflat.p, (size_t)G.nU, h->seed, STREAM_U_Z, sw);
+      gibbs_flat_normals_kernel<<<(G.nU + 255) / 256, 256, 0, s>>>(G.zflat.p, (size_t)G.nU, G.seed, STREAM_U_Z, sw);
       GB_TRY(launch_sample_u(G.cu, s));                                                       // bvar_cpp.cpp:659
       const int clampU = (G.hU.d.prior == BVB_PRIOR_DL || G.hU.d.prior == BVB_PRIOR_GT) ? 1 : 0;
-      chol_clamp_u_kernel<<<(M2 + 255) / 256, 256, 0, s>>>(G.U.p, G.hU.d.coef, M, clampU, G.L_tol, h->seed, sw);   // :667-688
-      GB_TRY(launch_hyper_update(G.hU.d, h->seed, sw, G.burnin, s));                          // :689-721
+      chol_clamp_u_kernel<<<(M2 + 255) / 256, 256, 0, s>>>(G.U.p, G.hU.d.coef, M, clampU, G.L_tol, G.seed, sw);   // :667-688
+      GB_TRY(launch_hyper_update(G.hU.d, G.seed, sw, G.burnin, s));                          // :689-721
     }
     chol_strres_kernel<<<M, 256, 0, s>>>(G.strres.p, G.resid.p, G.U.p, T, M);                 // :725
-    GB_TRY(launch_fsv_update(G.fsv, h->seed, sw, s));                                         // :727-746
+    GB_TRY(launch_fsv_update(G.fsv, G.seed, sw, s));                                         // :727-746
     const size_t tm = (size_t)T * M;
     chol_dsq_kernel<<<(unsigned)((tm + 255) / 256), 256, 0, s>>>(G.dsq.p, G.logvar.p, tm);
   } else {
@@ -558,7 +588,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
       // rotated graph: the series kernel writes next sweep's W itself (every idiosyncratic series passes through it)
       FsvDev fs = G.fsv;
       if (rotate) { fs.Wk1 = G.W.p; fs.Tp = G.geom.Tp; }
-      GB_TRY(launch_fsv_series(fs, h->seed, sw, s));
+      GB_TRY(launch_fsv_series(fs, G.seed, sw, s));
     }
     if (rotate && !timing) {
       // the idiosyncratic log-variances are final: the next sweep's Z tiles run on the (low-priority) side stream,
@@ -568,7 +598,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
       GB_TRY(enqueue_k1z(G, G.side));
       GB_TRY(cudaEventRecord(G.ev_k1z, G.side));
     }
-    GB_TRY(launch_fsv_rest(G.fsv, h->seed, sw, s, ng_side ? G.ev_ng : nullptr));
+    GB_TRY(launch_fsv_rest(G.fsv, G.seed, sw, s, ng_side ? G.ev_ng : nullptr));
   }
   mark(7);
   if (forked) GB_TRY(cudaStreamWaitEvent(s, G.ev_join, 0));
@@ -600,6 +630,8 @@ static void gibbs_free(bvb_handle* h) {
   if (G->ev_series) cudaEventDestroy(G->ev_series);
   if (G->ev_k1z) cudaEventDestroy(G->ev_k1z);
   if (G->side) cudaStreamDestroy(G->side);
+  if (G->copy) cudaStreamDestroy(G->copy);
+  for (int b = 0; b < 2; ++b) if (G->ev_sub[b]) cudaEventDestroy(G->ev_sub[b]);
   if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
   if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
   for (int b = 0; b < 2; ++b) if (G->ev_pin[b]) cudaEventDestroy(G->ev_pin[b]);
@@ -628,7 +660,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     return BVB_ERR_UNSUPPORTED;
   }
   const int r = chol ? 0 : ps->factor_factors;
-  if (r < 0 || r > FSV_RMAX) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "factor_factors=%d outside [0,%d]", r, FSV_RMAX); return BVB_ERR_UNSUPPORTED; }
+  if (r < 0 || r > FSV_RMAX_BIG) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "factor_factors=%d outside [0,%d]", r, FSV_RMAX_BIG); return BVB_ERR_UNSUPPORTED; }
   const bool use_huge = huge && !chol && K > 0;   // 'expert_huge=TRUE' is ignored for the cholesky structure (R/bvar_wrapper.R:389-391)
   if (use_huge && !k2_supported(T)) {
     bvb_set_error(h, BVB_ERR_UNSUPPORTED, "expert_huge: T=%d exceeds the in-SM panel of the T x T solve", T);
@@ -662,6 +694,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   G.sigma_type = ps->type;
   G.huge = use_huge ? 1 : 0;
   G.rank = h->rank; G.world = h->world > 0 ? h->world : 1; G.comm = h->comm;
+  G.seed = h->seed;   // the chain keeps the key it was set up with (bvb_set_seed only affects later chains)
   G.nloc_max = (M + G.world - 1) / G.world;
   G.j0 = std::min(M, G.rank * G.nloc_max);
   GB_TRY(G.first_slot.ensure(1, true));
@@ -676,6 +709,11 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   GB_TRY(G.status.ensure(8, true));
   GB_TRY(G.sweep.ensure(1, true));
   GB_TRY(G.nstored.ensure(2, true));
+  GB_TRY(G.ktime.ensure(8, true));
+  {
+    const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, 0, 0, 0, 0};
+    GB_TRY(cudaMemcpyAsync(G.ktime.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  }
   GB_TRY(G.eqstatus.ensure(std::max(M, 1), true));
   if (Kp > 0) {
     if ((rc = upload(h, G.X, X, (size_t)T * Kp))) return rc;
@@ -796,6 +834,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
                    pp->DL_plus, pp->c_rel_a, pp->GT_priorkernel, pp->GT_vs, pp->SSVS_tau0, pp->SSVS_tau1,
                    pp->SSVS_s_a, pp->SSVS_s_b, pp->SSVS_p, V_prep_small, loc1, loc2, V_init, STREAM_PHI_HYPER);
   if (rc) return rc;
+  G.hphi.d.status = G.status.p + 2;
 
   init_mark("prior block");
   // ---- Sigma_t block (factor SV)
@@ -935,6 +974,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
                      ps->cholesky_SSVS_p, Vprep, l1, l2, Vi, STREAM_U_HYPER);
     if (rc) return rc;
     G.hU.d.always_active = 1;
+    G.hU.d.status = G.status.p + 2;
     if (nU > 0) {
       const int nu = M - 1;
       if (!k2_supported(nu)) { bvb_set_error(h, BVB_ERR_UNSUPPORTED, "M=%d exceeds the in-SM panel of sample_U", M); return BVB_ERR_UNSUPPORTED; }
@@ -1037,6 +1077,8 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   }
   GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
   GB_TRY(cudaEventCreate(&G.ev_chunk[1]));
+  GB_TRY(cudaStreamCreateWithFlags(&G.copy, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_sub[b], cudaEventDisableTiming));
   for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_pin[b], cudaEventDisableTiming));
   GB_TRY(cudaStreamSynchronize(s));
   G.rep = 0;
@@ -1066,126 +1108,44 @@ static void scatter_to_caller(Gibbs& G, const double* chunk, int first, int coun
   }
 }
 
-int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
-  if (!h || !h->gibbs) return BVB_ERR_ARG;
-  Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
-  if (!G.ready) return BVB_ERR_ARG;
-  GB_TRY(cudaSetDevice(h->device));
+// Number of stored draws after `rep` sweeps.
+static inline int stored_count(const Gibbs& G, int rep) { return (rep <= G.burnin) ? 0 : (rep - G.burnin) / G.thin; }
+
+// One sweep launched eagerly (first sweep of a chain: lazily sized workspaces, kernel attributes; or the per-phase
+// timing pass).  It is an ordinary sweep of the chain: the sweep counter advances and its draw is stored.
+static int run_eager_sweep(bvb_handle* h, Gibbs& G, bool timing) {
   cudaStream_t s = h->stream;
-  const int tot = G.draws + G.burnin;
-  int todo = std::min(max_sweeps, tot - G.rep);
-  if (todo < 0) todo = 0;
-  h->err_step = 0;
-  // First sweep ever: eager (allocates lazily-sized workspaces, sets kernel
-  // attributes), then one sweep's launches are captured into a graph.
-  if (!G.graph_exec && todo > 0) {
-    int rc = enqueue_sweep(h, G);
-    if (rc) return rc;
+  const int stored_before = stored_count(G, G.rep);
+  GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
+  G.timing_pass = timing;
+  int rc = enqueue_sweep(h, G);
+  G.timing_pass = false;
+  if (rc) return rc;
+  G.rep += 1;
+  if (stored_count(G, G.rep) > stored_before) {   // this sweep was stored in ring slot 0
+    GB_TRY(cudaMemcpyAsync(G.pinned[0], G.ring.p, sizeof(double) * G.store.slot_doubles, cudaMemcpyDeviceToHost, s));
     GB_TRY(cudaStreamSynchronize(s));
-    G.rep += 1;
-    todo -= 1;
-    cudaGraph_t graph;
-    GB_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_sweep(h, G);
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    if (rc) return rc;
-    GB_TRY(ce);
-    size_t nn = 0;
-    cudaGraphGetNodes(graph, nullptr, &nn);
-    G.launches_per_sweep = (int)nn;
-    if (const char* dot = getenv("BVB_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, 0);
-    GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
-    cudaGraphDestroy(graph);
+    if (G.rank == 0) scatter_to_caller(G, G.pinned[0], stored_before, 1);
+  } else {
+    GB_TRY(cudaStreamSynchronize(s));
   }
-  // Per-phase device times: the LAST sweep of every call with >= 8 sweeps is
-  // launched eagerly with CUDA events between the phases (warm caches).
-  const bool time_last = (todo >= 8);
-  if (time_last) todo -= 1;
-  // Sub-chunks of <= 32 sweeps (and <= ring_slots stored draws).  The D2H copy of a
-  // sub-chunk's stored draws is queued behind its sweeps; the host scatters the
-  // PREVIOUS sub-chunk into the caller's arrays while the GPU runs the next one.
-  GB_TRY(cudaEventRecord(G.ev_chunk[0], s));
-  int ran = 0;
-  struct Pending { int buf, first, count; } pend = {-1, 0, 0};
-  auto flush = [&](Pending& pd) -> int {
-    if (pd.buf < 0) return BVB_OK;
-    GB_TRY(cudaEventSynchronize(G.ev_pin[pd.buf]));
-    if (G.rank == 0) scatter_to_caller(G, G.pinned[pd.buf], pd.first, pd.count);
-    pd.buf = -1;
-    return BVB_OK;
-  };
-  int flip = 0;
-  while (ran < todo) {
-    const int stored_before = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
-    int nsw = std::min(todo - ran, 32);
-    while (nsw > 1 && (std::max(0, G.rep + nsw - G.burnin) / G.thin) - stored_before > G.store.ring_slots) --nsw;
-    GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
-    static const bool dbg_eager = getenv("BVB_DEBUG_EAGER") != nullptr;
-    for (int i = 0; i < nsw; ++i) {
-      if (dbg_eager) { int rc = enqueue_sweep(h, G); if (rc) return rc; }
-      else GB_TRY(cudaGraphLaunch(G.graph_exec, s));
-    }
-    G.rep += nsw;
-    ran += nsw;
-    const int stored_after = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
-    const int cnt = stored_after - stored_before;
-    Pending cur = {-1, 0, 0};
-    if (cnt > 0) {
-      GB_TRY(cudaMemcpyAsync(G.pinned[flip], G.ring.p, sizeof(double) * (size_t)cnt * G.store.slot_doubles,
-                             cudaMemcpyDeviceToHost, s));
-      GB_TRY(cudaEventRecord(G.ev_pin[flip], s));
-      cur = {flip, stored_before, cnt};
-      flip ^= 1;
-    }
-    int rc = flush(pend);   // overlaps with the sweeps just queued
-    if (rc) return rc;
-    pend = cur;
-  }
-  if (time_last) {
-    const int stored_before = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
-    GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
-    G.timing_pass = true;
-    int rc = enqueue_sweep(h, G);
-    G.timing_pass = false;
-    if (rc) return rc;
-    G.rep += 1;
-    ran += 1;
-    const int stored_after = (G.rep <= G.burnin) ? 0 : (G.rep - G.burnin) / G.thin;
-    if (stored_after > stored_before) {
-      rc = flush(pend);
-      if (rc) return rc;
-      GB_TRY(cudaMemcpyAsync(G.pinned[flip], G.ring.p, sizeof(double) * G.store.slot_doubles, cudaMemcpyDeviceToHost, s));
-      GB_TRY(cudaEventRecord(G.ev_pin[flip], s));
-      pend = {flip, stored_before, 1};
-      flip ^= 1;
-    }
-    G.timed = true;
-  }
-  {
-    int rc = flush(pend);
-    if (rc) return rc;
-  }
-  if (time_last) {
+  if (timing) {
     for (int i = 0; i < 8; ++i) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]) != cudaSuccess) { ms = 0; cudaGetLastError(); }
       G.phase_ms[i] = ms;
     }
+    G.timed = true;
   }
-  GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
-  GB_TRY(cudaStreamSynchronize(s));
-  {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, G.ev_chunk[0], G.ev_chunk[1]);
-    G.last_chunk_ms = ms;
-    G.last_chunk_sweeps = ran;
-  }
-  // error status
+  return BVB_OK;
+}
+
+// Device status words -> error code + the reference's wording.
+static int check_status(bvb_handle* h, Gibbs& G) {
   int hst[8];
   GB_TRY(cudaMemcpy(hst, G.status.p, sizeof(hst), cudaMemcpyDeviceToHost));
   std::vector<int> eqs(G.M);
   GB_TRY(cudaMemcpy(eqs.data(), G.eqstatus.p, sizeof(int) * G.M, cudaMemcpyDeviceToHost));
-  if (done) *done = G.rep;
   for (int j = 0; j < G.M; ++j) {
     if (eqs[j] != 0) {
       h->err_step = 1; h->err_eq = j + 1; h->err_sweep = G.rep;
@@ -1214,6 +1174,177 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     bvb_set_error(h, BVB_ERR_NUMERIC, "factorstochvol::update_fsv() failed in run <= %i: small system not positive definite (%s)", G.rep,
                   hst[1] == 1 ? "loadings" : "factors");
     return BVB_ERR_NUMERIC;
+  }
+  if (hst[2] != 0) {
+    h->err_step = 2; h->err_sweep = G.rep;
+    bvb_set_error(h, BVB_ERR_NUMERIC, "GIG sampler: rejection loop exhausted in run <= %i (parameters outside the sampler's range)", G.rep);
+    return BVB_ERR_NUMERIC;
+  }
+  return BVB_OK;
+}
+
+int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
+  if (!h || !h->gibbs) return BVB_ERR_ARG;
+  Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
+  if (!G.ready) return BVB_ERR_ARG;
+  GB_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int tot = G.draws + G.burnin;
+  int todo = std::min(max_sweeps, tot - G.rep);
+  if (todo < 0) todo = 0;
+  h->err_step = 0;
+  int ran = 0;
+  // First sweep ever: eager (allocates lazily-sized workspaces, sets kernel
+  // attributes), then one sweep's launches are captured into a graph.
+  if (!G.graph_exec && todo > 0) {
+    int rc = run_eager_sweep(h, G, false);
+    if (rc) return rc;
+    todo -= 1;
+    ran += 1;
+    cudaGraph_t graph;
+    GB_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_sweep(h, G);
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc) return rc;
+    GB_TRY(ce);
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    G.launches_per_sweep = (int)nn;
+    if (const char* dot = getenv("BVB_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, 0);
+    GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  // Sub-chunks of <= 32 sweeps that store <= half a ring.  The two ring halves alternate: the D2H copy of a sub-chunk's
+  // stored draws runs on the copy stream (behind an event, off the sampler stream) while the next sub-chunk fills the
+  // other half, and the host scatters the PREVIOUS sub-chunk into the caller's arrays meanwhile.
+  const int half = std::max(1, G.store.ring_slots / 2);
+  const bool two_halves = G.store.ring_slots >= 2;
+  GB_TRY(cudaEventRecord(G.ev_chunk[0], s));
+  struct Pending { int buf, first, count; } pend = {-1, 0, 0};
+  auto flush = [&](Pending& pd) -> int {
+    if (pd.buf < 0) return BVB_OK;
+    GB_TRY(cudaEventSynchronize(G.ev_pin[pd.buf]));
+    if (G.rank == 0) scatter_to_caller(G, G.pinned[pd.buf], pd.first, pd.count);
+    pd.buf = -1;
+    return BVB_OK;
+  };
+  int flip = 0, timed_sweeps = 0;
+  bool used[2] = {false, false};
+  while (todo > 0) {
+    const int stored_before = stored_count(G, G.rep);
+    int nsw = std::min(todo, 32);
+    while (nsw > 1 && stored_count(G, G.rep + nsw) - stored_before > half) --nsw;
+    // ring half `flip` is free once the copy that last read it is done
+    if (used[flip]) GB_TRY(cudaStreamWaitEvent(s, G.ev_pin[flip], 0));
+    if (!two_halves && used[flip ^ 1]) GB_TRY(cudaStreamWaitEvent(s, G.ev_pin[flip ^ 1], 0));
+    const int first_slot = stored_before - (two_halves ? flip * half : 0);   // stored draw that maps to ring slot 0
+    GB_TRY(cudaMemcpyAsync(G.first_slot.p, &first_slot, sizeof(int), cudaMemcpyHostToDevice, s));
+#ifdef BVB_DEBUG_SWITCHES
+    static const bool dbg_eager = getenv("BVB_DEBUG_EAGER") != nullptr;
+#else
+    constexpr bool dbg_eager = false;
+#endif
+    for (int i = 0; i < nsw; ++i) {
+      if (dbg_eager) { int rc = enqueue_sweep(h, G); if (rc) return rc; }
+      else GB_TRY(cudaGraphLaunch(G.graph_exec, s));
+    }
+    G.rep += nsw;
+    ran += nsw;
+    todo -= nsw;
+    timed_sweeps += nsw;
+    const int cnt = stored_count(G, G.rep) - stored_before;
+    Pending cur = {-1, 0, 0};
+    if (cnt > 0) {
+      GB_TRY(cudaEventRecord(G.ev_sub[flip], s));
+      GB_TRY(cudaStreamWaitEvent(G.copy, G.ev_sub[flip], 0));
+      GB_TRY(cudaMemcpyAsync(G.pinned[flip], G.ring.p + (size_t)(two_halves ? flip * half : 0) * G.store.slot_doubles,
+                             sizeof(double) * (size_t)cnt * G.store.slot_doubles, cudaMemcpyDeviceToHost, G.copy));
+      GB_TRY(cudaEventRecord(G.ev_pin[flip], G.copy));
+      used[flip] = true;
+      cur = {flip, stored_before, cnt};
+      flip ^= 1;
+    }
+    int rc = flush(pend);   // overlaps with the sweeps just queued
+    if (rc) return rc;
+    pend = cur;
+  }
+  GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
+  {
+    int rc = flush(pend);
+    if (rc) return rc;
+  }
+  GB_TRY(cudaStreamSynchronize(s));
+  GB_TRY(cudaStreamSynchronize(G.copy));
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, G.ev_chunk[0], G.ev_chunk[1]);
+    G.last_chunk_ms = ms;                 // device time of the graph-replayed sweeps of this call
+    G.last_chunk_sweeps = timed_sweeps;   // (the eager first sweep of a chain is not part of it)
+  }
+  if (done) *done = G.rep;
+  (void)ran;
+  return check_status(h, G);
+}
+
+// The tolerance clamp of bvar_cpp.cpp:534-559 on host arrays (the kernel the sweep runs): |PHI - PHI0| on the K lag
+// rows is pushed up to `tol`, exact zeros get +tol or -tol with probability 1/2 each (R::rbinom(1, 0.5) there, the
+// Philox stream (STREAM_CLAMP, element, sweep) here).  Test hook for the exact-zero branch, which a chain never reaches.
+int bvb_tolerance_clamp(bvb_handle* h, int K, int Kp, int M, double* PHI_io, const double* PHI0, double tol, uint32_t sweep) {
+  if (!h || !PHI_io || !PHI0 || K < 0 || Kp < K || M <= 0) return BVB_ERR_ARG;
+  GB_TRY(cudaSetDevice(h->device));
+  const size_t nphi = (size_t)Kp * M;
+  double *dphi = nullptr, *dphi0 = nullptr, *dcoef = nullptr;
+  uint32_t* dsw = nullptr;
+  int* dst = nullptr;
+  auto cleanup = [&]() { cudaFree(dphi); cudaFree(dphi0); cudaFree(dcoef); cudaFree(dsw); cudaFree(dst); };
+  cudaError_t e = cudaMalloc(&dphi, nphi * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dphi0, nphi * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dcoef, std::max<size_t>((size_t)K * M, 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dsw, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&dst, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(dphi, PHI_io, nphi * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dphi0, PHI0, nphi * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dsw, &sweep, sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(dst, 0, sizeof(int));
+  if (e == cudaSuccess) {
+    gibbs_clamp_kernel<<<(unsigned)((nphi + 255) / 256), 256, 0, h->stream>>>(dphi, dphi0, dcoef, K, Kp, M, 1, tol, h->seed, dsw, dst, nullptr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(PHI_io, dphi, nphi * sizeof(double), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) { bvb_set_error(h, BVB_ERR_CUDA, "bvb_tolerance_clamp: %s", cudaGetErrorString(e)); return BVB_ERR_CUDA; }
+  return BVB_OK;
+}
+
+// One further sweep of the chain, launched eagerly in its serial form with CUDA events between the phases (the Z tiles
+// are recomputed at its start so that phase "k1" shows their cost).  out8 = ms of {prep, K1, K2, comm, clamp + hyper,
+// resid, Sigma_t, store}.  Outside every timed region: bvb_gibbs_run itself never instruments a sweep.
+int bvb_gibbs_profile_sweep(bvb_handle* h, double* out8, int* done) {
+  if (!h || !h->gibbs) return BVB_ERR_ARG;
+  Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
+  if (!G.ready || G.rep >= G.draws + G.burnin) return BVB_ERR_ARG;
+  GB_TRY(cudaSetDevice(h->device));
+  int rc = run_eager_sweep(h, G, true);
+  if (rc) return rc;
+  if (out8) for (int i = 0; i < 8; ++i) out8[i] = G.phase_ms[i];
+  if (done) *done = G.rep;
+  return check_status(h, G);
+}
+
+// Live kernel timers (device %globaltimer spans accumulated by the sweeps themselves, graph replay included):
+// out3 = {K1 Z-tile ms, K2 ms, sweeps counted} since the last reset.
+int bvb_gibbs_kernel_times(bvb_handle* h, double* out3, int reset) {
+  if (!h || !h->gibbs) return BVB_ERR_ARG;
+  Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
+  GB_TRY(cudaSetDevice(h->device));
+  GB_TRY(cudaStreamSynchronize(h->stream));
+  unsigned long long kt[8];
+  GB_TRY(cudaMemcpy(kt, G.ktime.p, sizeof(kt), cudaMemcpyDeviceToHost));
+  if (out3) { out3[0] = (double)kt[4] * 1e-6; out3[1] = (double)kt[5] * 1e-6; out3[2] = (double)kt[6]; }
+  if (reset) {
+    const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, 0, 0, 0, 0};
+    GB_TRY(cudaMemcpy(G.ktime.p, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   return BVB_OK;
 }

@@ -38,8 +38,8 @@ struct GBuf {
 
 struct GibbsHyper {
   HyperDev d;
-  GBuf<int> grp;
-  GBuf<double> coef, V_i, loc1, loc2, gpar, partial, gsum, a_vec, a_weight, norm_consts, c_vec, tau0, tau1, V_prep;
+  GBuf<int> grp, gstart, gmem;
+  GBuf<double> coef, V_i, loc1, loc2, gpar, red, gsum, a_vec, a_weight, norm_consts, c_vec, tau0, tau1, V_prep;
 };
 
 struct GibbsSeg {
@@ -62,6 +62,7 @@ struct Gibbs {
   int M = 0, T = 0, K = 0, Kp = 0, intercept = 0, r = 0, S = 0;
   int draws = 0, burnin = 0, thin = 1, nsave = 0, tvp_all = 0, rep = 0;
   double PHI_tol = 0, L_tol = 0;
+  uint64_t seed = 0;
   int rank = 0, world = 1, j0 = 0, nloc = 0, nloc_max = 0;
   void* comm = nullptr;
   PairGeom geom;
@@ -69,6 +70,7 @@ struct Gibbs {
   GBuf<int2> lut, pairs;
   GBuf<int> colbase, status, eqstatus, nstored, first_slot;
   GBuf<uint32_t> sweep;
+  GBuf<unsigned long long> ktime;   // live kernel timers: [0..1] K1 span, [2..3] K2 span, [4] K1 ns, [5] K2 ns, [6] sweeps
   GibbsHyper hphi;
   // Sigma_t block
   FsvDev fsv;
@@ -101,6 +103,8 @@ struct Gibbs {
   GBuf<double> ring;
   double* pinned[2] = {nullptr, nullptr};
   cudaStream_t side = nullptr;                 // hyper-parameter branch of the sweep graph
+  cudaStream_t copy = nullptr;                 // D2H of the stored-draw ring (its two halves alternate between sub-chunks)
+  cudaEvent_t ev_sub[2] = {nullptr, nullptr};  // sweeps of the sub-chunk that filled ring half b are done
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ng = nullptr, ev_series = nullptr, ev_k1z = nullptr;
   bool k1z_valid = false;                      // the Z tiles of the NEXT PHI draw are already in `omega` (see enqueue_sweep)
   cudaEvent_t ev_pin[2] = {nullptr, nullptr};

@@ -33,13 +33,14 @@ __host__ __device__ inline double gig_rou_noshift(RngStream& g, double lambda, d
   const double ym = ((lambda + 1.0) + sqrt((lambda + 1.0) * (lambda + 1.0) + omega * omega)) / omega;
   const double um = exp(0.5 * (lambda + 1.0) * log(ym) - s * (ym + 1.0 / ym) - nc);
   double X = xm;
+  bool ok = false;
   for (int it = 0; it < 100000; ++it) {
     const double U = um * g.uniform();
     const double V = g.uniform();
     X = U / V;
-    if (log(V) <= t * log(X) - s * (X + 1.0 / X) - nc) break;
+    if (log(V) <= t * log(X) - s * (X + 1.0 / X) - nc) { ok = true; break; }
   }
-  return X;
+  return ok ? X : nan("");   // exhausted rejection loop: never hand back an unaccepted candidate (the caller flags NaN)
 }
 
 // Ratio-of-uniforms with shift by the mode (lambda > 2 or omega > 3).
@@ -62,14 +63,15 @@ __host__ __device__ inline double gig_rou_shift(RngStream& g, double lambda, dou
   const double uplus = (y1 - xm) * exp(t * log(y1) - s * (y1 + 1.0 / y1) - nc);
   const double uminus = (y2 - xm) * exp(t * log(y2) - s * (y2 + 1.0 / y2) - nc);
   double X = xm;
+  bool ok = false;
   for (int it = 0; it < 100000; ++it) {
     const double U = uminus + g.uniform() * (uplus - uminus);
     const double V = g.uniform();
     X = U / V + xm;
-    if (X > 0.0 && log(V) <= t * log(X) - s * (X + 1.0 / X) - nc) break;
+    if (X > 0.0 && log(V) <= t * log(X) - s * (X + 1.0 / X) - nc) { ok = true; break; }
     X = xm;
   }
-  return X;
+  return ok ? X : nan("");
 }
 
 // Three-part hat for 0 <= lambda < 1 and small omega (Hoermann & Leydold, Alg. 3).  This is the branch the DL / NG /
@@ -138,11 +140,12 @@ __host__ __device__ inline double gig_newapproach(RngStream& g, double lambda, d
   const GigHat h = gig_hat_setup(lambda, omega);
   g.have = 0;                                          // attempts start on a Philox block boundary
   double X = h.xm;
+  bool ok = false;
   for (int it = 0; it < 100000; ++it) {
     const double u1 = g.uniform(), u2 = g.uniform();
-    if (gig_hat_attempt(h, u1, u2, X)) break;
+    if (gig_hat_attempt(h, u1, u2, X)) { ok = true; break; }
   }
-  return X;
+  return ok ? X : nan("");
 }
 #ifdef __CUDACC__
 // Warp form: all 32 lanes hold the SAME stream state; returns the same variate in every lane and leaves the
@@ -151,7 +154,7 @@ __device__ inline double gig_newapproach_warp(RngStream& g, double lambda, doubl
   const GigHat h = gig_hat_setup(lambda, omega);
   g.have = 0;
   const uint32_t c0 = g.ctr;
-  double X = h.xm;
+  double X = nan("");   // stays NaN if no attempt is accepted
   for (int round = 0; round < 3200; ++round) {
     RngStream a = g;
     a.ctr = c0 + (uint32_t)(round * 32 + lane);

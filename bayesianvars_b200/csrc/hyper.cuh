@@ -11,7 +11,6 @@
 
 namespace bvb {
 
-constexpr int HYP_MAXG = 32;      // max number of coefficient groups
 constexpr int HYP_NRED = 2;       // reductions per group per pass
 constexpr int HYP_THREADS = 256;
 
@@ -27,7 +26,12 @@ struct HyperDev {
   double* loc1 = nullptr;      // [n] lambda (DL/GT) | theta (HS) | gammas (SSVS)
   double* loc2 = nullptr;      // [n] psi    (DL/GT) | nu    (HS) | p_i    (SSVS)
   double* gpar = nullptr;      // [G][HYP_GP]
-  double* partial = nullptr;   // [nblocks][G][HYP_NRED]
+  // any number of groups (global_grouping = "equation-wise" / "covariate-wise" give M / K of them): the members of
+  // group g are gmem[gstart[g] .. gstart[g+1]) in ascending coefficient order, one CTA per group reduces them in a
+  // fixed order
+  const int* gstart = nullptr; // [G + 1]
+  const int* gmem = nullptr;   // [number of grouped coefficients]
+  double* red = nullptr;       // [HYP_NRED][n] per-coefficient terms of the group sums
   double* gsum = nullptr;      // [G][HYP_NRED]   reduced sums of the last pass
   // grids for the hyper-hyper update of `a` (DL/GT)
   double *a_vec = nullptr, *a_weight = nullptr, *norm_consts = nullptr, *c_vec = nullptr;
@@ -41,6 +45,7 @@ struct HyperDev {
   double* V_prep = nullptr;    // [n]
   uint32_t stream_base = 0;    // Philox stream ids stream_base .. stream_base+3
   int always_active = 0;       // U block: SSVS / HMP updates run from the first sweep (bvar_cpp.cpp:708-716)
+  int* status = nullptr;       // set to 1 when a GIG rejection loop is exhausted (the variate is NaN, never a rejected candidate)
 };
 
 // One full hyper-parameter update (up to four kernels).  The sweep index is read

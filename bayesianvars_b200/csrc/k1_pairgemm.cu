@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : 2)) k1_pairgemm(const 
   double* sB = smem + K1_STAGES * A_STAGE;         // [STAGES][NB][20]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) bvb_stamp_begin(p.tstamp);
   const int wm = warp >> 1, wn = warp & 1;
   const int nt0 = wn * NTW;                        // first n-tile of this warp
   const int ntc = wn == 0 ? NTW : NT - NTW;        // number of n-tiles of this warp
@@ -140,6 +141,10 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : 2)) k1_pairgemm(const 
       }
     }
   }
+  if (p.tstamp) {   // (uniform branch) last CTA end: after every warp's stores were issued
+    __syncthreads();
+    if (tid == 0) bvb_stamp_end(p.tstamp);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : (MW <= 4 ? 2 : 1))) k1
   __shared__ __align__(8) uint64_t full[ST];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) bvb_stamp_begin(p.tstamp);
   const int wm = warp >> 1, wn = warp & 1;
   const int nt0 = wn * NTW;
   const int ntc = wn == 0 ? NTW : NT - NTW;
@@ -244,6 +250,10 @@ __global__ void __launch_bounds__(MW * 64, (MW <= 3 ? 3 : (MW <= 4 ? 2 : 1))) k1
         p.omega[(size_t)j * p.ldo + l.x] = v;
       }
     }
+  }
+  if (p.tstamp) {   // (uniform branch) last CTA end: after every warp's stores were issued
+    __syncthreads();
+    if (tid == 0) bvb_stamp_end(p.tstamp);
   }
 }
 

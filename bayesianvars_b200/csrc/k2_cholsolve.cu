@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
+  if (tid == 0) bvb_stamp_begin(p.tstamp);
   const int eq = CL ? blockIdx.x / csize : blockIdx.x;
   const int crank = CL ? blockIdx.x % csize : 0;          // rank in the cluster (cluster dims = (csize, 1, 1))
   double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve(const K2Params
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
   K2_TICK(6);
+  if (tid == 0) bvb_stamp_end(p.tstamp);
   // sticky: the first failure of an equation is kept until the host clears it
   if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
 }
@@ -703,6 +705,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
   int* colb = reinterpret_cast<int*>(rsbuf + 32);         // [n]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) bvb_stamp_begin(p.tstamp);
   const int eq = blockIdx.x;
   double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
   double* __restrict__ lws = linv_ws + (size_t)eq * nbk * (K2_NB * K2_NB);
@@ -1080,6 +1083,7 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
   K2V_TICK(6);
+  if (tid == 0) bvb_stamp_end(p.tstamp);
   if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
 }
 

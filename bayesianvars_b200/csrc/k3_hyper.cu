@@ -5,8 +5,8 @@
 // (src/sample_coefficients.cpp:190-377): the per-coefficient loops there are
 // sequential scalar calls through an R function pointer; here every coefficient
 // is one thread, group statistics are fixed-order (deterministic) reductions and
-// the handful of per-group scalars (xi, zeta, varpi, p, a) are drawn by one warp
-// per group.  Four small kernels: local1 -> global1 -> local2 -> global2.
+// the per-group scalars (xi, zeta, varpi, p, a) are drawn by one CTA per group (any
+// number of groups).  Four small kernels: local1 -> global1 -> local2 -> global2.
 #include "hyper.cuh"
 
 namespace bvb {
@@ -20,33 +20,30 @@ __device__ __forceinline__ int hyper_active(const HyperDev& hd, uint32_t rep, in
   return 1;
 }
 
-__device__ __forceinline__ double block_group_sum(double v, int g, int G, double* sh, double* out) {
-  // deterministic per-group block reduction; result for group gg written to out[gg] by thread 0
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int gg = 0; gg < G; ++gg) {
-    double x = (g == gg) ? v : 0.0;
-    x = warp_sum(x);
-    if (lane == 0) sh[warp] = x;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int w = 0; w < nw; ++w) t += sh[w];
-      out[gg] = t;
-    }
-    __syncthreads();
-  }
-  return 0.0;
+// Sum of v over the members of group g (one CTA per group): every thread strides over the member list, then a
+// fixed-order block reduction - the result does not depend on the launch geometry of anything else.
+__device__ __forceinline__ double group_sum(const HyperDev& hd, const double* v, int g, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int beg = hd.gstart[g], end = hd.gstart[g + 1];
+  double x = 0.0;
+  for (int k = beg + (int)threadIdx.x; k < end; k += HYP_THREADS) x += v[hd.gmem[k]];
+  x = warp_sum(x);
+  __syncthreads();
+  if (lane == 0) sh[warp] = x;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < HYP_THREADS / 32; ++w) t += sh[w];
+  return t;
 }
 
 __global__ void __launch_bounds__(HYP_THREADS) hyper_local1(const HyperDev hd, uint64_t seed, const uint32_t* sweep_p, int burnin) {
   const uint32_t sweep = *sweep_p;
   const int active = hyper_active(hd, sweep, burnin);
-  __shared__ double sh[HYP_THREADS / 32];
-  __shared__ double res[HYP_MAXG];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int g = -1;
+  if (i >= hd.n) return;
+  const int g = hd.grp[i];
   double red = 0.0;
-  if (i < hd.n) g = hd.grp[i];
   if (g >= 0) {
     const double* gp = hd.gpar + g * HYP_GP;
     const double phi = hd.coef[i], c2 = phi * phi;
@@ -58,6 +55,7 @@ __global__ void __launch_bounds__(HYP_THREADS) hyper_local1(const HyperDev hd, u
         hd.loc1[i] = lam;
         hd.loc2[i] = psi;
         red = lam;
+        if (hd.status && (isnan(lam) || isnan(psi))) atomicExch(hd.status, 1);
       } break;
       case BVB_PRIOR_GT: {  // :202-210
         double psi = hd.loc2[i];
@@ -68,6 +66,7 @@ __global__ void __launch_bounds__(HYP_THREADS) hyper_local1(const HyperDev hd, u
         const double lam = gig_draw(rng, gp[GP_A] - 0.5, c2 / (psi * hd.vs), 2.0 * gp[GP_XI]);
         hd.loc1[i] = lam;
         red = lam;
+        if (hd.status && (isnan(lam) || isnan(psi))) atomicExch(hd.status, 1);
       } break;
       case BVB_PRIOR_HS: {  // :252-256  (R::rgamma(1, scale) = scale * Exp(1))
         const double theta = (1.0 / hd.loc2[i] + c2 / (2.0 * gp[GP_ZETA])) / rng.exponential();
@@ -94,25 +93,16 @@ __global__ void __launch_bounds__(HYP_THREADS) hyper_local1(const HyperDev hd, u
       default: break;
     }
   }
-  block_group_sum(red, g, hd.G, sh, res);
-  if (threadIdx.x < hd.G) hd.partial[((size_t)blockIdx.x * hd.G + threadIdx.x) * HYP_NRED + 0] = res[threadIdx.x];
+  hd.red[i] = red;
 }
 
-__device__ __forceinline__ double reduce_partials(const HyperDev& hd, int g, int r) {
-  // one warp per group, fixed order
-  const int lane = threadIdx.x & 31;
-  double s = 0.0;
-  for (int b = lane; b < hd.nblocks; b += 32) s += hd.partial[((size_t)b * hd.G + g) * HYP_NRED + r];
-  return warp_sum(s);
-}
-
-__global__ void hyper_global1(const HyperDev hd, uint64_t seed, const uint32_t* sweep_p, int burnin) {
+__global__ void __launch_bounds__(HYP_THREADS) hyper_global1(const HyperDev hd, uint64_t seed, const uint32_t* sweep_p, int burnin) {
+  __shared__ double sh[HYP_THREADS / 32];
   const uint32_t sweep = *sweep_p;
   const int active = hyper_active(hd, sweep, burnin);
-  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (g >= hd.G) return;
-  const double s0 = reduce_partials(hd, g, 0);
-  if (lane != 0) return;
+  const int g = blockIdx.x;
+  const double s0 = group_sum(hd, hd.red, g, sh);
+  if (threadIdx.x != 0) return;
   double* gp = hd.gpar + g * HYP_GP;
   hd.gsum[g * HYP_NRED + 0] = s0;
   RngStream rng(seed, hd.stream_base + 1, (uint32_t)g, sweep);
@@ -141,6 +131,7 @@ __global__ void hyper_global1(const HyperDev hd, uint64_t seed, const uint32_t* 
       if (active) {  // :361-363 / :374  (n/2 is INTEGER division in the reference)
         const double half = (double)(((long long)n) / 2);
         gp[GP_AUX] = gig_draw(rng, gp[GP_A] - half, s0, 2.0 * gp[GP_B]);
+        if (hd.status && isnan(gp[GP_AUX])) atomicExch(hd.status, 1);
       }
       break;
     default: break;
@@ -149,12 +140,10 @@ __global__ void hyper_global1(const HyperDev hd, uint64_t seed, const uint32_t* 
 
 __global__ void __launch_bounds__(HYP_THREADS) hyper_local2(const HyperDev hd, const uint32_t* sweep_p, int burnin) {
   const int active = hyper_active(hd, *sweep_p, burnin);
-  __shared__ double sh[HYP_THREADS / 32];
-  __shared__ double res[HYP_MAXG];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int g = -1;
+  if (i >= hd.n) return;
+  const int g = hd.grp[i];
   double red = 0.0;
-  if (i < hd.n) g = hd.grp[i];
   if (g >= 0) {
     const double* gp = hd.gpar + g * HYP_GP;
     switch (hd.prior) {
@@ -182,18 +171,16 @@ __global__ void __launch_bounds__(HYP_THREADS) hyper_local2(const HyperDev hd, c
       default: break;
     }
   }
-  if ((hd.prior == BVB_PRIOR_DL || hd.prior == BVB_PRIOR_GT) && hd.hyper) {
-    block_group_sum(red, g, hd.G, sh, res);
-    if (threadIdx.x < hd.G) hd.partial[((size_t)blockIdx.x * hd.G + threadIdx.x) * HYP_NRED + 1] = res[threadIdx.x];
-  }
+  hd.red[(size_t)hd.n + i] = red;
 }
 
 // Discrete update of `a` (and c when c_rel_a) over the grid: :297-314 / :227-244.
-__global__ void hyper_global2(const HyperDev hd, uint64_t seed, const uint32_t* sweep_p) {
+__global__ void __launch_bounds__(HYP_THREADS) hyper_global2(const HyperDev hd, uint64_t seed, const uint32_t* sweep_p) {
+  __shared__ double sh[HYP_THREADS / 32];
   const uint32_t sweep = *sweep_p;
-  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (g >= hd.G) return;
-  const double slog = reduce_partials(hd, g, 1);
+  const int g = blockIdx.x, lane = threadIdx.x & 31;
+  const double slog = group_sum(hd, hd.red + hd.n, g, sh);
+  if (threadIdx.x >= 32) return;
   double* gp = hd.gpar + g * HYP_GP;
   const double n = gp[GP_N], xi = gp[GP_XI], b = gp[GP_B], c = gp[GP_C];
   const double lxi = log(xi);
@@ -234,12 +221,11 @@ __global__ void hyper_global2(const HyperDev hd, uint64_t seed, const uint32_t* 
 
 cudaError_t launch_hyper_update(const HyperDev& hd, uint64_t seed, const uint32_t* sweep, int burnin, cudaStream_t s) {
   if (hd.prior == BVB_PRIOR_NORMAL || hd.prior == BVB_PRIOR_NOTHING || hd.n == 0) return cudaSuccess;
-  const int gthreads = 32 * hd.G;
   hyper_local1<<<hd.nblocks, HYP_THREADS, 0, s>>>(hd, seed, sweep, burnin);
-  hyper_global1<<<1, gthreads, 0, s>>>(hd, seed, sweep, burnin);
+  hyper_global1<<<hd.G, HYP_THREADS, 0, s>>>(hd, seed, sweep, burnin);
   hyper_local2<<<hd.nblocks, HYP_THREADS, 0, s>>>(hd, sweep, burnin);
   if ((hd.prior == BVB_PRIOR_DL || hd.prior == BVB_PRIOR_GT) && hd.hyper && hd.grid_len > 0)
-    hyper_global2<<<1, gthreads, 0, s>>>(hd, seed, sweep);
+    hyper_global2<<<hd.G, HYP_THREADS, 0, s>>>(hd, seed, sweep);
   return cudaGetLastError();
 }
 

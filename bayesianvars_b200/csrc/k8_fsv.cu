@@ -545,6 +545,136 @@ __global__ void __launch_bounds__(32 * FAC_SLICES) fsv_factors_kernel(const FsvD
   for (int p = 0; p < r; ++p) d.fac[(size_t)t * r + p] = b[p];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// r > FSV_RMAX: the r x r normal equations no longer fit a thread's registers.  One CTA per regression (a row of the
+// loadings / a time point of the factors); the lower triangle is accumulated entry-parallel in shared memory (fixed
+// summation order per entry), factorised column by column by the whole CTA, and thread 0 runs the two O(r^2)
+// substitutions with the normals of the same Philox stream the small-r path uses.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BIG_THREADS = 128;
+// A: n x n row-major (stride n) lower triangle in shared memory, b: rhs -> draw.  Returns false on a non-positive pivot.
+__device__ inline bool block_chol_draw(int n, double* A, double* b, RngStream& rng, int* okflag) {
+  const int tid = threadIdx.x;
+  if (tid == 0) *okflag = 1;
+  __syncthreads();
+  for (int c = 0; c < n; ++c) {
+    if (tid == 0) {
+      double dcc = A[c * n + c];
+      if (!(dcc > 0.0)) { *okflag = 0; dcc = 1.0; }
+      A[c * n + c] = sqrt(dcc);
+    }
+    __syncthreads();
+    const double l = A[c * n + c];
+    for (int i = c + 1 + tid; i < n; i += BIG_THREADS) A[i * n + c] /= l;
+    __syncthreads();
+    // trailing update of the lower triangle: entry (i, k), c < k <= i
+    const int m = n - c - 1;
+    for (int e = tid; e < m * (m + 1) / 2; e += BIG_THREADS) {
+      int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      while (i * (i + 1) / 2 > e) --i;
+      const int k = e - i * (i + 1) / 2;
+      const int gi = c + 1 + i, gk = c + 1 + k;
+      A[gi * n + gk] -= A[gi * n + c] * A[gk * n + c];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < n; ++i) {  // forward: L y = b
+      double v = b[i];
+      for (int k = 0; k < i; ++k) v -= A[i * n + k] * b[k];
+      b[i] = v / A[i * n + i];
+    }
+    for (int i = 0; i < n; ++i) b[i] += rng.normal();
+    for (int i = n - 1; i >= 0; --i) {  // backward: L' x = y + z
+      double v = b[i];
+      for (int k = i + 1; k < n; ++k) v -= A[k * n + i] * b[k];
+      b[i] = v / A[i * n + i];
+    }
+  }
+  __syncthreads();
+  return *okflag != 0;
+}
+
+__global__ void __launch_bounds__(BIG_THREADS) fsv_loadings_big_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+  extern __shared__ double bsm[];   // A[r*r] b[r] idx (ints)
+  __shared__ int okflag, ri_s;
+  const uint32_t sweep = *sweep_p;
+  const int i = blockIdx.x, tid = threadIdx.x, r = d.r;
+  double* A = bsm;
+  double* b = A + r * r;
+  int* idx = reinterpret_cast<int*>(b + r);
+  if (tid == 0) {
+    int ri = 0;
+    for (int k = 0; k < r; ++k) if (d.restr[(size_t)k * d.M + i]) idx[ri++] = k;
+    ri_s = ri;
+  }
+  __syncthreads();
+  const int ri = ri_s;
+  if (ri == 0) return;
+  const double* y = d.resid + (size_t)i * d.T;
+  const double* wx = d.wexp + (size_t)i * d.T;
+  const int nent = ri * (ri + 1) / 2;
+  for (int e = tid; e < nent + ri; e += BIG_THREADS) {
+    double acc = 0.0;
+    if (e < nent) {
+      int p = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((p + 1) * (p + 2) / 2 <= e) ++p;
+      while (p * (p + 1) / 2 > e) --p;
+      const int q = e - p * (p + 1) / 2;
+      const int kp = idx[p], kq = idx[q];
+      for (int t = 0; t < d.T; ++t) acc += d.fac[(size_t)t * r + kp] * wx[t] * d.fac[(size_t)t * r + kq];
+      if (p == q) acc += 1.0 / d.tau2[(size_t)kp * d.M + i];
+      A[p * ri + q] = acc;
+    } else {
+      const int p = e - nent, kp = idx[p];
+      for (int t = 0; t < d.T; ++t) acc += d.fac[(size_t)t * r + kp] * wx[t] * y[t];
+      b[p] = acc;
+    }
+  }
+  __syncthreads();
+  RngStream rng(seed, STREAM_FSV_LOAD, (uint32_t)i, sweep);
+  if (!block_chol_draw(ri, A, b, rng, &okflag) && tid == 0) d.status[0] = 1;
+  for (int p = tid; p < ri; p += BIG_THREADS) {
+    double l = b[p];
+    if (fabs(l) < d.facloadtol) l = (l < 0.0) ? -d.facloadtol : d.facloadtol;
+    d.facload[(size_t)idx[p] * d.M + i] = l;
+  }
+}
+
+__global__ void __launch_bounds__(BIG_THREADS) fsv_factors_big_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
+  extern __shared__ double bsm[];   // A[r*r] b[r]
+  __shared__ int okflag;
+  const uint32_t sweep = *sweep_p;
+  const int t = blockIdx.x, tid = threadIdx.x, r = d.r;
+  double* A = bsm;
+  double* b = A + r * r;
+  const int nent = r * (r + 1) / 2;
+  for (int e = tid; e < nent + r; e += BIG_THREADS) {
+    double acc = 0.0;
+    if (e < nent) {
+      int p = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((p + 1) * (p + 2) / 2 <= e) ++p;
+      while (p * (p + 1) / 2 > e) --p;
+      const int q = e - p * (p + 1) / 2;
+      for (int i = 0; i < d.M; ++i)
+        acc += d.facload[(size_t)p * d.M + i] * d.wexp[(size_t)i * d.T + t] * d.facload[(size_t)q * d.M + i];
+      if (p == q) acc += exp(-d.logvar[(size_t)(d.M + p) * d.T + t]);
+      A[p * r + q] = acc;
+    } else {
+      const int p = e - nent;
+      for (int i = 0; i < d.M; ++i)
+        acc += d.facload[(size_t)p * d.M + i] * d.wexp[(size_t)i * d.T + t] * d.resid[(size_t)i * d.T + t];
+      b[p] = acc;
+    }
+  }
+  __syncthreads();
+  RngStream rng(seed, STREAM_FSV_FAC, (uint32_t)t, sweep);
+  if (!block_chol_draw(r, A, b, rng, &okflag) && tid == 0) d.status[0] = 2;
+  for (int p = tid; p < r; p += BIG_THREADS) d.fac[(size_t)t * r + p] = b[p];
+}
+
 // The NG hyper-parameters of the loadings only read the loadings of the previous sweep: the Gibbs loop may run them on
 // its side stream next to the SV series kernel (launch_fsv_ng there, `ng_done` here instead of the launch).
 bool fsv_has_ng(const FsvDev& d) { return d.r > 0 && d.ngprior; }
@@ -579,9 +709,20 @@ cudaError_t launch_fsv_rest(const FsvDev& d, uint64_t seed, const uint32_t* swee
         fsv_ng_kernel<<<(units + 3) / 4, 128, 0, s>>>(d, seed, sweep);
       }
     }
-    fsv_loadings_kernel<<<(d.M + 3) / 4, 128, 0, s>>>(d, seed, sweep);
+    const size_t bigsmem = ((size_t)d.r * d.r + d.r) * sizeof(double) + (size_t)d.r * sizeof(int) + 16;
+    if (d.r > FSV_RMAX) {
+      if (bigsmem > 48 * 1024) {
+        cudaFuncSetAttribute(fsv_loadings_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigsmem);
+        cudaFuncSetAttribute(fsv_factors_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigsmem);
+      }
+      fsv_loadings_big_kernel<<<d.M, BIG_THREADS, bigsmem, s>>>(d, seed, sweep);
+    } else {
+      fsv_loadings_kernel<<<(d.M + 3) / 4, 128, 0, s>>>(d, seed, sweep);
+    }
     if (d.interweaving != 0) fsv_interweave_kernel<<<d.r, IW_THREADS, 0, s>>>(d, seed, sweep);
-    {
+    if (d.r > FSV_RMAX) {
+      fsv_factors_big_kernel<<<d.T, BIG_THREADS, bigsmem, s>>>(d, seed, sweep);
+    } else {
       const size_t per_slice = (size_t)(d.r * (d.r + 1) / 2 + d.r) * 32 * sizeof(double);
       int nsl = FAC_SLICES;
       while (nsl > 1 && nsl * per_slice > (size_t)200 * 1024) --nsl;      // r > 13: fewer row slices

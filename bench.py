@@ -10,18 +10,19 @@ factor SV (r=1), Dirichlet-Laplace prior - the shape `metric` is quoted on.
     python bench.py --gpus N --steps K --warmup W          # this repo (CUDA)
     python bench.py --impl reference --steps K --warmup W  # CPU restatement of the reference
 
-value  = sweeps/s with the chain resident in HBM (CUDA events on the sampler stream,
-         max over ranks), every sweep stored into the device ring.
-e2e    = sweeps/s through the public host API (bvar()-equivalent: host buffers in,
-         caller-owned draw arrays out, H2D of the data + per-sweep D2H of the stored
-         draw inside the timed region).
+value  = sweeps/s with the chain resident in HBM: W warm-up sweeps, then REPS back-to-back regions of exactly K
+         sweeps each, every region bracketed by barrier + synchronize and timed with CUDA events on the sampler
+         stream (max over ranks); `value` is K / median region time, all repetitions are in `repetitions_ms`.
+         Nothing but graph-replayed sweeps runs inside a region (no instrumented sweep, no subprocess).
+e2e    = sweeps/s through the public host API (bvar()-equivalent: host buffers in, caller-owned draw arrays out;
+         H2D of the data + per-sweep D2H of the stored draw inside the timed region), median of 3 fresh chains.
+roofline = the longer of K1 / K2, from their live %globaltimer spans accumulated over the timed regions.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -33,6 +34,16 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = dict(M=100, p=4, T=500, r=1, prior="DL")
+METRIC = "Gibbs draws/sec (M=100,p=4,T=500 factor-SV, DL)"
+REPS = 7
+
+
+def workload_config(n_gpus):
+    """The `config` object - identical keys and values for both arms."""
+    w = WORKLOAD
+    return dict(workload=f"M={w['M']} p={w['p']} T={w['T']} factor-SV r={w['r']} prior={w['prior']} (BASELINE configs[2])",
+                n_gpus=n_gpus, every_sweep_stored=True,
+                l2="state per sweep (Z 322 MB + packed systems 65 MB) exceeds the 126 MB L2; no flush needed")
 
 
 def synth_data(M, p, T, seed=123):
@@ -41,7 +52,7 @@ def synth_data(M, p, T, seed=123):
 
 
 def algorithmic_gflop(M, Kp, T, r):
-    """BASELINE.md §2 / SURVEY.md §8(d): per-sweep algorithmic work (GFLOP)."""
+    """BASELINE.md section 2 / SURVEY.md section 8(d): per-sweep algorithmic work (GFLOP)."""
     syrk = M * T * Kp * (Kp + 1)
     rhs = 2 * M * T * Kp
     chol = M * Kp ** 3 / 3
@@ -52,36 +63,51 @@ def algorithmic_gflop(M, Kp, T, r):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+    """SM clock / throttle reasons through NVML inside this process (no fork): samples continuously, keeps only the
+    samples taken while `active` is set (the timed regions)."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = threading.Event()
         self._halt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml is None:
+            return
+        nv = self.nvml
         while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+            if self.active.is_set():
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                    self.samples.append(mhz)
+                    for nm, bit in self.REASONS.items():
+                        if bits & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                time.sleep(0.0005)
+            else:
+                time.sleep(0.0002)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
-                    reasons=sorted(self.reasons), samples=len(self.samples))
+                    reasons=sorted(self.reasons), samples=len(self.samples), how="NVML in-process, timed regions only")
 
 
 def make_problem():
@@ -107,6 +133,27 @@ def cpu_reference_rate(prep, pp, ps, sweeps, warm=1):
     return sweeps / (time.perf_counter() - t0)
 
 
+def vignette_anchor():
+    """The reference's own published timing (vignettes/huge_all_combinations.RData row 24: M = 50, n = 100, p = 4, factor
+    r = 1, SV, default HS prior: 1.69 s user time for bvar(draws = 10, burnin = 0) on one core of an i7-10610U),
+    re-run with the oracle port on ONE thread of this host: the same protocol (iid N(0,1) data, seed 123)."""
+    from threadpoolctl import threadpool_limits
+    from bayesianvars_b200 import bvar as B
+    from oracle import gibbs as og
+    M, p, n = 50, 4, 100
+    data = np.random.default_rng(123).standard_normal((n + p, M))
+    pp = B.specify_prior_phi(M, p, "HS")
+    ps = B.specify_prior_sigma(M, type="factor", factor_factors=1)
+    prep = B.prepare(data, p, 10.0, pp, ps, rng=np.random.default_rng(123))
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        og.run(prep, pp, ps, draws=10, burnin=0, rng=np.random.default_rng(1))
+        sec = time.perf_counter() - t0
+    return dict(shape="M=50 n=100 p=4 factor r=1 SV, HS prior, 10 sweeps", port_seconds_1thread=sec,
+                published_seconds=1.69, published_on="i7-10610U, one core, R (vignettes/huge_all_combinations.RData row 24)",
+                ratio_port_over_published=sec / 1.69)
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -115,21 +162,34 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def cpu_baselines(prep, pp, ps, n_all=12, n_one=4):
+    """All-core and single-thread figures of the oracle port, plus the vignette anchor."""
+    from threadpoolctl import threadpool_limits
+    cores = blas_threads()
+    rate = cpu_reference_rate(prep, pp, ps, n_all, 1)
+    with threadpool_limits(limits=1):
+        rate1 = cpu_reference_rate(prep, pp, ps, n_one, 1)
+    cpu = dict(value=rate, unit="sweeps/s", cores=cores, kind="port",
+               sample=f"{n_all} full sweeps of oracle.gibbs on the same inputs (NumPy/SciPy-LAPACK restatement of bvar_cpp, "
+                      f"OpenBLAS {cores} threads); the R reference cannot run here")
+    cpu1 = dict(value=rate1, unit="sweeps/s", cores=1, kind="port",
+                sample=f"{n_one} full sweeps of oracle.gibbs with the BLAS pool limited to one thread (the vignette's 'one core' setting)")
+    return cpu, cpu1
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _, pp, ps, prep = make_problem()
     cores = blas_threads()
-    # each "step" = one CPU sweep (~1 s at this shape); bounded so the run ends within minutes
-    steps = min(args.steps, 40)
-    warm = min(args.warmup, 2)
+    # each "step" = one full CPU sweep (~0.4 s at this shape on 16 threads): K and W are honoured as given
+    steps, warm = args.steps, args.warmup
     rate = cpu_reference_rate(prep, pp, ps, steps, warm)
-    w = WORKLOAD
-    line = dict(metric="Gibbs draws/sec (M=100,p=4,T=500 factor-SV, DL)", value=rate, unit="sweeps/s", n_gpus=args.gpus,
+    line = dict(metric=METRIC, value=rate, unit="sweeps/s", n_gpus=args.gpus,
                 steps=steps, warmup=warm, ms_per_step=1e3 / rate, higher_is_better=True, scaling="strong",
                 vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=f"M={w['M']} p={w['p']} T={w['T']} factor-SV r={w['r']} prior={w['prior']} (BASELINE configs[2])"),
+                config=workload_config(args.gpus),
                 cpu_baseline=dict(value=rate, unit="sweeps/s", cores=cores, kind="port",
                                   sample=f"{steps} full sweeps of oracle.gibbs (NumPy/SciPy-LAPACK restatement of bvar_cpp, "
                                          f"OpenBLAS {cores} threads); the R reference cannot run here"),
@@ -151,6 +211,21 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    data, pp, ps, prep = make_problem()
+    w = WORKLOAD
+    Kp = prep["Kp"]
+    W, K = args.warmup, args.steps
+
+    # ---------------- N > 1: a short fixed-seed chain on ONE GPU first (rank 0), to compare the sharded chain with
+    parity_ref = None
+    PAR_SWEEPS = 12
+    if world > 1 and rank == 0:
+        with Handle(local_rank, seed=4242) as h1:
+            s1 = B.Sampler(h1, prep, pp, ps, draws=PAR_SWEEPS, burnin=0, thin=1, sv_keep="last")
+            s1.run()
+            parity_ref = {k: s1.out[k].copy() for k in ("PHI", "logvar", "sv_para", "V_prior")}
+            del s1
+
     h = Handle(local_rank, seed=2024)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -160,11 +235,6 @@ def run_cuda(args):
             uid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         h._check(h._lib.bvb_comm_init(h._h, rank, world, bytes(uid.cpu().tolist())))
-
-    data, pp, ps, prep = make_problem()
-    w = WORKLOAD
-    Kp = prep["Kp"]
-    W, K = args.warmup, args.steps
     peak = h.measure_fp64_peak() if rank == 0 else None
 
     def barrier():
@@ -172,24 +242,53 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: device-resident chain, K timed sweeps after W warm-up sweeps
-    smp = B.Sampler(h, prep, pp, ps, draws=W + K, burnin=0, thin=1, sv_keep="last")
-    smp.run(W)                       # warm-up (includes the eager first sweep + graph capture)
-    barrier()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- N > 1 parity: the same fixed-seed chain, equations sharded, against the one-GPU chain
+    parity = None
+    if world > 1:
+        seed_keep = h.seed
+        h.reseed(4242)
+        sp = B.Sampler(h, prep, pp, ps, draws=PAR_SWEEPS, burnin=0, thin=1, sv_keep="last")
+        sp.run()
+        if rank == 0:
+            parity = {}
+            for k, ref in parity_ref.items():
+                got = sp.out[k]
+                parity[k] = float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300))
+        del sp
+        h.reseed(seed_keep)
+        barrier()
+
+    # ---------------- value: device-resident chain, REPS regions of K timed sweeps after W warm-up sweeps
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    smp.run(K)
-    barrier()
-    tm = smp.timing()
+    smp = B.Sampler(h, prep, pp, ps, draws=W + 1 + REPS * K, burnin=0, thin=1, sv_keep="last")
+    smp.run(W)                        # warm-up (includes the eager first sweep + graph capture)
+    phases = smp.profile_sweep()      # per-phase events of one serial sweep: OUTSIDE the timed regions
+    smp.kernel_times(reset=True)
+    reps_ms = []
+    for _rep in range(REPS):
+        barrier()
+        clocks.active.set()
+        smp.run(K)
+        barrier()
+        clocks.active.clear()
+        tm = smp.timing()
+        assert tm["sweeps"] == K
+        reps_ms.append(max_over_ranks(tm["total_ms"]))
+    kt = smp.kernel_times()
     clk = clocks.stop() if rank == 0 else None
-    dev_ms = torch.tensor([tm["total_ms"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-    dev_ms = float(dev_ms.item())
+    dev_ms = float(np.median(reps_ms))
     value = K / (dev_ms * 1e-3)
     stored_bytes = sum(smp.out[k][..., 0].nbytes for k in ("PHI", "V_prior", "logvar", "sv_para", "phi_hyperparameter", "facload", "fac"))
     out_template = {k: v.shape for k, v in smp.out.items()}
+    launches_per_sweep = tm["launches_per_sweep"]
     del smp
 
     # ---------------- e2e: bvar()-equivalent through the host API, fresh chain of K sweeps
@@ -198,9 +297,7 @@ def run_cuda(args):
     out_arrays = {k: np.zeros((*shp[:-1], K if shp[-1] else 0), order="F") for k, shp in out_template.items()}
     for a in out_arrays.values():
         a.fill(0.0)
-    # best of three fresh chains (every repetition is the whole path: init, H2D, K sweeps, D2H of every stored draw);
-    # a single repetition swung between 0.40 and 0.55 s from one fresh box to the next (allocator / first graph upload)
-    e2e_best = float("inf")
+    e2e_s = []
     for _rep in range(3):
         barrier()
         t0 = time.perf_counter()
@@ -208,18 +305,11 @@ def run_cuda(args):
         while smp2.done < K:
             smp2.run(256)
         barrier()
-        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e_best = min(e2e_best, float(e2e_s.item()))
-        assert np.isfinite(smp2.out["PHI"]).all()
-        if _rep < 2:
-            del smp2
-    e2e = K / e2e_best
+        e2e_s.append(max_over_ranks(time.perf_counter() - t0))
+        assert np.isfinite(smp2.out["PHI"]).all() and np.abs(smp2.out["PHI"][..., 0]).max() > 0
+        del smp2
+    e2e = K / float(np.median(e2e_s))
     h2d = (prep["Y"].nbytes + prep["X"].nbytes + 3 * prep["PHI0"].nbytes + prep["startvals"]["sv_logvar"].nbytes) / K
-    assert np.isfinite(smp2.out["PHI"]).all()
-    launches = tm["launches_per_sweep"] * K
-    del smp2
 
     if world > 1:
         dist.barrier()
@@ -227,59 +317,70 @@ def run_cuda(args):
     if rank != 0:
         return
     gf = algorithmic_gflop(w["M"], Kp, w["T"], w["r"])
-    ph = tm["phase_ms"]
     nloc = -(-w["M"] // world)
     frac_local = nloc / w["M"]
     kern = {}
     for name, key in (("k1_pairgemm", "k1"), ("k2_cholsolve", "k2")):
-        ach = gf[key] * frac_local / (ph[key] * 1e-3) / 1e3 if ph[key] > 0 else None   # TFLOP/s
-        kern[name] = dict(ms=ph[key], achieved=ach, share_of_sweep=ph[key] / (1e3 / value) if value else None)
+        ms = kt[key + "_ms"]
+        ach = gf[key] * frac_local / (ms * 1e-3) / 1e3 if ms > 0 else None   # TFLOP/s
+        kern[name] = dict(ms=ms, achieved=ach, share_of_sweep=ms / (1e3 / value) if value else None,
+                          frac_of_self_measured_dmma_peak=(ach / peak["dmma_tflops"]) if ach else None)
     dom = max(kern, key=lambda k: kern[k]["ms"])
-    traffic = None
+    traffic, traffic_src = None, None
     prof = ROOT / "profiles" / "ncu_summary.json"
     if prof.exists():
         try:
             summ = json.loads(prof.read_text())
-            traffic = (summ.get(dom) or summ.get(dom + "_v2") or {}).get("dram_bytes_per_launch")
+            ent = summ.get(dom) or summ.get(dom + "_v2") or {}
+            traffic = ent.get("dram_bytes_per_launch")
+            traffic_src = f"profiles/ncu_summary.json (ncu --set full capture of {dom}, committed; not re-measured in this run)"
         except Exception:
             traffic = None
     roofline = dict(bound="tensor", kernel=dom, achieved=kern[dom]["achieved"], peak=peak["dmma_tflops"], unit="TFLOP/s",
                     frac=(kern[dom]["achieved"] / peak["dmma_tflops"]) if kern[dom]["achieved"] else None, traffic=traffic,
-                    peak_source="FP64 DMMA m8n8k4 micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                    traffic_source=traffic_src,
+                    peak_source="self-measured: FP64 DMMA m8n8k4 register-resident micro-kernel run in this process "
+                                "(MEASURED_PEAKS.json has no FP64 entry)",
+                    timing_source=f"live %globaltimer spans (first CTA start to last CTA end) of every launch inside the "
+                                  f"{REPS} timed regions, mean of {kt['sweeps']} launches",
                     algorithmic_gflop_per_launch=gf["k1" if dom == "k1_pairgemm" else "k2"] * frac_local,
-                    kernels=kern, dfma_peak_tflops=peak["dfma_tflops"], phases_ms=ph)
-    cpu = None
+                    kernels=kern, dfma_peak_tflops=peak["dfma_tflops"],
+                    phases_ms_serial_sweep=phases)
+    cpu = cpu1 = anchor = None
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu = 12
-        rate = cpu_reference_rate(prep, pp, ps, n_cpu, 1)
-        cpu = dict(value=rate, unit="sweeps/s", cores=blas_threads(), kind="port",
-                   sample=f"{n_cpu} full sweeps of oracle.gibbs on the same inputs (NumPy/SciPy-LAPACK restatement; "
-                          "the R reference cannot run here)")
-    line = dict(metric="Gibbs draws/sec (M=100,p=4,T=500 factor-SV, DL)", value=value, unit="sweeps/s", n_gpus=world,
+        cpu, cpu1 = cpu_baselines(prep, pp, ps)
+        anchor = vignette_anchor()
+    cfg = workload_config(world)
+    line = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=world,
                 steps=K, warmup=W, ms_per_step=dev_ms / K, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype="f64", data="synthetic",
-                config=dict(workload=f"M={w['M']} p={w['p']} T={w['T']} factor-SV r={w['r']} prior={w['prior']} (BASELINE configs[2])",
-                            parallelism=("single GPU" if world == 1 else f"equations sharded over {world} GPUs, NCCL allgather of PHI per sweep"),
-                            l2="state per sweep (Z 322 MB + packed systems 65 MB) exceeds the 126 MB L2; no flush needed",
-                            every_sweep_stored=True),
-                clocks=clk,
+                dtype="f64", data="synthetic", config=cfg,
+                parallelism=("single GPU" if world == 1 else f"equations sharded over {world} GPUs"),
+                repetitions=REPS, repetitions_ms=reps_ms, clocks=clk,
                 e2e=dict(value=e2e, unit="sweeps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=stored_bytes,
-                         note="best of 3 fresh chains, each: bvb_gibbs_init (H2D of data, priors, start values; pair-product build) + K sweeps, "
+                         repetitions_s=e2e_s,
+                         note="median of 3 fresh chains, each: bvb_gibbs_init (H2D of data, priors, start values) + K sweeps, "
                               "every sweep's draw copied into caller-owned (pre-allocated) host arrays"),
-                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+                gpu_launches=launches_per_sweep * K, roofline=roofline, cpu_baseline=cpu, cpu_baseline_1thread=cpu1,
+                vignette_anchor=anchor)
+    if parity is not None:
+        line["parity_vs_n1"] = dict(max_rel_err=parity, sweeps=PAR_SWEEPS,
+                                    note="fixed-seed chain with the equations sharded over the ranks against the same chain "
+                                         "on one GPU, computed in this run (max |diff| / max |ref| over all stored draws)")
     print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        if args.steps == 256 and args.warmup == 32:    # no flags given: a CPU run that still ends within minutes
+            args.steps, args.warmup = 20, 3
         run_reference(args)
     else:
         run_cuda(args)

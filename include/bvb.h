@@ -46,6 +46,11 @@ typedef struct bvb_handle bvb_handle;
 int bvb_create(bvb_handle** out, int device, uint64_t seed);
 void bvb_destroy(bvb_handle* h);
 const char* bvb_version(void);
+/* Re-key the Philox generator of an existing handle (takes effect for the calls that
+ * follow; call before bvb_gibbs_init for a new chain).  Lets a host keep ONE handle -
+ * one CUDA context, one set of cached workspaces - per process, as the Rcpp shim does,
+ * and still draw a fresh key from R's RNG at every entry point. */
+int bvb_set_seed(bvb_handle* h, uint64_t seed);
 
 /* Last error of this handle.  step: 1 = PHI draw, 2 = hyper-parameters,
  * 3 = Sigma_t update, 4 = irf, 5 = predict; sweep and equation are 1-based as
@@ -222,11 +227,33 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
  * end).  Stored draws are written into the bvb_draws given to bvb_gibbs_init. */
 int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done);
 
-/* Device time of the sweeps run by the last bvb_gibbs_run call: out[0] total ms
- * (CUDA events on the sampler stream), out[1] = kernels launched per sweep,
- * out[2..9] = ms per sweep of {prep, K1, K2, hyper, resid, sv, store, comm}
- * sampled on the last sweep.  Returns sweeps timed. */
+/* Device time of the graph-replayed sweeps of the last bvb_gibbs_run call: out[0]
+ * total ms (CUDA events on the sampler stream), out[1] = kernels launched per sweep,
+ * out[2..9] = ms of {prep, K1, K2, comm, clamp + hyper, resid, Sigma_t, store} as
+ * measured by the last bvb_gibbs_profile_sweep (0 before one ran).  Returns the
+ * number of sweeps out[0] covers (the eager first sweep of a chain is excluded). */
 int bvb_gibbs_timing(const bvb_handle* h, double* out10);
+
+/* One further sweep of the chain (counted and stored like any other) launched in its
+ * serial form with CUDA events between the phases; out8 = ms of the eight phases
+ * above.  bvb_gibbs_run itself never instruments a sweep, so callers decide where
+ * this lies relative to their own timed regions. */
+int bvb_gibbs_profile_sweep(bvb_handle* h, double* out8, int* done);
+
+/* Live kernel timers: K1 (pair-GEMM Z tiles) and K2 (Cholesky / solve / draw) stamp
+ * the device %globaltimer of their first CTA start and last CTA end in every sweep
+ * (graph replay included); out3 = {K1 ms, K2 ms, sweeps} accumulated since the last
+ * reset (reset != 0 clears the accumulators after reading). */
+int bvb_gibbs_kernel_times(bvb_handle* h, double* out3, int reset);
+
+/* ---- a12: the tolerance clamp of src/bvar_cpp.cpp:534-559 on host arrays ---------
+ * PHI_io / PHI0 are Kp x M; on the K lag rows |PHI - PHI0| is pushed up to tol and an
+ * exact zero becomes +tol or -tol with probability 1/2 (R::rbinom(1, 0.5) there, the
+ * Philox stream of (handle seed, element, sweep) here).  The Gibbs sweep runs the same
+ * kernel on device state; this entry point exists so that the exact-zero branch, which
+ * a chain never reaches, can be tested. */
+int bvb_tolerance_clamp(bvb_handle* h, int K, int Kp, int M, double* PHI_io,
+                        const double* PHI0, double tol, uint32_t sweep);
 
 /* Copy the current sampler state back (for tests): any pointer may be NULL. */
 int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,

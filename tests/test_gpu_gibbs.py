@@ -289,3 +289,104 @@ def test_tall_systems_beyond_one_panel(handle, sigma):
     res = B.bvar(Y, lags=p, draws=6, burnin=4, prior_phi=pp, prior_sigma=ps, handle=handle, rng=np.random.default_rng(5))
     assert res["PHI"].shape == (M * p + 1, M, 6) and np.isfinite(res["PHI"]).all()
     assert np.abs(res["PHI"][:-1]).max() < 1.0        # white noise data: shrunk towards zero
+
+
+# ------------------------------------------------------------------ round 2: gaps named by the review
+def test_first_sweep_is_stored_with_burnin_zero(handle):
+    """bvar_cpp.cpp:751 stores rep 0 when burnin = 0 and thin = 1; the first sweep of a chain is launched eagerly
+    (before the graph exists) and its draw must reach the caller's arrays like every other."""
+    M, p, T = 5, 2, 80
+    Y, A, pp, ps, prep = setup(M, p, T, "DL")
+    a = B.Sampler(handle, prep, pp, ps, draws=7, burnin=0, thin=1, sv_keep="all")
+    a.run()
+    c = B.Sampler(handle, prep, pp, ps, draws=7, burnin=0, thin=1, sv_keep="all")
+    c.run(1)
+    st = c.state()
+    for k in ("PHI", "V_prior", "logvar", "sv_para", "facload"):
+        assert np.array_equal(a.out[k][..., 0], st[k]), k          # draw 0 = the state after one sweep
+    assert np.abs(a.out["PHI"][..., 0]).max() > 0
+    # and the later draws are the same chain: thin = 2 keeps sweeps 1, 3, 5
+    b = B.Sampler(handle, prep, pp, ps, draws=6, burnin=0, thin=2, sv_keep="all")
+    b.run()
+    for k in ("PHI", "logvar", "phi_hyperparameter"):
+        assert np.array_equal(b.out[k], a.out[k][..., 1:6:2]), k
+
+
+def test_tolerance_clamp_exact_zero_branch(handle):
+    """bvar_cpp.cpp:534-559: |PHI - PHI0| below PHI_tol is pushed to +-PHI_tol keeping its sign; an exact zero gets
+    +tol or -tol with probability 1/2 (:541-547).  Intercept row untouched."""
+    K, M, tol = 300, 40, 1e-3
+    rng = np.random.default_rng(0)
+    PHI0 = np.asfortranarray(rng.standard_normal((K + 1, M)))
+    PHI = PHI0.copy(order="F")                        # exact zeros everywhere
+    PHI[:10] += 0.5                                   # far from the prior mean: untouched
+    PHI[10:20] += 1e-5                                # small positive -> +tol
+    PHI[20:30] -= 1e-5                                # small negative -> -tol
+    out = handle.tolerance_clamp(PHI, PHI0, K, tol, sweep=3)
+    d = out - PHI0
+    assert np.array_equal(out[:10], PHI[:10])
+    np.testing.assert_allclose(d[10:20], tol, rtol=1e-9)
+    np.testing.assert_allclose(d[20:30], -tol, rtol=1e-9)
+    z = d[30:K]
+    np.testing.assert_allclose(np.abs(z), tol, rtol=1e-9)
+    frac = (z > 0).mean()                             # 270 x 40 = 10 800 fair coins: 5 sd = 0.024
+    assert abs(frac - 0.5) < 0.03, frac
+    assert np.array_equal(out[K], PHI[K])             # the intercept row is never clamped
+    out2 = handle.tolerance_clamp(PHI, PHI0, K, tol, sweep=4)
+    assert not np.array_equal(np.sign(out2 - PHI0)[30:K], np.sign(z))   # keyed by the sweep
+    assert np.array_equal(handle.tolerance_clamp(PHI, PHI0, K, tol, sweep=3), out)   # and reproducible
+
+
+@pytest.mark.parametrize("grouping,prior", [("equation-wise", "DL"), ("covariate-wise", "HS"), ("equation-wise", "R2D2")])
+def test_many_coefficient_groups(handle, grouping, prior):
+    """global_grouping = 'equation-wise' / 'covariate-wise' (R/utility_functions.R:2028-2075) give M / K groups:
+    more than the 32 the first hyper-parameter kernels could reduce.  Chain against the oracle chain."""
+    M, p, T = 36, 1, 90
+    Y, A = sim_var(M, p, T)
+    pp = B.specify_prior_phi(M, p, prior, global_grouping=grouping)
+    assert pp["prior_phi_cpp"]["n_groups"] == 36
+    ps = B.specify_prior_sigma(M, factor_factors=1)
+    prep = B.prepare(Y, p, 10.0, pp, ps, rng=np.random.default_rng(3))
+    smp = B.Sampler(handle, prep, pp, ps, draws=1500, burnin=500)
+    smp.run()
+    orc = og.run(prep, pp, ps, draws=300, burnin=150, rng=np.random.default_rng(11))
+    G, n = 36, M * M
+    hyp_g, hyp_o = smp.out["phi_hyperparameter"], orc["phi_hyperparameter"]
+    assert hyp_g.shape == (2 * G + 2 * n, 1500) and np.isfinite(hyp_g).all()
+    # own-lag coefficients (0.5 in the simulation) and the per-group scalars (xi | zeta on the log scale)
+    own_g = np.array([smp.out["PHI"][j, j].mean() for j in range(M)])
+    own_o = np.array([orc["PHI"][j, j].mean() for j in range(M)])
+    assert np.abs(own_g - own_o).max() < 0.12, np.abs(own_g - own_o).max()
+    row = slice(G, 2 * G) if prior != "HS" else slice(0, G)
+    if prior != "DL":   # plain DL never updates xi (Q4)
+        lg, lo = np.log(hyp_g[row]).mean(axis=1), np.log(hyp_o[row]).mean(axis=1)
+        assert np.abs(lg - lo).mean() < 0.5, (lg, lo)
+    else:
+        assert np.all(hyp_g[row] == 0.5)
+
+
+def test_fifty_factors(handle):
+    """The reference's own benchmark uses r = 50 factors (vignettes/scalability-vignette.qmd:95): beyond 16 factors the
+    r x r systems of the loadings / factors move to shared memory.  Chain against the oracle chain at r = 20."""
+    M, p, T, r = 30, 1, 100, 20
+    Y, A = sim_var(M, p, T)
+    pp = B.specify_prior_phi(M, p, "HS")
+    ps = B.specify_prior_sigma(M, factor_factors=r)
+    prep = B.prepare(Y, p, 10.0, pp, ps, rng=np.random.default_rng(3))
+    smp = B.Sampler(handle, prep, pp, ps, draws=1200, burnin=400)
+    smp.run()
+    assert np.isfinite(smp.out["PHI"]).all() and smp.out["facload"].shape == (M, r, 1200)
+    orc = og.run(prep, pp, ps, draws=250, burnin=120, rng=np.random.default_rng(11))
+    own_g = np.array([smp.out["PHI"][j, j].mean() for j in range(M)])
+    own_o = np.array([orc["PHI"][j, j].mean() for j in range(M)])
+    assert np.abs(own_g - own_o).max() < 0.15, np.abs(own_g - own_o).max()
+    # implied idiosyncratic + common variance of every series at the last time point (identified, unlike the loadings)
+    def tot_var(o):
+        lam, lv = o["facload"], o["logvar"][-1]
+        return np.log((np.exp(lv[:M]) + np.einsum("mrd,rd->md", lam ** 2, np.exp(lv[M:]))).mean(axis=1))
+    assert np.abs(tot_var(smp.out) - tot_var(orc)).max() < 0.6
+    # r = 50 runs
+    ps50 = B.specify_prior_sigma(60, factor_factors=50)
+    Y50 = np.random.default_rng(1).standard_normal((64, 60))
+    res = B.bvar(Y50, lags=1, draws=12, burnin=8, prior_phi=B.specify_prior_phi(60, 1, "HS"), prior_sigma=ps50, handle=handle)
+    assert np.isfinite(res["PHI"]).all() and res["facload"].shape == (60, 50, 12)
