@@ -382,7 +382,7 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
   k2.n = Kp; k2.M = M; k2.ldo = ws.g.ldo; k2.ldz = Kp; k2.ldphi = Kp;
   static long long* d_prof = nullptr;
   if (getenv("BVB_K2_DEBUG")) k2.debug_mode = atoi(getenv("BVB_K2_DEBUG"));
-  if (getenv("BVB_K2_PROF")) {
+  if (getenv("BVB_K2_PROF") || getenv("BVB_K2T_PROF")) {
     if (!d_prof) cudaMalloc(&d_prof, 64 * sizeof(long long));
     cudaMemsetAsync(d_prof, 0, 64 * sizeof(long long), s);
     k2.prof = d_prof;
@@ -393,6 +393,13 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
     long long hp[64];
     cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
+    if (getenv("BVB_K2T_PROF")) {
+      fprintf(stderr, "K2 tiled chain CTA 0 (cycles, all steps): wait %lld load %lld syrk %lld factor %lld inverse %lld publish-diag %lld "
+                      "wait-history %lld sum %lld trsm+store %lld publish %lld | warp 1: old-history %lld wait-tile %lld new-history %lld\n",
+              hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7], hp[8], hp[9], hp[12], hp[13], hp[14]);
+      fprintf(stderr, "K2 tiled first bulk CTA: %lld tasks; cycles: wait-history %lld acc %lld P+C %lld wait-Linv %lld trsm+store+publish %lld "
+                      "wait-D %lld D-update %lld\n", hp[39], hp[32], hp[33], hp[34], hp[35], hp[36], hp[37], hp[38]);
+    } else
     fprintf(stderr, "K2 phase cycles (CTA 0) v1: gemm fill factor invert trsm writeback backsolve | v2: partA wait-panel trsm wb+partB fill - backsolve:\n  %lld %lld %lld %lld %lld %lld %lld\n", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
     fprintf(stderr, "K2 v2 panel warp: factor+invert %lld  wait#1 %lld  wait#2 %lld  wait#3 %lld  wait#4 %lld\n", hp[24], hp[25], hp[26], hp[27], hp[28]);
     fprintf(stderr, "K2 gemm cycles per block column:");

@@ -631,6 +631,7 @@ static void gibbs_free(bvb_handle* h) {
   if (G->ev_k1z) cudaEventDestroy(G->ev_k1z);
   if (G->side) cudaStreamDestroy(G->side);
   if (G->copy) cudaStreamDestroy(G->copy);
+  if (G->first_slot_host) cudaFreeHost(G->first_slot_host);
   for (int b = 0; b < 2; ++b) if (G->ev_sub[b]) cudaEventDestroy(G->ev_sub[b]);
   if (G->ev_chunk[0]) cudaEventDestroy(G->ev_chunk[0]);
   if (G->ev_chunk[1]) cudaEventDestroy(G->ev_chunk[1]);
@@ -681,12 +682,27 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     fprintf(stderr, "[bvb init] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - init_t0).count());
     init_t0 = t;
   };
-  gibbs_free(h);
-  init_mark("free previous chain");
+  // A handle that runs chain after chain of one shape (the usual case: bvar() called repeatedly, the bench's end-to-end
+  // repetitions) keeps its device buffers, streams and events: every buffer below is (re)filled by this function and
+  // GBuf::ensure only reallocates when a buffer must grow.  Freeing and reallocating ~0.5 GB cost 6 ms per chain.
+  Gibbs* Gp = static_cast<Gibbs*>(h->gibbs);
+  const int world_now = h->world > 0 ? h->world : 1;
+  const bool reuse = Gp && Gp->M == M && Gp->T == T && Gp->K == K && Gp->Kp == Kp && Gp->r == r && Gp->sigma_type == ps->type &&
+                     Gp->huge == (use_huge ? 1 : 0) && Gp->world == world_now && Gp->rank == h->rank &&
+                     Gp->tvp_all == (tvp_keep_all ? 1 : 0) && !getenv("BVB_NO_REUSE");
+  if (reuse) {
+    GB_TRY(cudaStreamSynchronize(h->stream));
+    if (Gp->graph_exec) { cudaGraphExecDestroy(Gp->graph_exec); Gp->graph_exec = nullptr; }   // kernel arguments (seed, priors) change
+    Gp->ready = false; Gp->k1z_valid = false; Gp->timed = false; Gp->timing_pass = false; Gp->rep = 0;
+    for (auto& v : Gp->phase_ms) v = 0;
+  } else {
+    gibbs_free(h);
+    Gp = new (std::nothrow) Gibbs();
+    if (!Gp) return BVB_ERR_CUDA;
+    h->gibbs = Gp;
+  }
+  init_mark(reuse ? "previous chain recycled" : "free previous chain");
   gbuf_stream() = h->stream;
-  Gibbs* Gp = new (std::nothrow) Gibbs();
-  if (!Gp) return BVB_ERR_CUDA;
-  h->gibbs = Gp;
   Gibbs& G = *Gp;
   G.M = M; G.T = T; G.K = K; G.Kp = Kp; G.intercept = intercept ? 1 : 0; G.r = r; G.S = M + r;
   G.draws = draws; G.burnin = burnin; G.thin = thin; G.tvp_all = tvp_keep_all ? 1 : 0;
@@ -730,8 +746,10 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     GB_TRY(G.WY.ensure((size_t)Nalloc * G.geom.Tp, true));
     if (!use_huge) GB_TRY(G.omega.ensure((size_t)std::max(G.nloc, 1) * G.geom.ldo));
     GB_TRY(G.Zn.ensure((size_t)Kp * std::max(use_huge ? M : G.nloc, 1)));
-    // the pair-product matrix Z is built ONCE per chain: X never changes
-    if (!use_huge) GB_TRY(launch_build_A(G.A.p, G.X.p, G.pairs.p, T, G.geom.Tp, Kp, G.geom.nArows, 0, s));
+    // the pair-product matrix Z is built ONCE per chain (X never changes) - and kept when the next chain has the same X
+    const bool sameX = reuse && G.Xhost.size() == (size_t)T * Kp && memcmp(G.Xhost.data(), X, sizeof(double) * (size_t)T * Kp) == 0;
+    if (!sameX) G.Xhost.assign(X, X + (size_t)T * Kp);
+    if (!use_huge && !sameX) GB_TRY(launch_build_A(G.A.p, G.X.p, G.pairs.p, T, G.geom.Tp, Kp, G.geom.nArows, 0, s));
     if (use_huge) {
       make_pair_geom(G.geomH, Kp, T);   // pairs of observations, contraction over the coefficients
       const int Kp_pad = G.geomH.Tp;
@@ -1064,22 +1082,28 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     G.pinned[b] = static_cast<double*>(h->pin[b]);
   }
   init_mark("ring + pinned staging");
-  for (auto& e : G.ev) GB_TRY(cudaEventCreate(&e));
-  if (!getenv("BVB_NO_FORK")) {
+  for (auto& e : G.ev) if (!e) GB_TRY(cudaEventCreate(&e));
+  if (getenv("BVB_NO_FORK") && G.side) { cudaStreamDestroy(G.side); G.side = nullptr; }   // (a recycled chain honours the switch)
+  if (!getenv("BVB_NO_FORK") && !G.side) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     GB_TRY(cudaStreamCreateWithPriority(&G.side, cudaStreamNonBlocking, lo));
+  }
+  if (G.side && !G.ev_fork) {
     GB_TRY(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_ng, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_series, cudaEventDisableTiming));
     GB_TRY(cudaEventCreateWithFlags(&G.ev_k1z, cudaEventDisableTiming));
   }
-  GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
-  GB_TRY(cudaEventCreate(&G.ev_chunk[1]));
-  GB_TRY(cudaStreamCreateWithFlags(&G.copy, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_sub[b], cudaEventDisableTiming));
-  for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_pin[b], cudaEventDisableTiming));
+  if (!G.copy) {
+    GB_TRY(cudaEventCreate(&G.ev_chunk[0]));
+    GB_TRY(cudaEventCreate(&G.ev_chunk[1]));
+    GB_TRY(cudaStreamCreateWithFlags(&G.copy, cudaStreamNonBlocking));
+    GB_TRY(cudaMallocHost(&G.first_slot_host, sizeof(int) * Gibbs::FS_SLOTS));
+    for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_sub[b], cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) GB_TRY(cudaEventCreateWithFlags(&G.ev_pin[b], cudaEventDisableTiming));
+  }
   GB_TRY(cudaStreamSynchronize(s));
   G.rep = 0;
   G.ready = true;
@@ -1116,7 +1140,8 @@ static inline int stored_count(const Gibbs& G, int rep) { return (rep <= G.burni
 static int run_eager_sweep(bvb_handle* h, Gibbs& G, bool timing) {
   cudaStream_t s = h->stream;
   const int stored_before = stored_count(G, G.rep);
-  GB_TRY(cudaMemcpyAsync(G.first_slot.p, &stored_before, sizeof(int), cudaMemcpyHostToDevice, s));
+  G.first_slot_host[0] = stored_before;
+  GB_TRY(cudaMemcpyAsync(G.first_slot.p, &G.first_slot_host[0], sizeof(int), cudaMemcpyHostToDevice, s));
   G.timing_pass = timing;
   int rc = enqueue_sweep(h, G);
   G.timing_pass = false;
@@ -1228,7 +1253,8 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     pd.buf = -1;
     return BVB_OK;
   };
-  int flip = 0, timed_sweeps = 0;
+  int flip = 0, timed_sweeps = 0, nchunk = 0;
+  bool closed = false;
   bool used[2] = {false, false};
   while (todo > 0) {
     const int stored_before = stored_count(G, G.rep);
@@ -1237,8 +1263,12 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     // ring half `flip` is free once the copy that last read it is done
     if (used[flip]) GB_TRY(cudaStreamWaitEvent(s, G.ev_pin[flip], 0));
     if (!two_halves && used[flip ^ 1]) GB_TRY(cudaStreamWaitEvent(s, G.ev_pin[flip ^ 1], 0));
-    const int first_slot = stored_before - (two_halves ? flip * half : 0);   // stored draw that maps to ring slot 0
-    GB_TRY(cudaMemcpyAsync(G.first_slot.p, &first_slot, sizeof(int), cudaMemcpyHostToDevice, s));
+    // stored draw that maps to ring slot 0 (pinned staging, one word per sub-chunk of this call: a pageable source
+    // would make the copy - and with it the enqueue of the next sub-chunk - wait for the stream)
+    if (nchunk > 0 && nchunk % (Gibbs::FS_SLOTS - 1) == 0) GB_TRY(cudaStreamSynchronize(s));   // staging words are reused
+    int* fs = &G.first_slot_host[1 + (nchunk++ % (Gibbs::FS_SLOTS - 1))];
+    *fs = stored_before - (two_halves ? flip * half : 0);
+    GB_TRY(cudaMemcpyAsync(G.first_slot.p, fs, sizeof(int), cudaMemcpyHostToDevice, s));
 #ifdef BVB_DEBUG_SWITCHES
     static const bool dbg_eager = getenv("BVB_DEBUG_EAGER") != nullptr;
 #else
@@ -1252,6 +1282,9 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     ran += nsw;
     todo -= nsw;
     timed_sweeps += nsw;
+    // the closing event goes in right behind the last sweep: recorded after the host-side scatter below it would carry
+    // the host's copy time (seen as 0.86 instead of 0.76 ms per sweep for calls of 16 + 4 sweeps)
+    if (todo == 0) { GB_TRY(cudaEventRecord(G.ev_chunk[1], s)); closed = true; }
     const int cnt = stored_count(G, G.rep) - stored_before;
     Pending cur = {-1, 0, 0};
     if (cnt > 0) {
@@ -1268,7 +1301,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     if (rc) return rc;
     pend = cur;
   }
-  GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
+  if (!closed) GB_TRY(cudaEventRecord(G.ev_chunk[1], s));
   {
     int rc = flush(pend);
     if (rc) return rc;

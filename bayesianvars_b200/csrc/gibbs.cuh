@@ -67,6 +67,7 @@ struct Gibbs {
   void* comm = nullptr;
   PairGeom geom;
   GBuf<double> X, Y, A, W, WY, omega, Vprior, PHI0, PHI, Zn, resid;
+  std::vector<double> Xhost;   // the regressors the pair-product matrix A was built from (a recycled chain skips the rebuild)
   GBuf<int2> lut, pairs;
   GBuf<int> colbase, status, eqstatus, nstored, first_slot;
   GBuf<uint32_t> sweep;
@@ -104,6 +105,8 @@ struct Gibbs {
   double* pinned[2] = {nullptr, nullptr};
   cudaStream_t side = nullptr;                 // hyper-parameter branch of the sweep graph
   cudaStream_t copy = nullptr;                 // D2H of the stored-draw ring (its two halves alternate between sub-chunks)
+  static constexpr int FS_SLOTS = 65;          // pinned staging words of `first_slot` ([0]: eager sweeps, rest: sub-chunks in flight)
+  int* first_slot_host = nullptr;
   cudaEvent_t ev_sub[2] = {nullptr, nullptr};  // sweeps of the sub-chunk that filled ring half b are done
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ng = nullptr, ev_series = nullptr, ev_k1z = nullptr;
   bool k1z_valid = false;                      // the Z tiles of the NEXT PHI draw are already in `omega` (see enqueue_sweep)

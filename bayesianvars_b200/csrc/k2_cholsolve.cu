@@ -1090,14 +1090,38 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
 static double* g_linv_ws = nullptr;
 static size_t g_linv_ws_bytes = 0;
 
+// The [M][nbk][32 x 32] inverses of the diagonal blocks, shared by every K2 form and by the solve-only kernel.
+double* k2_linv_workspace(size_t need) {
+  if (need > g_linv_ws_bytes) {
+    if (g_linv_ws) cudaFree(g_linv_ws);
+    if (cudaMalloc(&g_linv_ws, need) != cudaSuccess) { g_linv_ws = nullptr; g_linv_ws_bytes = 0; return nullptr; }
+    g_linv_ws_bytes = need;
+  }
+  return g_linv_ws;
+}
+
+cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s);   // k2_tiled.cu
+
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
   const int nbk = k2_nblocks(p.n);
   const size_t need = (size_t)p.M * nbk * K2_NB * K2_NB * sizeof(double);
-  if (need > g_linv_ws_bytes) {
-    if (g_linv_ws) cudaFree(g_linv_ws);
-    cudaError_t e = cudaMalloc(&g_linv_ws, need);
-    if (e != cudaSuccess) { g_linv_ws = nullptr; g_linv_ws_bytes = 0; return e; }
-    g_linv_ws_bytes = need;
+  if (!k2_linv_workspace(need)) return cudaErrorMemoryAllocation;
+  {
+    // The tile-queue form (k2_tiled.cu) when the equations alone cannot fill the chip: measured at n = 401 on 148 SMs,
+    // tiled / one-CTA-per-equation: 13 equations 242 / 303 us, 25: 250 / 307, 50: 277 / 334, 100: 483 / 338 (the look-ahead
+    // kernel below keeps the headline shape).  BVB_K2_TILED=0 / 1 forces one or the other; the phase-profile and
+    // timing-experiment switches of the kernels below select them too.
+    static int tiled = -2, num_sms_t = 0;
+    if (tiled == -2) {
+      const char* ev = getenv("BVB_K2_TILED");
+      tiled = ev ? atoi(ev) : -1;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms_t, cudaDevAttrMultiProcessorCount, dev);
+    }
+    static const bool tprof = getenv("BVB_K2T_PROF") != nullptr;   // phase profile of the tiled form's chain step
+    const bool want = tiled == 1 || (tiled == -1 && 2 * p.M <= num_sms_t && p.n >= 96);
+    if (want && (p.prof == nullptr || tprof) && p.debug_mode == 0) return launch_k2_tiled(p, s);
   }
   // Thread-block clusters when the equations leave SMs idle: csize = 8 or 4 with M * csize <= SMs.
   {

@@ -17,10 +17,13 @@ void make_pair_geom(PairGeom& g, int T, int n) {
   g.nXtiles = ((n + K1_BM - 1) / K1_BM + 5) / 6 * 6;
   g.nArows = K1_BM * (g.nZtiles + g.nXtiles);
   g.colbase.assign(n > 0 ? n : 1, 0);
-  // column c stores rows c..n at colbase[c] + row; colbase[c] even.
+  // column c stores rows c..n at colbase[c] + row; colbase[c] is a multiple of 16 doubles (128 bytes), so the 32-row
+  // segments the tiled factorisation (k2_tiled.cu) works on - rows 32 I .. 32 I + 31 of a column - are whole 128-byte
+  // lines: a line never holds entries of two tiles, which is what makes L1-cached reads of FINISHED tiles safe while
+  // other CTAs are still writing their neighbours.  (Even colbase = 16-byte aligned even rows is what K2 v1 / v2 need.)
   long start = 0;  // storage index of element (c, c)
   for (int c = 0; c < n; ++c) {
-    if (((start - c) & 1) != 0) ++start;  // make colbase = start - c even
+    while (((start - c) & 15) != 0) ++start;
     g.colbase[c] = (int)(start - c);
     start += (n + 1 - c);
   }

@@ -177,6 +177,52 @@ def cpu_baselines(prep, pp, ps, n_all=12, n_one=4):
     return cpu, cpu1
 
 
+def draw_sharded_postprocessing(h, rank, world, barrier, max_over_ranks):
+    """irf() and predict() over stored posterior draws, the draws sharded over the ranks
+    (contiguous ranges, disjoint output slices, no collective).  Shape: BASELINE configs[4] (M = 200, p = 4, Kp = 801,
+    one factor), irf(ahead = 12) over 4096 draws and predict(ahead = 1:12) over 592 draws in total whatever N is
+    (strong scaling).  Host arrays in and out (the C-ABI copies them), wall clock between barriers, max over ranks."""
+    from bayesianvars_b200 import bvar as B
+    M, p, r = 200, 4, 1
+    Kp = M * p + 1
+    out = {}
+    rng = np.random.default_rng(99)
+    base = 32
+    PHIb = np.asfortranarray(rng.standard_normal((Kp, M, base)) * 0.3 / np.sqrt(M * p))
+    flb = np.asfortranarray(rng.standard_normal((M, r, base)))
+    lvb = np.asfortranarray(rng.normal(-1.0, 0.3, (M + r, base)))
+    for name, R_total in (("irf", 4096), ("predict", 592)):
+        r0, cnt = B.shard_draws(R_total, rank, world)
+        reps = -(-max(cnt, 1) // base)
+        PHI = np.asfortranarray(np.tile(PHIb, (1, 1, reps))[:, :, :max(cnt, 1)])
+        fl = np.asfortranarray(np.tile(flb, (1, 1, reps))[:, :, :max(cnt, 1)])
+        lv = np.asfortranarray(np.tile(lvb, (1, reps))[:, :max(cnt, 1)])
+        if name == "irf":
+            run = lambda: h.irf_cpp(PHI, fl, None, lv, np.eye(r), 12)
+        else:
+            nsv = M + r
+            mu = np.full((nsv, PHI.shape[2]), -1.0); ph = np.full_like(mu, 0.9); sg = np.full_like(mu, 0.2)
+            x = np.concatenate([rng.standard_normal(M * p), [1.0]])
+            yobs = rng.standard_normal((12, M))
+            run = lambda: h.out_of_sample(1, x, PHI, None, fl, lv, np.arange(1, 13), mu, ph, sg, np.arange(nsv), True, True,
+                                          yobs, False, None, True, None, None)
+        if cnt > 0:
+            run()                      # warm-up (workspaces, kernel attributes)
+        barrier()
+        t0 = time.perf_counter()
+        res = run() if cnt > 0 else None
+        barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        dev_ms = max_over_ranks(h.last_timing()["rest_ms"] if cnt > 0 else 0.0)
+        ok = True if res is None else bool(np.isfinite(res if name == "irf" else res["predictions"]).all())
+        out[name] = dict(draws_total=R_total, draws_this_rank=cnt, wall_s=sec, draws_per_s=R_total / sec,
+                         kernel_ms_max_over_ranks=dev_ms, finite=ok)
+        del PHI, fl, lv, res
+    out["shape"] = "BASELINE configs[4]: M=200 p=4 Kp=801 r=1, irf ahead=12 / predict ahead=1:12, LPL + predictive draws"
+    out["scaling"] = "strong (total draws fixed), draws sharded in contiguous ranges, no collective"
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -311,6 +357,9 @@ def run_cuda(args):
     e2e = K / float(np.median(e2e_s))
     h2d = (prep["Y"].nbytes + prep["X"].nbytes + 3 * prep["PHI0"].nbytes + prep["startvals"]["sv_logvar"].nbytes) / K
 
+    sharded = None
+    if not args.no_draw_sharded:
+        sharded = draw_sharded_postprocessing(h, rank, world, barrier, max_over_ranks)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -361,7 +410,7 @@ def run_cuda(args):
                          note="median of 3 fresh chains, each: bvb_gibbs_init (H2D of data, priors, start values) + K sweeps, "
                               "every sweep's draw copied into caller-owned (pre-allocated) host arrays"),
                 gpu_launches=launches_per_sweep * K, roofline=roofline, cpu_baseline=cpu, cpu_baseline_1thread=cpu1,
-                vignette_anchor=anchor)
+                vignette_anchor=anchor, draw_sharded=sharded)
     if parity is not None:
         line["parity_vs_n1"] = dict(max_rel_err=parity, sweeps=PAR_SWEEPS,
                                     note="fixed-seed chain with the equations sharded over the ranks against the same chain "
@@ -376,6 +425,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-draw-sharded", action="store_true", help="skip the irf / predict draw-sharding section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -123,7 +123,12 @@ def test_huge_branch_matches_oracle(handle, M, p, T, r):
                                 d["facload"], d["fac"], True, d["z"], delta)
     out = handle.sample_PHI_factor(d["PHI0"], d["Y"], d["X"], d["logvar"], d["V"], d["facload"], d["fac"],
                                    huge=True, z=d["z"], delta=delta)
-    assert per_eq_relerr(out, ref) < TOL
+    # 1e-9 as everywhere, except where the T x T system X_norm V X_norm' + I is itself too ill-conditioned for two
+    # correct factorisations (LAPACK's dgesv there, blocked Cholesky here) to agree that closely: then 10 cond eps.
+    # (T = 530 with the heavy-tailed prior variances: cond = 3.4e6, measured difference 1.8e-9.)
+    Xn = d["X"] * np.exp(-0.5 * d["logvar"][:, :1])
+    cond = max(np.linalg.cond((Xn * d["V"][:, j]) @ Xn.T + np.eye(T)) for j in range(min(M, 3)))
+    assert per_eq_relerr(out, ref) < max(TOL, 10 * cond * np.finfo(float).eps), cond
 
 
 def test_huge_and_standard_agree_in_mean(handle):
