@@ -36,6 +36,8 @@ SIGNATURES = {
                                               C.c_int, _ip, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
     "bvb_predh": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
     "bvb_vcov": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    "bvb_insample": (C.c_int, [_vp] + [C.c_int] * 7 + [_dp] * 7),
+    "bvb_sv_latent_draw": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(C.c_ubyte)] + [C.c_double] * 4 + [_dp]),
     "bvb_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "bvb_last_timing": (C.c_int, [_vp, _dp]),
 }

@@ -187,6 +187,39 @@ class Handle:
         self._check(rc)
         return out
 
+    def insample(self, X, PHI, U, facload, logvar, prediction, factor, z=None):
+        """Same arguments as the Rcpp export (R/RcppExports.R:62); returns y_pred (T, M, nsave).
+        z (optional, parity tests): injected normals, shape (T, nsave, M)."""
+        X = np.asfortranarray(X, dtype=np.float64)
+        PHI = np.asfortranarray(PHI, dtype=np.float64)
+        T, Kp = X.shape
+        _, M, R = PHI.shape
+        factor, prediction = bool(factor), bool(prediction)
+        nf = (0 if facload is None or np.size(facload) == 0 else np.shape(facload)[1]) if factor else 0
+        F = lambda a: fptr(np.asfortranarray(a, dtype=np.float64).reshape(-1, order="F"))
+        fl = F(facload) if (prediction and nf) else None
+        uv = F(U) if (prediction and not factor and M > 1) else None
+        lv = F(logvar) if prediction else None
+        zz = fptr(np.ascontiguousarray(z, dtype=np.float64).reshape(-1)) if (z is not None and prediction) else None
+        out = np.empty((T, M, R), order="F")
+        rc = self._lib.bvb_insample(self._h, T, Kp, M, R, nf, int(factor), int(prediction), F(X), F(PHI), uv, fl, lv, zz,
+                                    fptr(out.reshape(-1, order="F")))
+        self._check(rc)
+        return out
+
+    def sv_latent_draw(self, ystar, mixind, mu, phi, sigma, h0_var=-1.0, n_rep=1):
+        """Test hook: n_rep draws of h_{0:T} | ystar, r, (mu, phi, sigma) from the series kernel's parallel state draw;
+        returns (n_rep, T+1)."""
+        import ctypes as C
+        ystar = np.ascontiguousarray(ystar, dtype=np.float64)
+        mixind = np.ascontiguousarray(mixind, dtype=np.uint8)
+        T = ystar.size
+        out = np.empty((int(n_rep), T + 1))
+        rc = self._lib.bvb_sv_latent_draw(self._h, T, int(n_rep), fptr(ystar), mixind.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                          float(mu), float(phi), float(sigma), float(h0_var), fptr(out.reshape(-1)))
+        self._check(rc)
+        return out
+
     # -- a15: out_of_sample (src/utilities_cpp.cpp:216-393) ----------------------------
     def out_of_sample(self, each, X_T_plus_1, PHI, U, facload, logvar_T, ahead, sv_mu, sv_phi, sv_sigma,
                       sv_indicator, factor, LPL, Y_obs, LPL_subset, VoI, simulate_predictive,

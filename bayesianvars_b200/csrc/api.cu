@@ -4,6 +4,7 @@
 #include "gig.cuh"
 #include "chol.cuh"
 #include "huge.cuh"
+#include "fsv.cuh"
 
 #include <string.h>
 #include <stdlib.h>
@@ -618,6 +619,38 @@ int bvb_gig(bvb_handle* h, int n, const double* lambda, int len_lambda, const do
       return fin(BVB_ERR_ARG);
     }
   }
+  return fin(BVB_OK);
+}
+
+/* Test hook for the parallel state draw of the SV series kernel (see include/bvb.h). */
+int bvb_sv_latent_draw(bvb_handle* h, int T, int n_rep, const double* ystar, const unsigned char* mixind, double mu,
+                       double phi, double sigma, double h0_var, double* out) {
+  if (!h) return BVB_ERR_ARG;
+  h->err_code = 0; h->err_step = 2; h->err_msg[0] = 0;
+  if (T < 1 || n_rep < 1 || !ystar || !mixind || !out || !(sigma > 0.0) || !(phi > -1.0 && phi < 1.0)) {
+    bvb_set_error(h, BVB_ERR_ARG, "bvb_sv_latent_draw: invalid argument");
+    return BVB_ERR_ARG;
+  }
+  for (int t = 0; t < T; ++t) if (mixind[t] > 9) { bvb_set_error(h, BVB_ERR_ARG, "bvb_sv_latent_draw: mixture indicator out of range"); return BVB_ERR_ARG; }
+  BVB_CUDA_TRY(cudaSetDevice(h->device));
+  DevBuf<double> dy, dout;
+  DevBuf<unsigned char> dr;
+  cudaStream_t s = h->stream;
+  auto fin = [&](int rc) { dy.release(); dr.release(); dout.release(); return rc; };
+  if (dy.ensure(T) || dr.ensure(T) || dout.ensure((size_t)n_rep * (T + 1))) {
+    bvb_set_error(h, BVB_ERR_CUDA, "bvb_sv_latent_draw: allocation failed");
+    return fin(BVB_ERR_CUDA);
+  }
+  cudaMemcpyAsync(dy.p, ystar, sizeof(double) * T, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dr.p, mixind, (size_t)T, cudaMemcpyHostToDevice, s);
+  cudaError_t e = launch_sv_latent_test(T, n_rep, dy.p, dr.p, mu, phi, sigma, h0_var, h->seed, dout.p, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout.p, sizeof(double) * (size_t)n_rep * (T + 1), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    bvb_set_error(h, BVB_ERR_CUDA, "bvb_sv_latent_draw: %s", cudaGetErrorString(e));
+    return fin(BVB_ERR_CUDA);
+  }
+  h->last_launches = 1;
   return fin(BVB_OK);
 }
 

@@ -32,6 +32,7 @@ struct FsvDev {
   double* Wk1 = nullptr;            // [M][Tp] weight operand of the pair-GEMM (written by the series kernel when set)
   int Tp = 0;
   int* status = nullptr;
+  int prof = 0;                     // BVB_FSV_PROF: clock64 phase profile of the series kernel (series 0)
   // configuration
   const int* hetero = nullptr;      // [M+r]
   const int* restr = nullptr;       // M x r, 1 = unrestricted
@@ -50,6 +51,9 @@ cudaError_t launch_fsv_update(const FsvDev& d, uint64_t seed, const uint32_t* sw
 cudaError_t launch_fsv_series(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s);
 cudaError_t launch_fsv_rest(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s, cudaEvent_t ng_done = nullptr);
 bool fsv_has_ng(const FsvDev& d);
+void fsv_print_profile();
+cudaError_t launch_sv_latent_test(int T, int n_rep, const double* ystar, const unsigned char* mixind, double mu, double phi, double sigma,
+                                  double h0_var, uint64_t seed, double* out, cudaStream_t s);
 cudaError_t launch_fsv_ng(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s);
 
 }  // namespace bvb

@@ -622,6 +622,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
 static void gibbs_free(bvb_handle* h) {
   if (!h->gibbs) return;
   Gibbs* G = static_cast<Gibbs*>(h->gibbs);
+  if (G->fsv.prof) fsv_print_profile();
   if (G->graph_exec) cudaGraphExecDestroy(G->graph_exec);
   for (auto& e : G->ev) if (e) cudaEventDestroy(e);
   if (G->ev_fork) cudaEventDestroy(G->ev_fork);
@@ -916,6 +917,7 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   for (int i = 0; i < 4; ++i) F.priorphi[i] = ps->sv_priorphi[chol ? i % 2 : i];
   F.facloadtol = ps->factor_facloadtol; F.ngprior = ps->factor_ngprior; F.columnwise = ps->factor_columnwise;
   F.interweaving = ps->factor_interweaving > 4 ? 4 : ps->factor_interweaving;
+  F.prof = getenv("BVB_FSV_PROF") ? 1 : 0;
   if (Kp == 0) GB_TRY(cudaMemcpyAsync(G.resid.p, G.Y.p, sizeof(double) * (size_t)T * M, cudaMemcpyDeviceToDevice, s));
   if (use_huge) {
     HugeCtx& c = G.chuge;

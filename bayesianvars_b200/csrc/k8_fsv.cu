@@ -34,6 +34,7 @@ __global__ void fsv_elem_kernel(const FsvDev d, uint64_t seed, const uint32_t* s
   const int s = (int)(idx / (d.T + 1)), t = (int)(idx % (d.T + 1));
   RngStream rng(seed, STREAM_SV_ELEM, (uint32_t)idx, sweep);
   d.eps[idx] = rng.normal();
+  d.scratch[idx] = rng.normal();   // the Box-Muller partner: the second noise vector of the parallel state draw
   if (t >= d.T) return;
   double ys;
   if (s < d.M) {
@@ -49,7 +50,11 @@ __global__ void fsv_elem_kernel(const FsvDev d, uint64_t seed, const uint32_t* s
   d.mixind[(size_t)s * d.T + t] = (unsigned char)sv_draw_indicator(ys - d.logvar[(size_t)s * d.T + t], rng.uniform());
 }
 
-constexpr int SV_THREADS = 128;
+constexpr int SV_THREADS = 512;   // one row of the T+1 = 501 state equations per thread at the headline shape
+constexpr int SV_PCR = SV_THREADS - 32;   // threads of the cyclic reduction (the last warp draws the parameter variates meanwhile)
+
+// phase profile of the series kernel (series 0, thread 0; BVB_FSV_PROF=1 prints it when the chain is released)
+__device__ long long g_fsv_prof[16];
 
 template <int N>
 __device__ __forceinline__ void block_sum(double (&v)[N], double* sh /* [N][SV_THREADS/32] */) {
@@ -74,6 +79,85 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* sh /* [N][SV_T
 // One CTA per series: the element-wise parts and the sufficient statistics use
 // all threads, only the (T+1)-step tridiagonal recursion and the scalar
 // parameter draws run on thread 0, out of shared memory.
+// "All without a loop" draw of h_{0:T} ~ N(Omega^-1 c, Omega^-1), in parallel, by the first SV_PCR threads of the CTA.
+// A factorisation of the tridiagonal precision is a (T+1)-step dependent chain (501 steps x ~70 cycles even split in two
+// from both ends: it was the bulk of the series kernel's time, and it does not shrink when series are sharded over GPUs).
+// Instead: perturb, then solve.  Omega = B'B + D with B the bidiagonal AR(1) innovation map (row 0: sqrt(B0inv)/sigma;
+// row t: (h_t - phi h_{t-1})/sigma) and D = diag(0, 1/v_1, .., 1/v_T) the mixture precisions, so
+// eta = B' xi + sqrt(D) zeta with xi ~ N(0, I_{T+1}), zeta ~ N(0, I_T) has covariance Omega and  h = Omega^-1 (c + eta)
+// has exactly the law above.  The solve is a parallel cyclic reduction: ceil(log2(T+1)) sweeps in which every row
+// eliminates its two neighbours at distance 1, 2, 4, .. (Omega is strictly diagonally dominant: no pivoting).
+// sm: 12 (T+1) doubles; rows 0..4 = od, c, lo, hh, ep (ep = xi filled by the caller); e2 = zeta (index 1..T).
+// All SV_THREADS threads call this; the threads beyond SV_PCR run `other()` during the reduction.  Result in hh (row 3).
+template <class F>
+__device__ __forceinline__ void sv_state_draw_parallel(int T, int tid, double* sm, const double* ys, const unsigned char* rr,
+                                                       const double* e2, double mu, double phi, double sigma, double h0_var,
+                                                       F other, bool prof, long long& tp) {
+  double* od = sm;
+  double* c = od + (T + 1);
+  double* lo = c + (T + 1);
+  double* hh = lo + (T + 1);
+  double* ep = hh + (T + 1);
+  const double s2inv = 1.0 / (sigma * sigma);
+  const double B0inv = (h0_var <= 0.0) ? (1.0 - phi * phi) : 1.0 / h0_var;
+  for (int t = tid; t <= T; t += SV_THREADS)
+    sv_system_row(t, T, t > 0 ? ys[t - 1] : 0.0, t > 0 ? rr[t - 1] : 0, mu, phi, s2inv, B0inv, od[t], c[t]);
+  __syncthreads();
+  const double off = -phi * s2inv;
+  const double sinv = 1.0 / sigma;
+  // PCR work arrays (double-buffered): sub-diagonal a, diagonal b (= od), super-diagonal g, rhs r
+  double* pa[2] = {lo, sm + 5 * (size_t)(T + 1)};
+  double* pb[2] = {od, sm + 6 * (size_t)(T + 1)};
+  double* pg[2] = {hh, sm + 7 * (size_t)(T + 1)};
+  double* pr_[2] = {c, sm + 8 * (size_t)(T + 1)};
+  for (int t = tid; t <= T; t += SV_THREADS) {
+    double eta;
+    if (t == 0) eta = sqrt(B0inv) * sinv * ep[0] - phi * sinv * ep[1];
+    else {
+      double p_, m_, v2;
+      sv_mix(rr[t - 1], p_, m_, v2);
+      eta = sinv * ep[t] - (t < T ? phi * sinv * ep[t + 1] : 0.0) + e2[t] * rsqrt(v2);
+    }
+    c[t] += eta;
+    lo[t] = (t > 0) ? off : 0.0;
+    hh[t] = (t < T) ? off : 0.0;
+  }
+  __syncthreads();
+  if (prof) { const long long tn = clock64(); g_fsv_prof[1] += tn - tp; tp = tn; }
+  if (tid < SV_PCR) {
+    // the diagonal travels with its reciprocal (q): one division per row and sweep
+    double* pq[2] = {sm + 10 * (size_t)(T + 1), sm + 11 * (size_t)(T + 1)};
+    for (int i = tid; i <= T; i += SV_PCR) pq[0][i] = 1.0 / od[i];
+    asm volatile("bar.sync 1, %0;" ::"n"(SV_PCR) : "memory");
+    int cur = 0;
+    for (int st = 1; st <= T; st <<= 1) {
+      const double *a0 = pa[cur], *b0 = pb[cur], *g0 = pg[cur], *r0 = pr_[cur], *q0 = pq[cur];
+      double *a1 = pa[cur ^ 1], *b1 = pb[cur ^ 1], *g1 = pg[cur ^ 1], *r1 = pr_[cur ^ 1], *q1 = pq[cur ^ 1];
+      for (int i = tid; i <= T; i += SV_PCR) {
+        const int im = i - st, ip = i + st;
+        const double ai = a0[i], gi = g0[i];
+        double bn = b0[i], rn = r0[i], an = 0.0, gn = 0.0;
+        if (im >= 0) { const double k1 = ai * q0[im]; bn -= g0[im] * k1; rn -= r0[im] * k1; an = -a0[im] * k1; }
+        if (ip <= T) { const double k2 = gi * q0[ip]; bn -= a0[ip] * k2; rn -= r0[ip] * k2; gn = -g0[ip] * k2; }
+        a1[i] = an; b1[i] = bn; g1[i] = gn; r1[i] = rn; q1[i] = 1.0 / bn;
+      }
+      cur ^= 1;
+      asm volatile("bar.sync 1, %0;" ::"n"(SV_PCR) : "memory");
+    }
+    const double *qf = pq[cur], *rf = pr_[cur];
+    double* hout = sm + 9 * (size_t)(T + 1);
+    for (int i = tid; i <= T; i += SV_PCR) hout[i] = rf[i] * qf[i];
+  } else {
+    other(tid - SV_PCR);
+  }
+  __syncthreads();
+  {
+    const double* hout = sm + 9 * (size_t)(T + 1);
+    for (int t = tid; t <= T; t += SV_THREADS) hh[t] = hout[t];
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[8 * (SV_THREADS / 32)];
@@ -82,6 +166,9 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
   const uint32_t sweep = *sweep_p;
   const int S = d.M + d.r, T = d.T, tid = threadIdx.x;
   const int s = blockIdx.x;
+  const bool prof = d.prof && s == 0 && tid == 0;
+  long long tp = prof ? clock64() : 0;
+#define SV_TICK(slot) do { if (prof) { const long long tn = clock64(); g_fsv_prof[slot] += tn - tp; tp = tn; } } while (0)
   double* h = d.logvar + (size_t)s * T;
   if (!d.hetero[s]) {
     if (s < d.M) {
@@ -107,7 +194,7 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
   double* lo = c + (T + 1);        // [T+1]
   double* hh = lo + (T + 1);       // [T+1]  hh[0] = h0
   double* ep = hh + (T + 1);       // [T+1]
-  double* ys = ep + (T + 1);       // [T]
+  double* ys = sm + 12 * (size_t)(T + 1);   // [T]   (sm + 5..11 (T+1): buffers of the cyclic reduction and its result)
   unsigned char* rr = reinterpret_cast<unsigned char*>(ys + T);  // [T]
   SvPrior pr;
   pr.mu_mean = d.priormu[0]; pr.mu_sd = d.priormu[1];
@@ -122,94 +209,29 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
   }
   for (int t = tid; t <= T; t += SV_THREADS) ep[t] = d.eps[(size_t)s * (T + 1) + t];
   __syncthreads();
-  // (a) tridiagonal system, AWOL draw
-  {
-    const double s2inv = 1.0 / (sigma * sigma);
-    const double B0inv = (pr.h0_var <= 0.0) ? (1.0 - phi * phi) : 1.0 / pr.h0_var;
-    for (int t = tid; t <= T; t += SV_THREADS)
-      sv_system_row(t, T, t > 0 ? ys[t - 1] : 0.0, t > 0 ? rr[t - 1] : 0, mu, phi, s2inv, B0inv, od[t], c[t]);
-    __syncthreads();
-    // AWOL draw with a TWISTED factorisation of the tridiagonal precision (eliminate from both ends towards the
-    // middle row m, substitute from m outwards): the same law as sv_awol's one-sided Cholesky - any factor F with
-    // F F' = Omega maps N(0, I) noise to N(0, Omega^-1) - but two threads (in different warps) each walk half of the
-    // dependent chain, which is what the kernel's time is made of (1002 steps x ~70 cycles on one thread).
-    {
-      const double off = -phi * s2inv;
-      const int m = (T + 1) / 2;                       // rows 0..m-1 from the top, T..m+1 from the bottom
-      if (tid == 0) {
-        double lprev = 0.0, aprev = 0.0;
-        double od_n = od[0], c_n = c[0];
-        for (int t = 0; t < m; ++t) {
-          const double od_t = od_n, c_t = c_n;
-          od_n = od[t + 1]; c_n = c[t + 1];
-          const double ri = rsqrt(od_t - lprev * lprev);
-          const double at = (c_t - lprev * aprev) * ri;
-          od[t] = ri; c[t] = at;
-          lprev = off * ri;
-          lo[t] = lprev;                               // couples row t with row t+1
-          aprev = at;
-        }
-      } else if (tid >= 64 && tid < 69) {
-        // Meanwhile warps 2 and 3 draw the variates of the parameter updates (they do not depend on the state): the
-        // five normals in lock step on five lanes of warp 2, the three log-uniforms and the gamma on warp 3.
-        // Disjoint counter ranges of the series' stream.
-        RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
-        gq.ctr = 16u * (uint32_t)(tid - 64 + 1);
-        const double z = gq.normal();
-        double* dst[5] = {&rvs.z1, &rvs.z2, &rvs.nz1, &rvs.nz0, &rvs.nzphi};
-        *dst[tid - 64] = z;
-      } else if (tid >= 96 && tid < 99) {
-        RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
-        gq.ctr = 16u * (uint32_t)(tid - 96 + 8);
-        const double lu = log(gq.uniform());
-        double* dst[3] = {&rvs.lu_s2, &rvs.lu_mh, &rvs.nlu};
-        *dst[tid - 96] = lu;
-      } else if (tid == 99) {
-        RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
-        gq.ctr = 4096u;
-        rvs.gam = gq.gamma(sv_gamma_shape(T, pr));
-      } else if (tid == 32) {
-        double lprev = 0.0, aprev = 0.0;
-        double od_n = od[T], c_n = c[T];
-        for (int t = T; t > m; --t) {
-          const double od_t = od_n, c_t = c_n;
-          od_n = od[t - 1]; c_n = c[t - 1];
-          const double ri = rsqrt(od_t - lprev * lprev);
-          const double at = (c_t - lprev * aprev) * ri;
-          od[t] = ri; c[t] = at;
-          lprev = off * ri;
-          lo[t] = lprev;                               // couples row t with row t-1
-          aprev = at;
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {                                  // middle row: both neighbours are eliminated
-        const double lu = (m > 0) ? lo[m - 1] : 0.0, au = (m > 0) ? c[m - 1] : 0.0;
-        const double ld = (m < T) ? lo[m + 1] : 0.0, ad = (m < T) ? c[m + 1] : 0.0;
-        const double ri = rsqrt(od[m] - lu * lu - ld * ld);
-        const double at = (c[m] - lu * au - ld * ad) * ri;
-        od[m] = ri; c[m] = at;
-        hh[m] = (at + ep[m]) * ri;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        double hnext = hh[m];
-        for (int t = m - 1; t >= 0; --t) {
-          const double ht = (c[t] + ep[t] - lo[t] * hnext) * od[t];
-          hh[t] = ht;
-          hnext = ht;
-        }
-      } else if (tid == 32) {
-        double hprev = hh[m];
-        for (int t = m + 1; t <= T; ++t) {
-          const double ht = (c[t] + ep[t] - lo[t] * hprev) * od[t];
-          hh[t] = ht;
-          hprev = ht;
-        }
-      }
+  SV_TICK(0);
+  // (a) tridiagonal system and state draw (parallel "all without a loop")
+  sv_state_draw_parallel(T, tid, sm, ys, rr, d.scratch + (size_t)s * (T + 1), mu, phi, sigma, pr.h0_var, [&](int l3) {
+    // last warp: the variates of the parameter updates (they do not depend on the state); disjoint counter ranges
+    if (l3 < 5) {
+      RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+      gq.ctr = 16u * (uint32_t)(l3 + 1);
+      const double z = gq.normal();
+      double* dst[5] = {&rvs.z1, &rvs.z2, &rvs.nz1, &rvs.nz0, &rvs.nzphi};
+      *dst[l3] = z;
+    } else if (l3 >= 8 && l3 < 11) {
+      RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+      gq.ctr = 16u * (uint32_t)(l3);
+      const double lu = log(gq.uniform());
+      double* dst[3] = {&rvs.lu_s2, &rvs.lu_mh, &rvs.nlu};
+      *dst[l3 - 8] = lu;
+    } else if (l3 == 16) {
+      RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
+      gq.ctr = 4096u;
+      rvs.gam = gq.gamma(sv_gamma_shape(T, pr));
     }
-    __syncthreads();
-  }
+  }, prof, tp);
+  SV_TICK(2);
   // (b) centered draw
   {
     double v[5] = {0, 0, 0, 0, 0};
@@ -227,12 +249,14 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       for (int t = 1 + tid; t <= T; t += SV_THREADS) { const double e = hh[t] - b0 - b1 * hh[t - 1]; rss[0] += e * e; }
     }
     block_sum<1>(rss, red);
+    SV_TICK(3);
     if (tid < 32) {   // warp 0, all lanes with identical arguments: the lanes share the terms of the MH ratio
       const SvVariates rv = rvs;
       sv_draw_centered(rv, T, cs, hh[0], mu, phi, sigma, pr, rss[0], tid);
       if (tid == 0) { bc[0] = mu; bc[1] = phi; bc[2] = sigma; }
     }
     __syncthreads();
+    SV_TICK(4);
     mu = bc[0]; phi = bc[1]; sigma = bc[2];
   }
   // (b') non-centered draw (ASIS) and transformation back
@@ -243,6 +267,7 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       sv_nc_accumulate(ns, (hh[t] - mu_c) / sg_c, (hh[t - 1] - mu_c) / sg_c, ys[t - 1], rr[t - 1]);
     double v[7] = {ns.p00, ns.p01, ns.p11, ns.l0, ns.l1, ns.n_prev2, ns.n_cross};
     block_sum<7>(v, red);
+    SV_TICK(5);
     if (tid < 32) {
       const SvVariates rv = rvs;
       SvNSums tot = {v[0], v[1], v[2], v[3], v[4], v[5], v[6]};
@@ -251,6 +276,7 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       if (tid == 0) { bc[0] = mu_n; bc[1] = sg_n; bc[2] = phi; }
     }
     __syncthreads();
+    SV_TICK(6);
     const double mu_n = bc[0], sg_n = bc[1];
     for (int t = 1 + tid; t <= T; t += SV_THREADS) {
       const double hv = mu_n + sg_n * ((hh[t] - mu_c) / sg_c);
@@ -266,6 +292,50 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
       d.sv_para[3 * s + 0] = mu_n; d.sv_para[3 * s + 1] = bc[2]; d.sv_para[3 * s + 2] = fabs(sg_n);
     }
   }
+  SV_TICK(7);
+  if (prof) g_fsv_prof[15] += 1;
+#undef SV_TICK
+}
+
+// Test hook (bvb_sv_latent_draw): n_rep independent draws of h_{0:T} | ystar, mixture indicators, (mu, phi, sigma) with
+// the series kernel's parallel state draw; replica b uses Philox element index b.  out[b*(T+1) + t].
+__global__ void __launch_bounds__(SV_THREADS) sv_latent_test_kernel(int T, const double* ystar, const unsigned char* mixind, double mu,
+                                                                    double phi, double sigma, double h0_var, uint64_t seed, double* out) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  double* ep = sm + 4 * (size_t)(T + 1);
+  double* ys = sm + 12 * (size_t)(T + 1);
+  double* e2 = ys + T;                                                  // [T+1]
+  unsigned char* rr = reinterpret_cast<unsigned char*>(e2 + T + 1);
+  for (int t = tid; t < T; t += SV_THREADS) { ys[t] = ystar[t]; rr[t] = mixind[t]; }
+  for (int t = tid; t <= T; t += SV_THREADS) {
+    RngStream rng(seed, STREAM_SV_ELEM, (uint32_t)(b * (T + 1) + t), 0u);
+    ep[t] = rng.normal();
+    e2[t] = rng.normal();
+  }
+  __syncthreads();
+  long long tp = 0;
+  sv_state_draw_parallel(T, tid, sm, ys, rr, e2, mu, phi, sigma, h0_var, [](int) {}, false, tp);
+  const double* hh = sm + 3 * (size_t)(T + 1);
+  for (int t = tid; t <= T; t += SV_THREADS) out[(size_t)b * (T + 1) + t] = hh[t];
+}
+cudaError_t launch_sv_latent_test(int T, int n_rep, const double* ystar, const unsigned char* mixind, double mu, double phi, double sigma,
+                                  double h0_var, uint64_t seed, double* out, cudaStream_t s) {
+  const size_t smem = (size_t)(12 * (T + 1) + T + T + 1) * sizeof(double) + (size_t)T + 16;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(sv_latent_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sv_latent_test_kernel<<<n_rep, SV_THREADS, smem, s>>>(T, ystar, mixind, mu, phi, sigma, h0_var, seed, out);
+  return cudaGetLastError();
+}
+
+void fsv_print_profile() {
+  long long hp[16];
+  if (cudaMemcpyFromSymbol(hp, g_fsv_prof, sizeof(hp)) != cudaSuccess) return;
+  if (hp[15] == 0) return;
+  const double n = (double)hp[15];
+  fprintf(stderr, "fsv_series_kernel (series 0, thread 0, cycles per launch over %lld launches): load %.0f system+eta %.0f cyclic-reduction %.0f "
+                  "centered sums %.0f centered draw %.0f non-centered sums %.0f non-centered draw %.0f write-back %.0f\n",
+          hp[15], hp[0] / n, hp[1] / n, hp[2] / n, hp[3] / n, hp[4] / n, hp[5] / n, hp[6] / n, hp[7] / n);
 }
 
 // Normal-gamma prior on the loadings: lambda2 then tau2 (Kastner 2019, eq. 6-7).
@@ -691,7 +761,7 @@ cudaError_t launch_fsv_series(const FsvDev& d, uint64_t seed, const uint32_t* sw
   const int S = d.M + d.r;
   const size_t nel = (size_t)(d.T + 1) * S;
   fsv_elem_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(d, seed, sweep);
-  const size_t smem = (size_t)(6 * (d.T + 1)) * sizeof(double) + (size_t)d.T + 16;
+  const size_t smem = (size_t)(12 * (d.T + 1) + d.T) * sizeof(double) + (size_t)d.T + 16;
   if (smem > 48 * 1024) cudaFuncSetAttribute(fsv_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fsv_series_kernel<<<S, SV_THREADS, smem, s>>>(d, seed, sweep);
   return cudaGetLastError();

@@ -68,21 +68,40 @@ __host__ __device__ inline int sv_draw_indicator(double resid /* y*_t - h_t */, 
   return r;
 }
 
-// Sum of n independent terms term(k), k < n.  lane < 0: one thread evaluates them in order (host, tests).
-// lane >= 0 (device): the 32 lanes of a warp call this together with IDENTICAL arguments; lane k evaluates term k and
-// the warp adds them up - the log-density terms of an MH ratio are independent chains of log / divide.
+// Sum of n independent log-density terms.  term(k) only SELECTS the data of term k (what, at which point, with which
+// parameters and sign); the arithmetic - logs, divides - is the same code for every k.  lane < 0: one thread evaluates
+// them in order (host, tests).  lane >= 0 (device): the 32 lanes of a warp call this together with IDENTICAL arguments,
+// lane k evaluates term k and the warp adds them up.  (A lambda that computed its term inside a `switch (k)` made the
+// warp run the ten branches one after the other: divergence serialised what was meant to be parallel.)
+struct SvTerm {
+  int kind;          // 0: normal log-kernel of x with mean m, sd s;  1: Beta((x+1)/2; a = m, b = s) log-kernel;  2: nothing
+  double x, m, s, sign;
+};
+__host__ __device__ inline double sv_eval_term(const SvTerm& t) {
+  if (t.kind == 2) return 0.0;
+  // both kernels are "c1 log(u1) + c2 log(u2)"-shaped; evaluate with common code: normal -> -log(s) - z^2/2
+  const bool beta = t.kind == 1;
+  const double u1 = beta ? 0.5 * (1.0 + t.x) : t.s;
+  const double u2 = beta ? 0.5 * (1.0 - t.x) : 1.0;
+  const double c1 = beta ? (t.m - 1.0) : -1.0;
+  const double c2 = beta ? (t.s - 1.0) : 0.0;
+  const double z = beta ? 0.0 : (t.x - t.m) / t.s;
+  return t.sign * (c1 * log(u1) + c2 * log(u2) - 0.5 * z * z);
+}
 template <class F>
 __host__ __device__ inline double sv_sum_terms(int n, int lane, F term) {
 #ifdef __CUDA_ARCH__
   if (lane >= 0) {
-    double v = (lane < n) ? term(lane) : 0.0;
+    SvTerm t = term(lane < n ? lane : 0);
+    if (lane >= n) t.kind = 2;
+    double v = sv_eval_term(t);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
 #endif
   double t = 0.0;
-  for (int k = 0; k < n; ++k) t += term(k);
+  for (int k = 0; k < n; ++k) t += sv_eval_term(term(k));
   return t;
 }
 
@@ -212,20 +231,21 @@ __host__ __device__ inline void sv_draw_centered(const SvVariates& rv, int T, co
       const double gam_old = mu * (1.0 - phi);
       const double mu_prop = gam_prop / (1.0 - phi_prop);
       const double mu_o = mu, phi_o = phi;
-      const double lr = sv_sum_terms(10, lane, [&](int k) -> double {
+      const double sd0p = (pr.h0_var <= 0.0) ? sg / sqrt(1.0 - phi_prop * phi_prop) : sg * sqrt(pr.h0_var);
+      const double sd0o = (pr.h0_var <= 0.0) ? sg / sqrt(1.0 - phi_o * phi_o) : sg * sqrt(pr.h0_var);
+      const double sdg = sg / sqrt(BVB_SV_B011INV), sdp = sg / sqrt(BVB_SV_B022INV);
+      const double lr = sv_sum_terms(10, lane, [&](int k) -> SvTerm {
         switch (k) {
-          case 0: return (pr.h0_var <= 0.0) ? sv_log_norm(h0, mu_prop, sg / sqrt(1.0 - phi_prop * phi_prop))
-                                            : sv_log_norm(h0, mu_prop, sg * sqrt(pr.h0_var));
-          case 1: return (pr.h0_var <= 0.0) ? -sv_log_norm(h0, mu_o, sg / sqrt(1.0 - phi_o * phi_o))
-                                            : -sv_log_norm(h0, mu_o, sg * sqrt(pr.h0_var));
-          case 2: return sv_log_norm(gam_prop, pr.mu_mean * (1.0 - phi_prop), pr.mu_sd * (1.0 - phi_prop));
-          case 3: return -sv_log_norm(gam_old, pr.mu_mean * (1.0 - phi_o), pr.mu_sd * (1.0 - phi_o));
-          case 4: return sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b);
-          case 5: return -sv_log_beta_kernel(phi_o, pr.phi_a, pr.phi_b);
-          case 6: return sv_log_norm(gam_old, 0.0, sg / sqrt(BVB_SV_B011INV));
-          case 7: return -sv_log_norm(gam_prop, 0.0, sg / sqrt(BVB_SV_B011INV));
-          case 8: return sv_log_norm(phi_o, 0.0, sg / sqrt(BVB_SV_B022INV));
-          default: return -sv_log_norm(phi_prop, 0.0, sg / sqrt(BVB_SV_B022INV));
+          case 0: return SvTerm{0, h0, mu_prop, sd0p, 1.0};
+          case 1: return SvTerm{0, h0, mu_o, sd0o, -1.0};
+          case 2: return SvTerm{0, gam_prop, pr.mu_mean * (1.0 - phi_prop), pr.mu_sd * (1.0 - phi_prop), 1.0};
+          case 3: return SvTerm{0, gam_old, pr.mu_mean * (1.0 - phi_o), pr.mu_sd * (1.0 - phi_o), -1.0};
+          case 4: return SvTerm{1, phi_prop, pr.phi_a, pr.phi_b, 1.0};
+          case 5: return SvTerm{1, phi_o, pr.phi_a, pr.phi_b, -1.0};
+          case 6: return SvTerm{0, gam_old, 0.0, sdg, 1.0};
+          case 7: return SvTerm{0, gam_prop, 0.0, sdg, -1.0};
+          case 8: return SvTerm{0, phi_o, 0.0, sdp, 1.0};
+          default: return SvTerm{0, phi_prop, 0.0, sdp, -1.0};
         }
       });
       if (rv.lu_mh < lr) { mu = mu_prop; phi = phi_prop; }
@@ -244,14 +264,17 @@ __host__ __device__ inline void sv_draw_centered(const SvVariates& rv, int T, co
     const double phi_prop = S.s_cross / den + sg / sqrt(den) * rv.z1;
     if (phi_prop > -1.0 && phi_prop < 1.0) {
       const double phi_o = phi;
-      const double lr = sv_sum_terms(6, lane, [&](int k) -> double {
+      const bool stat0 = pr.h0_var <= 0.0;
+      const double sd0p = stat0 ? sg / sqrt(1.0 - phi_prop * phi_prop) : 1.0, sd0o = stat0 ? sg / sqrt(1.0 - phi_o * phi_o) : 1.0;
+      const double sdp = sg / sqrt(BVB_SV_B022INV);
+      const double lr = sv_sum_terms(6, lane, [&](int k) -> SvTerm {
         switch (k) {
-          case 0: return (pr.h0_var <= 0.0) ? sv_log_norm(h0, 0.0, sg / sqrt(1.0 - phi_prop * phi_prop)) : 0.0;
-          case 1: return (pr.h0_var <= 0.0) ? -sv_log_norm(h0, 0.0, sg / sqrt(1.0 - phi_o * phi_o)) : 0.0;
-          case 2: return sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b);
-          case 3: return -sv_log_beta_kernel(phi_o, pr.phi_a, pr.phi_b);
-          case 4: return sv_log_norm(phi_o, 0.0, sg / sqrt(BVB_SV_B022INV));
-          default: return -sv_log_norm(phi_prop, 0.0, sg / sqrt(BVB_SV_B022INV));
+          case 0: return SvTerm{stat0 ? 0 : 2, h0, 0.0, sd0p, 1.0};
+          case 1: return SvTerm{stat0 ? 0 : 2, h0, 0.0, sd0o, -1.0};
+          case 2: return SvTerm{1, phi_prop, pr.phi_a, pr.phi_b, 1.0};
+          case 3: return SvTerm{1, phi_o, pr.phi_a, pr.phi_b, -1.0};
+          case 4: return SvTerm{0, phi_o, 0.0, sdp, 1.0};
+          default: return SvTerm{0, phi_prop, 0.0, sdp, -1.0};
         }
       });
       if (rv.lu_mh < lr) phi = phi_prop;
@@ -296,14 +319,17 @@ __host__ __device__ inline void sv_draw_noncentered(const SvVariates& rv, const 
   const double phi_prop = S.n_cross / den + rv.nzphi / sqrt(den);
   if (phi_prop > -1.0 && phi_prop < 1.0) {
     const double phi_o = phi;
-    const double lr = sv_sum_terms(6, lane, [&](int k) -> double {
+    const bool stat0 = pr.h0_var <= 0.0;
+    const double sd0p = stat0 ? 1.0 / sqrt(1.0 - phi_prop * phi_prop) : 1.0, sd0o = stat0 ? 1.0 / sqrt(1.0 - phi_o * phi_o) : 1.0;
+    const double sdp = 1.0 / sqrt(BVB_SV_B022INV);
+    const double lr = sv_sum_terms(6, lane, [&](int k) -> SvTerm {
       switch (k) {
-        case 0: return (pr.h0_var <= 0.0) ? sv_log_norm(ht0, 0.0, 1.0 / sqrt(1.0 - phi_prop * phi_prop)) : 0.0;
-        case 1: return (pr.h0_var <= 0.0) ? -sv_log_norm(ht0, 0.0, 1.0 / sqrt(1.0 - phi_o * phi_o)) : 0.0;
-        case 2: return sv_log_beta_kernel(phi_prop, pr.phi_a, pr.phi_b);
-        case 3: return -sv_log_beta_kernel(phi_o, pr.phi_a, pr.phi_b);
-        case 4: return sv_log_norm(phi_o, 0.0, 1.0 / sqrt(BVB_SV_B022INV));
-        default: return -sv_log_norm(phi_prop, 0.0, 1.0 / sqrt(BVB_SV_B022INV));
+        case 0: return SvTerm{stat0 ? 0 : 2, ht0, 0.0, sd0p, 1.0};
+        case 1: return SvTerm{stat0 ? 0 : 2, ht0, 0.0, sd0o, -1.0};
+        case 2: return SvTerm{1, phi_prop, pr.phi_a, pr.phi_b, 1.0};
+        case 3: return SvTerm{1, phi_o, pr.phi_a, pr.phi_b, -1.0};
+        case 4: return SvTerm{0, phi_o, 0.0, sdp, 1.0};
+        default: return SvTerm{0, phi_prop, 0.0, sdp, -1.0};
       }
     });
     if (rv.nlu < lr) phi = phi_prop;

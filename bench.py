@@ -110,6 +110,12 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(self.reasons), samples=len(self.samples), how="NVML in-process, timed regions only")
 
 
+def trace(msg):
+    """Stage markers on stderr (BENCH_TRACE=1): where a multi-rank run is when it is killed."""
+    if os.environ.get("BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def make_problem():
     from bayesianvars_b200 import bvar as B
     w = WORKLOAD
@@ -265,6 +271,7 @@ def run_cuda(args):
     # ---------------- N > 1: a short fixed-seed chain on ONE GPU first (rank 0), to compare the sharded chain with
     parity_ref = None
     PAR_SWEEPS = 12
+    trace("problem ready")
     if world > 1 and rank == 0:
         with Handle(local_rank, seed=4242) as h1:
             s1 = B.Sampler(h1, prep, pp, ps, draws=PAR_SWEEPS, burnin=0, thin=1, sv_keep="last")
@@ -272,6 +279,7 @@ def run_cuda(args):
             parity_ref = {k: s1.out[k].copy() for k in ("PHI", "logvar", "sv_para", "V_prior")}
             del s1
 
+    trace("one-GPU parity chain done")
     h = Handle(local_rank, seed=2024)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -281,6 +289,7 @@ def run_cuda(args):
             uid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         h._check(h._lib.bvb_comm_init(h._h, rank, world, bytes(uid.cpu().tolist())))
+    trace("communicator ready")
     peak = h.measure_fp64_peak() if rank == 0 else None
 
     def barrier():
@@ -300,7 +309,9 @@ def run_cuda(args):
         seed_keep = h.seed
         h.reseed(4242)
         sp = B.Sampler(h, prep, pp, ps, draws=PAR_SWEEPS, burnin=0, thin=1, sv_keep="last")
+        trace("sharded parity chain initialised")
         sp.run()
+        trace("sharded parity chain done")
         if rank == 0:
             parity = {}
             for k, ref in parity_ref.items():
@@ -315,8 +326,11 @@ def run_cuda(args):
     if rank == 0:
         clocks.start()
     smp = B.Sampler(h, prep, pp, ps, draws=W + 1 + REPS * K, burnin=0, thin=1, sv_keep="last")
+    trace("main chain initialised")
     smp.run(W)                        # warm-up (includes the eager first sweep + graph capture)
+    trace("warm-up done")
     phases = smp.profile_sweep()      # per-phase events of one serial sweep: OUTSIDE the timed regions
+    trace("profile sweep done")
     smp.kernel_times(reset=True)
     reps_ms = []
     for _rep in range(REPS):
@@ -329,6 +343,7 @@ def run_cuda(args):
         assert tm["sweeps"] == K
         reps_ms.append(max_over_ranks(tm["total_ms"]))
     kt = smp.kernel_times()
+    trace("timed regions done")
     clk = clocks.stop() if rank == 0 else None
     dev_ms = float(np.median(reps_ms))
     value = K / (dev_ms * 1e-3)
@@ -352,11 +367,13 @@ def run_cuda(args):
             smp2.run(256)
         barrier()
         e2e_s.append(max_over_ranks(time.perf_counter() - t0))
-        assert np.isfinite(smp2.out["PHI"]).all() and np.abs(smp2.out["PHI"][..., 0]).max() > 0
+        if rank == 0:   # (the stored draws land in rank 0's arrays only)
+            assert np.isfinite(smp2.out["PHI"]).all() and np.abs(smp2.out["PHI"][..., 0]).max() > 0
         del smp2
     e2e = K / float(np.median(e2e_s))
     h2d = (prep["Y"].nbytes + prep["X"].nbytes + 3 * prep["PHI0"].nbytes + prep["startvals"]["sv_logvar"].nbytes) / K
 
+    trace("e2e done")
     sharded = None
     if not args.no_draw_sharded:
         sharded = draw_sharded_postprocessing(h, rank, world, barrier, max_over_ranks)

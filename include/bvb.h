@@ -316,6 +316,23 @@ int bvb_predh(bvb_handle* h, int M, int R, int each, const int* ahead, int n_ahe
 int bvb_vcov(bvb_handle* h, int factor, int T, int M, int n_factors, int R, const double* facload,
              const double* logvar, const double* U, double* out);
 
+/* ---- section 8(f) rank 2: insample (src/utilities_cpp.cpp:396-433, predict_y :69-93) -----
+ * In-sample fit x_t' PHI_r for every t and stored draw r, plus - prediction != 0 - the error term z' chol_upper(Sigma_tr).
+ * X T x Kp; PHI Kp x M x R; U n_U x R (cholesky); facload M x n_factors x R (factor); logvar T x (M + n_factors | M) x R.
+ * z: NULL = counter-based device normals, otherwise the normals the reference takes from R::norm_rand, C-ordered
+ * [T][R][M] (its loop order: t outer, draw inner, :417-418).  out: T x M x R column-major (the returned cube). */
+int bvb_insample(bvb_handle* h, int T, int Kp, int M, int R, int n_factors, int factor, int prediction,
+                 const double* X, const double* PHI, const double* U, const double* facload,
+                 const double* logvar, const double* z, double* out);
+
+/* ---- test hook: the latent-state draw of the SV update ---------------------------------
+ * n_rep independent draws of h_{0:T} | ystar_{1:T}, mixture indicators r_{1:T} (0..9), mu, phi, sigma from the parallel
+ * ("perturb, then solve") form of the all-without-a-loop sampler the series kernel runs; the reference takes this step
+ * from stochvol's update_fast_sv (called at src/bvar_cpp.cpp:761-777).  h0_var <= 0: stationary prior on h_0.
+ * out: n_rep x (T+1), replica-major.  The tests compare sample mean / covariance with Omega^-1 c and Omega^-1. */
+int bvb_sv_latent_draw(bvb_handle* h, int T, int n_rep, const double* ystar, const unsigned char* mixind, double mu,
+                       double phi, double sigma, double h0_var, double* out);
+
 /* ---- diagnostics -------------------------------------------------------------
  * Measured FP64 peaks on this device (own micro-kernels, register-resident):
  * out[0] = DMMA m8n8k4 TFLOP/s, out[1] = DFMA TFLOP/s, out[2] = SM clock MHz
