@@ -693,7 +693,9 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
                      Gp->tvp_all == (tvp_keep_all ? 1 : 0) && !getenv("BVB_NO_REUSE");
   if (reuse) {
     GB_TRY(cudaStreamSynchronize(h->stream));
-    if (Gp->graph_exec) { cudaGraphExecDestroy(Gp->graph_exec); Gp->graph_exec = nullptr; }   // kernel arguments (seed, priors) change
+    // the executable sweep graph is kept: kernel arguments (seed, priors) change, the topology does not, so the first
+    // run of the new chain re-captures one sweep and patches the executable in place (cudaGraphExecUpdate)
+    Gp->graph_stale = Gp->graph_exec != nullptr;
     Gp->ready = false; Gp->k1z_valid = false; Gp->timed = false; Gp->timing_pass = false; Gp->rep = 0;
     for (auto& v : Gp->phase_ms) v = 0;
   } else {
@@ -1223,9 +1225,18 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   int ran = 0;
   // First sweep ever: eager (allocates lazily-sized workspaces, sets kernel
   // attributes), then one sweep's launches are captured into a graph.
-  if (!G.graph_exec && todo > 0) {
+  if ((!G.graph_exec || G.graph_stale) && todo > 0) {
+    const bool run_prof = getenv("BVB_INIT_PROF") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+      if (!run_prof) return;
+      auto t = std::chrono::steady_clock::now();
+      fprintf(stderr, "[bvb run ] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
+      t0 = t;
+    };
     int rc = run_eager_sweep(h, G, false);
     if (rc) return rc;
+    mark("eager first sweep");
     todo -= 1;
     ran += 1;
     cudaGraph_t graph;
@@ -1234,12 +1245,21 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     cudaError_t ce = cudaStreamEndCapture(s, &graph);
     if (rc) return rc;
     GB_TRY(ce);
+    mark("capture");
     size_t nn = 0;
     cudaGraphGetNodes(graph, nullptr, &nn);
     G.launches_per_sweep = (int)nn;
     if (const char* dot = getenv("BVB_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, 0);
-    GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
+    bool patched = false;
+    if (G.graph_exec && G.graph_stale) {
+      cudaGraphExecUpdateResultInfo info;
+      if (cudaGraphExecUpdate(G.graph_exec, graph, &info) == cudaSuccess) patched = true;
+      else { cudaGetLastError(); cudaGraphExecDestroy(G.graph_exec); G.graph_exec = nullptr; }
+    }
+    if (!patched) GB_TRY(cudaGraphInstantiate(&G.graph_exec, graph, 0));
+    G.graph_stale = false;
     cudaGraphDestroy(graph);
+    mark(patched ? "graph exec update" : "graph instantiate");
   }
   // Sub-chunks of <= 32 sweeps that store <= half a ring.  The two ring halves alternate: the D2H copy of a sub-chunk's
   // stored draws runs on the copy stream (behind an event, off the sampler stream) while the next sub-chunk fills the

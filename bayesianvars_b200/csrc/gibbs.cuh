@@ -116,6 +116,7 @@ struct Gibbs {
   int hyper_rows = 0;
   // execution
   cudaGraphExec_t graph_exec = nullptr;
+  bool graph_stale = false;   // chain recycled: re-capture and cudaGraphExecUpdate before the next replay
   bool timing_pass = false, timed = false;
   cudaEvent_t ev[9] = {};
   cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
