@@ -72,6 +72,7 @@ __device__ __forceinline__ void kt_acquire() { asm volatile("fence.acq_rel.gpu;"
 __device__ __forceinline__ void kt_st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void kt_st_relaxed(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int kt_rowstart(int I, int nbk, int n) { return I < nbk ? KT_NB * I : n; }
 __device__ __forceinline__ int kt_rowend(int I, int nbk, int n) { return I < nbk ? min(KT_NB * I + KT_NB, n) : n + 1; }
 
@@ -210,7 +211,7 @@ __device__ __forceinline__ void kt_syrk32_dispatch(double (&g)[4][2], const doub
 }
 
 struct KtCtx {
-  double *panel, *aux, *linvT, *rsbuf, *colbuf;
+  double *panel, *aux, *linvT, *dn0, *dn1, *rsbuf, *colbuf;
   int* colb;
   int* s_avail;
   int tid, lane, warp, fr, fk;
@@ -262,24 +263,29 @@ __device__ __forceinline__ void kt_sub(const KtArgs& a, const KtCtx& x, int eq, 
     acc2[nt][0] = acc2[nt][1] = acc3[nt][0] = acc3[nt][1] = 0.0;
   }
 
-  const bool profb = p.prof != nullptr && (int)blockIdx.x == a.ncrit && tid == 0;
+  const bool profb = p.prof != nullptr && eq == 0 && pa && tid == 0;   // the look-ahead tasks of equation 0
   long long tb = profb ? clock64() : 0;
 #define KB_TICK(slot) do { if (profb) { const long long tn = clock64(); p.prof[slot] += tn - tb; tb = tn; } } while (0)
   if (profb) p.prof[39] += 1;
   // ---- history: block columns b < k, consumed as they become final for row block k (the B operand) and for my rows
   int bdone = 0;
   while (bdone < k) {
-    if (tid == 0) {
+    if (warp == 0) {
+      // one request per poll: lane I reads the counter of row block I (the equation's counters share a cache line) and the
+      // warp takes the minimum over the ones this task depends on; waiting CTAs back off (hundreds of them polled the
+      // same few lines every ~50 cycles: the L2 slices holding them were saturated and every hop of the chain paid for it)
       int av;
+      unsigned ns = 32;
       for (;;) {
-        av = min(kt_ld_acquire(prog + k), k);
-        if (pa) av = min(av, kt_ld_acquire(prog + k + 1));
-        for (int I = i0; I < i1; ++I) av = min(av, kt_ld_acquire(prog + I));
+        int v = 0x7fffffff;
+        for (int I = lane; I < nrb; I += 32)
+          if (I == k || (pa && I == k + 1) || (I >= i0 && I < i1)) v = min(v, kt_ld_acquire(prog + I));
+        av = min(__reduce_min_sync(0xffffffffu, v), k);
         if (av > bdone) break;
-        __nanosleep(20);
+        __nanosleep(ns);
+        ns = min(ns * 2, 1024u);
       }
-      kt_acquire();
-      *x.s_avail = av;
+      if (lane == 0) { kt_acquire(); *x.s_avail = av; }
     }
     __syncthreads();
     const int avail = *x.s_avail;
@@ -326,7 +332,7 @@ __device__ __forceinline__ void kt_sub(const KtArgs& a, const KtCtx& x, int eq, 
   }
   KB_TICK(34);
   // ---- the inverse of the diagonal block (DIAG(eq, k))
-  if (tid == 0) { while (kt_ld_acquire(prog + k) < k + 1) __nanosleep(20); kt_acquire(); }
+  if (tid == 0) { unsigned ns = 20; while (kt_ld_acquire(prog + k) < k + 1) { __nanosleep(ns); ns = min(ns * 2, 320u); } kt_acquire(); }
   __syncthreads();
   KB_TICK(35);
   for (int idx = tid; idx < KT_NB * KT_NB; idx += KT_THREADS) linvT[(idx >> 5) * KT_LS + (idx & 31)] = __ldcg(lwsk + idx);   // row-major
@@ -362,8 +368,10 @@ __device__ __forceinline__ void kt_sub(const KtArgs& a, const KtCtx& x, int eq, 
     for (int li = lane; li < R; li += 32) dst[li] = src[li];
   }
   __syncthreads();
-  if (tid == 0)
-    for (int I = i0; I < i1; ++I) kt_st_release(prog + I, k + 1);
+  if (tid == 0) {
+    kt_acquire();                                    // one gpu-scope fence for the whole tile, then plain flags
+    for (int I = i0; I < i1; ++I) kt_st_relaxed(prog + I, k + 1);
+  }
   KB_TICK(36);
   // ---- the diagonal accumulator of my first row block (look-ahead task only): D_{k+2} = -(sum_{b < k} + this block column)
   if (pa && i0 < nbk) {
@@ -614,6 +622,295 @@ __device__ __forceinline__ void kt_chain_step(const KtArgs& a, const KtCtx& x, i
 #undef KT_TICK
 }
 
+// ================================ an equation's diagonal chain, warp-specialised ================================
+// One chain CTA walks ONE equation (the launch gives every equation its own chain CTA).  Per block column k the only
+// strictly sequential work is the 32 pivots of the diagonal block - everything else is arranged around them:
+//   warp 0  factorises the diagonal block, one column at a time, and announces every finished column on a shared-memory
+//           mbarrier; the next pivot never leaves the registers of its lane (no shared-memory round trip);
+//   warp 2  inverts the block by substitution, one column behind warp 0 (the triangular solves below, the far tiles and
+//           the back-solve all use Linv);
+//   warps 1, 3  form C = A(k+1,k) - P - L(k+1,k-1) L(k,k-1)' as soon as the far tile L(k+1,k-1) of the previous block
+//           column has arrived (operands straight from L2 into DMMA fragments), then X = C Linv' (DMMA), 16 rows each;
+//   warp 3  also polls the counters, publishes the step (one gpu-scope fence, two flags) and stages the NEXT diagonal
+//           block (original entries + accumulator D) while warps 0-2 wait for nothing but that.
+// The solved tile L(k+1,k) stays in shared memory (`aux`): it is the newest term of the next diagonal block.
+constexpr int KT_BAR_DN = 1, KT_BAR_S = 2, KT_BAR_C = 3, KT_BAR_L = 4, KT_BAR_PUB = 5;
+__device__ __forceinline__ void kt_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void kt_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, int eq, uint64_t* colbar /* [32], count 1 */, long long* sprof /* [24] shared */) {
+  const K2Params& p = a.p;
+  const int n = p.n, nbk = a.nbk, nrb = a.nrb;
+  const int tid = x.tid, lane = x.lane, warp = x.warp, fr = x.fr, fk = x.fk;
+  double* Lc = x.panel;                       // [32][KT_RS], rows 0..31: columns of the factor (+ identity padding)
+  double* cb = x.panel + 32;                  //              rows 32..63: C, the tile below before its solve
+  double* aux = x.aux;                        // [32][KT_LS]  L(k, k-1), then L(k+1, k)
+  double* lv = x.linvT;                       // [32][KT_LS]  Linv of the diagonal block, row-major
+  double* dnb[2] = {x.dn0, x.dn1};            // [32][KT_LS]  diagonal block k (even / odd k): A_kk + D_k
+  double* rsbuf = x.rsbuf;
+  const int* colb = x.colb;
+  double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
+  int* prog = a.progress + (size_t)eq * nrb;
+  int* dprog = a.dprogress + (size_t)eq * nrb;
+  int* pprog = a.pprogress + (size_t)eq * nrb;
+  const bool prof0 = p.prof != nullptr && blockIdx.x == 0 && tid == 0, prof1 = p.prof != nullptr && blockIdx.x == 0 && tid == 32;
+  const bool prof3 = p.prof != nullptr && blockIdx.x == 0 && tid == 96;
+  long long tp = (prof0 || prof1 || prof3) ? clock64() : 0;
+  // (phase cycles accumulate in shared memory - a global read-modify-write per tick cost an L2 round trip itself)
+#define KT_TICK(cond, slot) do { if (cond) { const long long tn = clock64(); sprof[slot] += tn - tp; tp = tn; } } while (0)
+
+  // diagonal block kk into dst: lower triangle of A + D, identity padding of a partial block (one warp)
+  auto load_diag = [&](int kk, double* dst) {
+    const int c0 = kk * KT_NB, w = min(KT_NB, n - c0);
+    const double* Dk = a.D + ((size_t)eq * nbk + kk) * (KT_NB * KT_NB);
+    double va[KT_NB], vd[KT_NB];
+#pragma unroll
+    for (int c = 0; c < KT_NB; ++c) {
+      const bool in = c < w && lane >= c && lane < w;
+      va[c] = in ? __ldcg(om + colb[min(c0 + c, n - 1)] + c0 + lane) : 0.0;
+      vd[c] = (in && kk >= 2) ? __ldcg(Dk + c * KT_NB + lane) : 0.0;
+    }
+    KT_TICK(prof3, 22);
+    if (prof3 && va[0] == 12345.678) sprof[23] += 1;   // (forces the first load to have landed)
+    KT_TICK(prof3, 23);
+#pragma unroll
+    for (int c = 0; c < KT_NB; ++c) dst[c * KT_LS + lane] = (c < w) ? va[c] + vd[c] : ((lane == c) ? 1.0 : 0.0);
+  };
+
+  if (warp == 3) {
+    load_diag(0, dnb[0]);
+    kt_bar_arrive(KT_BAR_DN, KT_THREADS);
+  }
+  for (int k = 0; k < nbk; ++k) {
+    const int c0 = k * KT_NB;
+    const int w = min(KT_NB, n - c0);
+    const int r_lo = kt_rowstart(k + 1, nbk, n), r_hi = kt_rowend(k + 1, nbk, n);   // the tile below: row block k+1
+    const int R = r_hi - r_lo;
+    double* dn = dnb[k & 1];
+    const uint32_t par = (uint32_t)(k & 1);   // every column barrier completes one phase per block column
+    if (warp < 3) {
+      kt_bar_sync(KT_BAR_DN, KT_THREADS);     // diagonal block staged (warp 3), L(k,k-1) in aux (warps 1 and 3, previous step)
+      KT_TICK(prof0, 0);
+      if (k > 0) {
+        // the newest block column's term: - L(k,k-1) L(k,k-1)'.  m-tiles: warp 0 -> 0 and 1, warp 1 -> 2, warp 2 -> 3
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int mt = (warp == 0) ? h : warp + 1;
+          if (warp == 0 || h == 0) {
+            double g[4][2];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) g[nt][0] = g[nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KT_NB / 4; ++ks) {
+              const double* col = aux + (4 * ks + fk) * KT_LS;
+              const double av = col[8 * mt + fr];
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                if (nt <= mt) dmma884(g[nt][0], g[nt][1], av, col[8 * nt + fr]);
+            }
+            const int r = 8 * mt + fr;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = 8 * nt + 2 * fk + e;
+                if (nt <= mt && c <= r) dn[c * KT_LS + r] -= g[nt][e];
+              }
+          }
+        }
+      }
+      kt_bar_sync(KT_BAR_S, 96);
+      KT_TICK(prof0, 2);
+    }
+    if (warp == 0) {
+      // ---- factorisation of the diagonal block: lane = row
+      int fail = 0;
+      double av[KT_NB];
+#pragma unroll
+      for (int c = 0; c < KT_NB; ++c) av[c] = (c <= lane) ? dn[c * KT_LS + lane] : 0.0;
+      double xx = __shfl_sync(0xffffffffu, av[0], 0);
+      if (!(xx > 0.0) || !isfinite(xx)) { fail = c0 + 1; xx = 1.0; }
+      double rs = rsqrt(xx);
+#pragma unroll
+      for (int c = 0; c < KT_NB; ++c) {
+        const double l = (lane >= c) ? av[c] * rs : 0.0;
+        av[c] = l;
+        Lc[c * KT_RS + lane] = l;
+        if (lane == c) rsbuf[c] = rs;
+        if (c + 1 < KT_NB) {
+          const double dpiv = fma(-l, l, av[c + 1]);          // lane c+1: its own pivot, straight from registers
+          xx = __shfl_sync(0xffffffffu, dpiv, c + 1);
+          if (!(xx > 0.0) || !isfinite(xx)) { if (fail == 0) fail = c0 + c + 2; xx = 1.0; }
+          rs = rsqrt(xx);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&colbar[c]);    // (release.cta: the column and rsbuf[c] are visible to whoever sees the phase flip)
+#pragma unroll
+        for (int c2 = c + 1; c2 < KT_NB; ++c2) av[c2] = fma(-l, Lc[c * KT_RS + c2], av[c2]);
+      }
+      KT_TICK(prof0, 3);
+#pragma unroll
+      for (int c = 0; c < KT_NB; ++c)
+        if (c < w && lane >= c && lane < w) om[colb[c0 + c] + c0 + lane] = av[c];
+      if (lane == 0 && fail) atomicCAS(&p.status[eq], 0, fail);
+      kt_bar_arrive(KT_BAR_PUB, KT_THREADS);
+      KT_TICK(prof0, 8);
+    } else if (warp == 2) {
+      // ---- inverse of the diagonal block, lane = column of Linv, one column behind the factorisation
+      double* lwsk = a.lws + ((size_t)eq * nbk + k) * (KT_NB * KT_NB);
+      double sacc[KT_NB];
+#pragma unroll
+      for (int i = 0; i < KT_NB; ++i) sacc[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KT_NB; ++kk) {
+        mbar_wait(&colbar[kk], par);
+        const double xk = (kk >= lane) ? sacc[kk] * rsbuf[kk] : 0.0;
+        sacc[kk] = xk;
+#pragma unroll
+        for (int i = kk + 1; i < KT_NB; ++i) sacc[i] = fma(-Lc[kk * KT_RS + i], xk, sacc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < KT_NB; ++i) lv[i * KT_LS + lane] = sacc[i];       // row-major Linv[i][j], lane j
+      kt_bar_arrive(KT_BAR_L, 96);
+#pragma unroll
+      for (int i = 0; i < KT_NB; ++i) lwsk[i * KT_NB + lane] = sacc[i];
+      kt_bar_arrive(KT_BAR_PUB, KT_THREADS);
+    } else {
+      // ---- warps 1 and 3: the tile below.  Warp 3 polls for the far tile of the previous block column first.
+      if (warp == 3) {
+        if (k > 0 && lane == 0) {
+          if (k >= 2) while (kt_ld_acquire(pprog + k + 1) < 1) { }
+          while (kt_ld_acquire(prog + k + 1) < k) { }
+          kt_acquire();
+        }
+        __syncwarp();
+        KT_TICK(prof3, 16);
+      } else {
+        KT_TICK(prof1, 12);
+      }
+      kt_bar_sync(KT_BAR_C, 64);
+      KT_TICK(prof1, 13);
+      const int mt0 = (warp == 1) ? 0 : 2;
+      // C = A - P - L(k+1,k-1) L(k,k-1)' for m-tiles mt0, mt0+1: every operand straight from L2 into its fragment
+      const double* Pw = a.P + ((size_t)eq * nbk + (k + 1)) * (KT_NB * KT_NB);
+      double ao[2][KT_NB / 4], co[2][4][2], po[2][4][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // every load is unconditional on a clamped (always valid) address and masked afterwards: predicated loads made
+        // the compiler split them into branchy groups with the DMMAs in between - several L2 round trips instead of one
+        const int li = 8 * (mt0 + h) + fr;
+        const int lic = r_lo + min(li, R - 1);
+        const int cprev = max(c0 - KT_NB, 0);
+#pragma unroll
+        for (int ks = 0; ks < KT_NB / 4; ++ks) ao[h][ks] = __ldcg(om + colb[cprev + 4 * ks + fk] + lic);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * nt + 2 * fk + e;
+            co[h][nt][e] = __ldcg(om + colb[min(c0 + c, n - 1)] + lic);
+            po[h][nt][e] = __ldcg(Pw + c * KT_NB + li);
+          }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool rin = 8 * (mt0 + h) + fr < R;
+#pragma unroll
+        for (int ks = 0; ks < KT_NB / 4; ++ks) ao[h][ks] = (k >= 1 && rin) ? ao[h][ks] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) po[h][nt][e] = (k >= 2) ? po[h][nt][e] : 0.0;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double g[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) g[nt][0] = g[nt][1] = 0.0;
+        if (k > 0) {
+#pragma unroll
+          for (int ks = 0; ks < KT_NB / 4; ++ks) {
+            const double* bcol = aux + (4 * ks + fk) * KT_LS;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(g[nt][0], g[nt][1], ao[h][ks], bcol[8 * nt + fr]);
+          }
+        }
+        const int li = 8 * (mt0 + h) + fr;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * nt + 2 * fk + e;
+            cb[c * KT_RS + li] = (li < R && c < w) ? co[h][nt][e] - (po[h][nt][e] + g[nt][e]) : 0.0;
+          }
+      }
+      KT_TICK(prof1, 14);
+      kt_bar_sync(KT_BAR_L, 96);              // Linv in shared memory (warp 2), every read of the old aux done
+      // X = C Linv'  (skipping the zero triangle)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int mt = mt0 + h;
+        double xt[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) xt[nt][0] = xt[nt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KT_NB / 4; ++ks) {
+          const double avv = cb[(4 * ks + fk) * KT_RS + 8 * mt + fr];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            if (4 * ks <= 8 * nt + 7) dmma884(xt[nt][0], xt[nt][1], avv, lv[(8 * nt + fr) * KT_LS + 4 * ks + fk]);
+        }
+        const int li = 8 * mt + fr;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * nt + 2 * fk + e;
+            const bool in = li < R && c < w;
+            if (in) om[colb[c0 + c] + r_lo + li] = xt[nt][e];
+            aux[c * KT_LS + li] = in ? xt[nt][e] : 0.0;      // next step's L(k+1, k)
+          }
+      }
+      KT_TICK(prof1, 15);
+      if (warp == 1) {
+        kt_bar_arrive(KT_BAR_PUB, KT_THREADS);
+      } else {
+        KT_TICK(prof3, 17);
+        kt_bar_sync(KT_BAR_PUB, KT_THREADS);    // warps 0-2 have issued every store of this step
+        if (lane == 0) {
+          kt_acquire();                         // (fence.acq_rel.gpu: one fence, then two relaxed flags)
+          kt_st_relaxed(prog + k, k + 1);
+          kt_st_relaxed(prog + k + 1, k + 1);
+        }
+        __syncwarp();
+        KT_TICK(prof3, 18);
+        if (k + 1 < nbk) {
+          if (k + 1 >= 2 && lane == 0) {
+            while (kt_ld_acquire(dprog + k + 1) < 1) { }
+            kt_acquire();
+          }
+          __syncwarp();
+          KT_TICK(prof3, 19);
+          if (prof3) {   // probe: one dependent L2 read (a word another SM wrote a while ago)
+            const long long t0 = clock64();
+            const int v = kt_ld_acquire(dprog + k + 1);
+            if (v < 0) sprof[23] += 1;
+            const long long t1 = clock64();
+            sprof[20] += t1 - t0;
+            tp = clock64();
+          }
+          load_diag(k + 1, dnb[(k + 1) & 1]);
+          KT_TICK(prof3, 21);
+          kt_bar_arrive(KT_BAR_DN, KT_THREADS);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (p.prof != nullptr && blockIdx.x == 0 && tid < 24) p.prof[tid] += sprof[tid];
+#undef KT_TICK
+}
+
 // Scheduling.  The diagonal chain of an equation - DIAG(e,0), its first sub-diagonal tile, DIAG(e,1), .. - is latency:
 // 13 sequential steps however many SMs there are.  The first `ncrit` CTAs own these chains statically (equation e
 // belongs to CTA e mod ncrit, which walks the block columns in order), so a chain step never queues behind bulk work;
@@ -625,11 +922,15 @@ __device__ __forceinline__ void kt_chain_step(const KtArgs& a, const KtCtx& x, i
 __global__ void __launch_bounds__(KT_THREADS, KT_CTAS) k2_tiled_kernel(const KtArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_task, s_avail;
+  __shared__ __align__(8) uint64_t s_colbar[KT_NB];
+  __shared__ long long s_prof[24];
   KtCtx x;
   x.panel = smem;                                        // [32][KT_RS]  panel[c][local row]
   x.aux = x.panel + KT_NB * KT_RS;                       // [32][KT_LS]  L(k, k-1) / the originals of the tile below
   x.linvT = x.aux + KT_NB * KT_LS;                       // [32][KT_LS]  Linv of the diagonal block, row-major
-  x.rsbuf = x.linvT + KT_NB * KT_LS;                     // [32]
+  x.dn0 = x.linvT + KT_NB * KT_LS;                       // [2][32][KT_LS]  diagonal-block staging of the chain (even / odd block column)
+  x.dn1 = x.dn0 + KT_NB * KT_LS;
+  x.rsbuf = x.dn1 + KT_NB * KT_LS;                       // [32]
   x.colbuf = x.rsbuf + 32;                               // [2][32]
   x.colb = reinterpret_cast<int*>(x.colbuf + 64);        // [n]
   x.s_avail = &s_avail;
@@ -641,9 +942,16 @@ __global__ void __launch_bounds__(KT_THREADS, KT_CTAS) k2_tiled_kernel(const KtA
   __syncthreads();
 
   if ((int)blockIdx.x < a.ncrit) {
-    const bool carry = p.M <= a.ncrit;   // one equation per chain CTA: the solved tile stays in shared memory between steps
-    for (int k = 0; k < a.nbk; ++k)
-      for (int e = blockIdx.x; e < p.M; e += a.ncrit) kt_chain_step(a, x, e, k, carry);
+    if (p.M <= a.ncrit) {                // one equation per chain CTA: the warp-specialised walk
+      if (tid < KT_NB) mbar_init(&s_colbar[tid], 1);
+      if (tid < 24) s_prof[tid] = 0;
+      mbar_fence_init();
+      __syncthreads();
+      kt_chain_run(a, x, blockIdx.x, s_colbar, s_prof);
+    } else {
+      for (int k = 0; k < a.nbk; ++k)
+        for (int e = blockIdx.x; e < p.M; e += a.ncrit) kt_chain_step(a, x, e, k, false);
+    }
   }
   for (;;) {
     if (tid == 0) s_task = atomicAdd(a.head, 1);
@@ -831,7 +1139,7 @@ void kt_build_tasks(std::vector<KtTask>& out, int n, int M) {
 }  // namespace
 
 size_t k2_tiled_smem_bytes(int n) {
-  return ((size_t)KT_NB * KT_RS + 2 * (size_t)KT_NB * KT_LS + 32 + 64) * sizeof(double) + (size_t)(n + 4) * sizeof(int);
+  return ((size_t)KT_NB * KT_RS + 4 * (size_t)KT_NB * KT_LS + 32 + 64) * sizeof(double) + (size_t)(n + 4) * sizeof(int);
 }
 
 // mode 0: factor + forward solve + back-solve / draw; mode 1: factor (+ forward solve) only.
@@ -857,7 +1165,8 @@ cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s) {
     e = cudaMemcpy(C.tasks, tasks.data(), tasks.size() * sizeof(KtTask), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&C.ctrl, ctrl_ints * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&C.D, D_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&C.P, D_bytes);
+    // (P is indexed by row block 2..nbk: the right-hand-side row block nbk of the LAST equation lies one tile past M*nbk)
+    if (e == cudaSuccess) e = cudaMalloc(&C.P, D_bytes + KT_NB * KT_NB * sizeof(double));
     if (e != cudaSuccess) { cudaFree(C.tasks); cudaFree(C.ctrl); cudaFree(C.D); cudaFree(C.P); return e; }
     C.ntasks = (int)tasks.size();
     C.n = p.n; C.M = p.M;
@@ -888,7 +1197,7 @@ cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s) {
   if (cap > 0 && cap < occ) occ = cap;
   const int resident = occ * num_sms[dev];
   // chain CTAs: one per equation while that leaves two thirds of the grid to the bulk queue
-  const int ncrit = std::max(1, std::min(p.M, resident / 3));
+  const int ncrit = (p.M <= resident / 2) ? p.M : std::max(1, std::min(p.M, resident / 3));
   const int grid = std::max(ncrit + 1, std::min(ncrit + C.ntasks, resident));
   KtArgs a{};
   a.ncrit = ncrit;
