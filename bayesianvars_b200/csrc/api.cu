@@ -395,9 +395,9 @@ int bvb_phi_draw_factor(bvb_handle* h, int T, int Kp, int M, int r, const double
     cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
     if (getenv("BVB_K2T_PROF")) {
-      fprintf(stderr, "K2 tiled chain CTA 0, cycles over all block columns | warp 0: wait-diag %lld syrk %lld factor %lld stores %lld | warp 1: to-barrier %lld wait-operands %lld "
+      fprintf(stderr, "K2 tiled chain CTA 0, cycles over all block columns | warp 0: wait-diag %lld syrk %lld load+first-pivot %lld factor-loop %lld stores %lld | warp 1: to-barrier %lld wait-operands %lld "
                       "loads+product %lld wait-Linv+solve+stores %lld | warp 3: poll %lld product+solve %lld wait-stores+publish %lld poll-D %lld one-L2-read %lld next-diag(stores) %lld [issue %lld first-landed %lld]\n",
-              hp[0], hp[2], hp[3], hp[8], hp[12], hp[13], hp[14], hp[15], hp[16], hp[17], hp[18], hp[19], hp[20], hp[21], hp[22], hp[23]);
+              hp[0], hp[2], hp[4], hp[3], hp[8], hp[12], hp[13], hp[14], hp[15], hp[16], hp[17], hp[18], hp[19], hp[20], hp[21], hp[22], hp[23]);
       fprintf(stderr, "K2 tiled look-ahead tasks of equation 0: %lld tasks; cycles: wait-history %lld acc %lld P+C %lld wait-Linv %lld trsm+store+publish %lld "
                       "wait-D %lld D-update %lld\n", hp[39], hp[32], hp[33], hp[34], hp[35], hp[36], hp[37], hp[38]);
     } else

@@ -1121,7 +1121,10 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     }
     static const bool tprof = getenv("BVB_K2T_PROF") != nullptr;   // phase profile of the tiled form's chain step
     const bool want = tiled == 1 || (tiled == -1 && 2 * p.M <= num_sms_t && p.n >= 96);
-    if (want && (p.prof == nullptr || tprof) && p.debug_mode == 0) return launch_k2_tiled(p, s);
+    if (want && (p.prof == nullptr || tprof) && p.debug_mode == 0) {
+      const cudaError_t te = launch_k2_tiled(p, s);
+      if (te != cudaErrorNotSupported) return te;     // (more equations than chain CTAs fit: the kernels below)
+    }
   }
   // Thread-block clusters when the equations leave SMs idle: csize = 8 or 4 with M * csize <= SMs.
   {

@@ -152,41 +152,6 @@ __device__ __forceinline__ void kt_acc_any(bool pa, double (&acc)[KT_MAXQ][4][2]
   else kt_acc<NQ, KT_DEPTH, false>(acc, acc2, acc3, om, colb, cbeg, cend, arow, brow, brow2, brow3, fk);
 }
 
-// The same product for ONE warp working alone on a 32-row tile (the chain step): all four m-tiles, k4-steps
-// [sbeg, send) of the history, FOUR steps of operands in flight in named registers (an L2 round trip is ~1000 cycles
-// under load, four steps of DMMA issue).
-#define KT_OP_LOAD(A, B, step)                                                   \
-  {                                                                              \
-    const double* col_ = om + colb[4 * (step) + fk];                             \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) A[q] = __ldcg(col_ + arow[q]); \
-    _Pragma("unroll") for (int nt = 0; nt < 4; ++nt) B[nt] = col_[brow[nt]];     \
-  }
-#define KT_OP_STEP(A, B, step_next, have_next)                                                         \
-  {                                                                                                    \
-    double ta_[4], tb_[4];                                                                             \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) ta_[q] = A[q];                                       \
-    _Pragma("unroll") for (int nt = 0; nt < 4; ++nt) tb_[nt] = B[nt];                                  \
-    if (have_next) KT_OP_LOAD(A, B, step_next)                                                         \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                      \
-      _Pragma("unroll") for (int nt = 0; nt < 4; ++nt) dmma884(acc[q][nt][0], acc[q][nt][1], ta_[q], tb_[nt]); \
-  }
-__device__ __forceinline__ void kt_acc_chain(double (&acc)[KT_MAXQ][4][2], const double* __restrict__ om, const int* colb, int sbeg,
-                                             int send, const int (&arow)[KT_MAXQ], const int (&brow)[4], int fk) {
-  double a0[4], b0[4], a1[4], b1[4], a2[4], b2[4], a3[4], b3[4];
-  if (sbeg < send) KT_OP_LOAD(a0, b0, sbeg)
-  if (sbeg + 1 < send) KT_OP_LOAD(a1, b1, sbeg + 1)
-  if (sbeg + 2 < send) KT_OP_LOAD(a2, b2, sbeg + 2)
-  if (sbeg + 3 < send) KT_OP_LOAD(a3, b3, sbeg + 3)
-  for (int s0 = sbeg; s0 < send; s0 += 4) {
-    KT_OP_STEP(a0, b0, s0 + 4, s0 + 4 < send)
-    if (s0 + 1 < send) KT_OP_STEP(a1, b1, s0 + 5, s0 + 5 < send)
-    if (s0 + 2 < send) KT_OP_STEP(a2, b2, s0 + 6, s0 + 6 < send)
-    if (s0 + 3 < send) KT_OP_STEP(a3, b3, s0 + 7, s0 + 7 < send)
-  }
-}
-#undef KT_OP_LOAD
-#undef KT_OP_STEP
-
 // G(8 rows of this warp x 8 NTC columns) = X(rows rb + 8 warp ..) X(rows rb ..)' over the 32 columns of a tile held in
 // shared memory as t[c][row] (row stride RSX); only the n-tiles at or below the diagonal (NTC = warp + 1) are formed.
 template <int NTC>
@@ -211,7 +176,7 @@ __device__ __forceinline__ void kt_syrk32_dispatch(double (&g)[4][2], const doub
 }
 
 struct KtCtx {
-  double *panel, *aux, *linvT, *dn0, *dn1, *rsbuf, *colbuf;
+  double *panel, *aux, *linvT, *dn0, *dn1, *dd0, *dd1, *lr, *rsbuf;
   int* colb;
   int* s_avail;
   int tid, lane, warp, fr, fk;
@@ -337,40 +302,46 @@ __device__ __forceinline__ void kt_sub(const KtArgs& a, const KtCtx& x, int eq, 
   KB_TICK(35);
   for (int idx = tid; idx < KT_NB * KT_NB; idx += KT_THREADS) linvT[(idx >> 5) * KT_LS + (idx & 31)] = __ldcg(lwsk + idx);   // row-major
   __syncthreads();
-  // ---- X = C Linv'  (DMMA, skipping the zero triangle); every warp works on its own rows only
-  for (int mt = warp; mt < mtiles; mt += KT_WARPS) {
-    double xt[4][2];
+  // ---- X = C Linv'  (DMMA, skipping the zero triangle); every warp works on its own rows only.  Two passes: the first
+  // row block (m-tiles 0..3, one per warp) is solved, stored straight from the fragments and PUBLISHED before the rest
+  // of the tile is touched - it is the tile the equation's diagonal chain is waiting for (7.9 k cycles from the arrival
+  // of Linv to the flag when the whole 128-row tile went out at once).
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cbl = colb[min(c0 + lane, n - 1)];
+    for (int mt = warp + (pass ? KT_WARPS : 0); mt < (pass ? mtiles : min(mtiles, KT_WARPS)); mt += KT_WARPS) {
+      double xt[4][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) xt[nt][0] = xt[nt][1] = 0.0;
+      for (int nt = 0; nt < 4; ++nt) xt[nt][0] = xt[nt][1] = 0.0;
 #pragma unroll
-    for (int ks = 0; ks < KT_NB / 4; ++ks) {
-      const double av = panel[(4 * ks + fk) * KT_RS + 8 * mt + fr];
+      for (int ks = 0; ks < KT_NB / 4; ++ks) {
+        const double av = panel[(4 * ks + fk) * KT_RS + 8 * mt + fr];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (4 * ks <= 8 * nt + 7) dmma884(xt[nt][0], xt[nt][1], av, linvT[(8 * nt + fr) * KT_LS + 4 * ks + fk]);
+        for (int nt = 0; nt < 4; ++nt) {
+          if (4 * ks <= 8 * nt + 7) dmma884(xt[nt][0], xt[nt][1], av, linvT[(8 * nt + fr) * KT_LS + 4 * ks + fk]);
+        }
       }
+      __syncwarp();
+      const int li = 8 * mt + fr;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 8 * nt + 2 * fk + e;
+          const bool in = li < R && c < w;
+          const int cbc = __shfl_sync(0xffffffffu, cbl, c);
+          if (in) om[cbc + r_lo + li] = xt[nt][e];
+          panel[c * KT_RS + li] = in ? xt[nt][e] : 0.0;       // (kept for the diagonal accumulator below)
+        }
     }
-    __syncwarp();
-    const int li = 8 * mt + fr;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = 8 * nt + 2 * fk + e;
-        panel[c * KT_RS + li] = (li < R && c < w) ? xt[nt][e] : 0.0;
-      }
-  }
-  __syncthreads();
-  // ---- store the tile
-  for (int c = warp; c < w; c += KT_WARPS) {
-    double* dst = om + colb[c0 + c] + r_lo;
-    const double* src = panel + c * KT_RS;
-    for (int li = lane; li < R; li += 32) dst[li] = src[li];
-  }
-  __syncthreads();
-  if (tid == 0) {
-    kt_acquire();                                    // one gpu-scope fence for the whole tile, then plain flags
-    for (int I = i0; I < i1; ++I) kt_st_relaxed(prog + I, k + 1);
+    __syncthreads();
+    if (tid == 0) {
+      kt_acquire();                                    // one gpu-scope fence per pass, then plain flags
+      // (a task whose rows fit the first pass - the partial last row block with the right-hand-side row - is complete now)
+      const int Ib = (pass == 0) ? i0 : i0 + 1, Ie = (pass == 0 && mtiles > KT_WARPS) ? i0 + 1 : i1;
+      for (int I = Ib; I < Ie; ++I) kt_st_relaxed(prog + I, k + 1);
+    }
+    if (pass == 0 && mtiles <= KT_WARPS) break;
   }
   KB_TICK(36);
   // ---- the diagonal accumulator of my first row block (look-ahead task only): D_{k+2} = -(sum_{b < k} + this block column)
@@ -395,233 +366,6 @@ __device__ __forceinline__ void kt_sub(const KtArgs& a, const KtCtx& x, int eq, 
 #undef KB_TICK
 }
 
-// ================================ one step of an equation's diagonal chain ================================
-// DIAG(eq, k) and the tile below it, SUB(eq, k, row block k+1), fused.  While warp 0 factorises and inverts the
-// diagonal block (a 32-step dependent chain), warps 1-3 fetch the tile's original entries and form its history product
-// (each a third of the block columns, all 32 rows); then warp 0 publishes the block and its inverse while warps 1-3 do
-// the triangular solve with Linv straight from shared memory.  The solved tile stays in shared memory (`aux`): it is the
-// newest block column's term of the NEXT diagonal block, so a CTA that walks a single equation (`carry`) never reads it
-// back.  Same arithmetic as the separate tasks except that the history of the tile is summed in three parts (fixed order).
-__device__ __forceinline__ void kt_chain_step(const KtArgs& a, const KtCtx& x, int eq, int k, bool carry) {
-  const K2Params& p = a.p;
-  const int n = p.n, nbk = a.nbk, nrb = a.nrb;
-  const int tid = x.tid, lane = x.lane, warp = x.warp, fr = x.fr, fk = x.fk;
-  double* panel = x.panel; double* aux = x.aux; double* linvT = x.linvT; double* rsbuf = x.rsbuf; double* colbuf = x.colbuf;
-  const int* colb = x.colb;
-  double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
-  int* prog = a.progress + (size_t)eq * nrb;
-  double* lwsk = a.lws + ((size_t)eq * nbk + k) * (KT_NB * KT_NB);
-  const int c0 = k * KT_NB;
-  const int w = min(KT_NB, n - c0);
-  const int r_lo = kt_rowstart(k + 1, nbk, n), r_hi = kt_rowend(k + 1, nbk, n);   // the tile below: row block k+1
-  const int R = r_hi - r_lo;
-  const bool prof0 = p.prof != nullptr && blockIdx.x == 0 && tid == 0, prof1 = p.prof != nullptr && blockIdx.x == 0 && tid == 32;
-  long long tp = (prof0 || prof1) ? clock64() : 0;
-#define KT_TICK(cond, slot) do { if (cond) { const long long tn = clock64(); p.prof[slot] += tn - tp; tp = tn; } } while (0)
-  if (k > 0) {
-    if (tid == 0) {
-      if (!carry) while (kt_ld_acquire(prog + k) < k) __nanosleep(20);   // (carry: this CTA released it itself one step ago)
-      if (k >= 2) while (kt_ld_acquire(a.dprogress + (size_t)eq * nrb + k) < 1) __nanosleep(20);
-      kt_acquire();
-    }
-    __syncthreads();
-  }
-  KT_TICK(prof0, 0);
-  {
-    // diagonal block A_kk + D_k (and L(k,k-1) unless carried over): warp w takes columns w, w+4, ..; every load of the
-    // eight columns is issued before the first use
-    const double* Dk = a.D + ((size_t)eq * nbk + k) * (KT_NB * KT_NB);
-    double va[8], vd[8], vx[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = warp + KT_WARPS * i;
-      const bool in = c < w && lane >= c && lane < w;
-      va[i] = in ? __ldcg(om + colb[min(c0 + c, n - 1)] + c0 + lane) : 0.0;
-      vd[i] = (in && k >= 2) ? __ldcg(Dk + c * KT_NB + lane) : 0.0;
-      vx[i] = (k > 0 && !carry && lane < w) ? __ldcg(om + colb[c0 - KT_NB + c] + c0 + lane) : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = warp + KT_WARPS * i;
-      panel[c * KT_RS + lane] = (c < w) ? va[i] + vd[i] : ((lane == c) ? 1.0 : 0.0);   // identity padding of a partial block
-      if (k > 0 && !carry) aux[c * KT_LS + lane] = vx[i];
-    }
-  }
-  __syncthreads();
-  KT_TICK(prof0, 1);
-  if (k > 0) {
-    // the newest block column's term: - L(k,k-1) L(k,k-1)'  (older ones arrived through D)
-    double g[4][2];
-    kt_syrk32_dispatch(g, aux, KT_LS, 0, warp, fr, fk);
-    const int r = 8 * warp + fr;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = 8 * nt + 2 * fk + e;
-        if (nt <= warp && c <= r) panel[c * KT_RS + r] -= g[nt][e];
-      }
-    __syncthreads();
-  }
-  KT_TICK(prof0, 2);
-  if (prof1) tp = clock64();
-  if (warp == 0) {
-    int fail = 0;
-    double av[KT_NB];     // row `lane` of the factor
-#pragma unroll
-    for (int c = 0; c < KT_NB; ++c) av[c] = (c <= lane) ? panel[c * KT_RS + lane] : 0.0;
-    double xx = __shfl_sync(0xffffffffu, av[0], 0);
-    if (!(xx > 0.0) || !isfinite(xx)) { if (fail == 0) fail = c0 + 1; xx = 1.0; }
-    double rs = rsqrt(xx);
-#pragma unroll
-    for (int c = 0; c < KT_NB; ++c) {
-      const double l = (lane >= c) ? av[c] * rs : 0.0;
-      av[c] = l;
-      double* cb = colbuf + (c & 1) * 32;
-      cb[lane] = l;
-      if (lane == c) rsbuf[c] = rs;
-      __syncwarp();
-      if (c + 1 < KT_NB) {
-        av[c + 1] = fma(-l, cb[c + 1], av[c + 1]);
-        xx = __shfl_sync(0xffffffffu, av[c + 1], c + 1);
-        if (!(xx > 0.0) || !isfinite(xx)) { if (fail == 0) fail = c0 + c + 2; xx = 1.0; }
-        rs = rsqrt(xx);
-      }
-#pragma unroll
-      for (int c2 = c + 2; c2 < KT_NB; ++c2) av[c2] = fma(-l, cb[c2], av[c2]);
-    }
-#pragma unroll
-    for (int c = 0; c < KT_NB; ++c) panel[c * KT_RS + lane] = av[c];
-    __syncwarp();
-    KT_TICK(prof0, 3);
-    double sacc[KT_NB];
-#pragma unroll
-    for (int i = 0; i < KT_NB; ++i) sacc[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int kk = 0; kk < KT_NB; ++kk) {
-      const double xk = (kk >= lane) ? sacc[kk] * rsbuf[kk] : 0.0;
-      sacc[kk] = xk;
-#pragma unroll
-      for (int i = kk + 1; i < KT_NB; ++i) sacc[i] = fma(-panel[kk * KT_RS + i], xk, sacc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < KT_NB; ++i) linvT[i * KT_LS + lane] = sacc[i];   // row-major Linv[i][j], lane j (conflict-free both ways)
-    if (lane == 0 && fail) atomicCAS(&p.status[eq], 0, fail);
-    KT_TICK(prof0, 4);
-  } else {
-    // ---- warps 1-3: original entries of the tile below -> aux is still needed by nobody else (the syrk above is done),
-    // but it becomes the solved tile at the end, so the originals go to panel rows 32.. of a scratch column block:
-    // panel[c][96 + li] is free (parts use rows 32 w .. 32 w + 31 for w = 1..3 -> rows 32..127; rows 0..31 the factor).
-    // They are kept in registers instead: 1024 entries over 96 threads, issued now, consumed after the history.
-    // (`aux` is free between the syrk above and the solved tile written at the end: asynchronous 8-byte copies, no registers)
-#pragma unroll
-    for (int i = 0; i < 11; ++i) {
-      const int idx = (tid - 32) + 96 * i;
-      const int c = idx >> 5, li = idx & 31;
-      if (idx < KT_NB * KT_NB && li < R && c < w) cp_async8(aux + c * KT_LS + li, om + colb[c0 + c] + r_lo + li);
-    }
-    cp_async_commit();
-    // history of the tile below: sum_{b < k} L(k+1, b) L(k, b)'
-    double pold[11];
-#pragma unroll
-    for (int i = 0; i < 11; ++i) pold[i] = 0.0;
-    double acc[KT_MAXQ][4][2];
-#pragma unroll
-    for (int q = 0; q < KT_MAXQ; ++q)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
-    if (k > 0) {
-      int arow[KT_MAXQ], brow[4];
-#pragma unroll
-      for (int q = 0; q < KT_MAXQ; ++q) arow[q] = min(r_lo + 8 * q + fr, n);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) brow[nt] = min(c0 + 8 * nt + fr, n);
-      // the old part of the history (block columns b <= k-2) arrives as P from the bulk task that owned these rows one
-      // block column ago; only the newest block column (b = k-1, a bulk tile) is formed here, a third per warp
-      if (tid == 32) {
-        if (k >= 2) while (kt_ld_acquire(a.pprogress + (size_t)eq * nrb + k + 1) < 1) __nanosleep(20);
-        while (kt_ld_acquire(prog + k + 1) < k) __nanosleep(20);
-        kt_acquire();
-      }
-      asm volatile("bar.sync 1, 96;" ::: "memory");
-      KT_TICK(prof1, 13);
-      if (k >= 2) {
-        const double* Pw = a.P + ((size_t)eq * nbk + (k + 1)) * (KT_NB * KT_NB);
-#pragma unroll
-        for (int i = 0; i < 11; ++i) {
-          const int idx = (tid - 32) + 96 * i;
-          pold[i] = (idx < KT_NB * KT_NB) ? __ldcg(Pw + idx) : 0.0;     // idx = c * 32 + li
-        }
-      }
-      {
-        const int s0 = 8 * (k - 1);
-        const int sb = s0 + (warp == 1 ? 0 : (warp == 2 ? 3 : 6)), se = s0 + (warp == 1 ? 3 : (warp == 2 ? 6 : 8));
-        kt_acc_chain(acc, om, colb, sb, se, arow, brow, fk);
-      }
-    }
-    KT_TICK(prof1, 14);
-    double* part = panel + 32 * warp;   // rows [32 warp, 32 warp + 32) of every panel column
-#pragma unroll
-    for (int q = 0; q < KT_MAXQ; ++q)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) part[(8 * nt + 2 * fk + e) * KT_RS + 8 * q + fr] = acc[q][nt][e];
-    cp_async_wait<0>();
-    asm volatile("bar.sync 1, 96;" ::: "memory");
-    // C = A - (part 1 + part 2 + part 3) -> panel rows 32..63 (each thread sums its own entries)
-#pragma unroll
-    for (int i = 0; i < 11; ++i) {
-      const int idx = (tid - 32) + 96 * i;
-      if (idx < KT_NB * KT_NB) {
-        const int c = idx >> 5, li = idx & 31;
-        double* pc = panel + c * KT_RS + li;
-        pc[32] = (li < R && c < w) ? aux[c * KT_LS + li] - (((pold[i] + pc[32]) + pc[64]) + pc[96]) : 0.0;
-      }
-    }
-  }
-  __syncthreads();     // Linv (warp 0) and C (warps 1-3) are in shared memory
-  KT_TICK(prof0, 6);
-  // the diagonal block and its inverse go out (all threads, from shared memory); they are published with the tile below
-  // after ONE fence at the end of the step
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = warp + KT_WARPS * i;
-    if (c < w && lane >= c && lane < w) om[colb[c0 + c] + c0 + lane] = panel[c * KT_RS + lane];
-    lwsk[c * KT_NB + lane] = linvT[c * KT_LS + lane];
-  }
-  {
-    // X = C Linv' : warp w takes rows 8 w .. 8 w + 7; the solved tile goes to global memory and to `aux`
-    double xt[4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) xt[nt][0] = xt[nt][1] = 0.0;
-#pragma unroll
-    for (int ks = 0; ks < KT_NB / 4; ++ks) {
-      const double avv = panel[(4 * ks + fk) * KT_RS + 32 + 8 * warp + fr];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (4 * ks <= 8 * nt + 7) dmma884(xt[nt][0], xt[nt][1], avv, linvT[(8 * nt + fr) * KT_LS + 4 * ks + fk]);
-      }
-    }
-    __syncthreads();   // every warp has read the originals in `aux` (sum) and its C rows before `aux` is overwritten
-    const int li = 8 * warp + fr;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = 8 * nt + 2 * fk + e;
-        const bool in = li < R && c < w;
-        if (in) om[colb[c0 + c] + r_lo + li] = xt[nt][e];
-        aux[c * KT_LS + li] = in ? xt[nt][e] : 0.0;      // next step's L(k+1, k) (rows beyond the block: zero)
-      }
-  }
-  __syncthreads();
-  KT_TICK(prof0, 8);
-  if (tid == 0) { kt_st_release(prog + k, k + 1); kt_st_release(prog + k + 1, k + 1); }
-  KT_TICK(prof0, 9);
-#undef KT_TICK
-}
-
 // ================================ an equation's diagonal chain, warp-specialised ================================
 // One chain CTA walks ONE equation (the launch gives every equation its own chain CTA).  Per block column k the only
 // strictly sequential work is the 32 pivots of the diagonal block - everything else is arranged around them:
@@ -638,15 +382,53 @@ constexpr int KT_BAR_DN = 1, KT_BAR_S = 2, KT_BAR_C = 3, KT_BAR_L = 4, KT_BAR_PU
 __device__ __forceinline__ void kt_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void kt_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-__device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, int eq, uint64_t* colbar /* [32], count 1 */, long long* sprof /* [24] shared */) {
+__device__ __forceinline__ void kt_ctx_init(KtCtx& x, double* smem) {
+  x.panel = smem;                                        // [32][KT_RS]  panel[c][local row]
+  x.aux = x.panel + KT_NB * KT_RS;                       // [32][KT_LS]  L(k, k-1) / the originals of the tile below
+  x.linvT = x.aux + KT_NB * KT_LS;                       // [32][KT_LS]  Linv of the diagonal block, row-major
+  x.dn0 = x.linvT + KT_NB * KT_LS;                       // [2][32][KT_LS]  diagonal-block staging of the chain (even / odd block column)
+  x.dn1 = x.dn0 + KT_NB * KT_LS;
+  x.dd0 = x.dn1 + KT_NB * KT_LS;
+  x.dd1 = x.dd0 + KT_NB * KT_LS;
+  x.lr = x.dd1 + KT_NB * KT_LS;                          // [32][KT_LS]  the chain's factor columns, relative layout
+  x.rsbuf = x.lr + KT_NB * KT_LS;                        // [32] 1/l(c,c), [32] l(c,c)
+  x.colb = reinterpret_cast<int*>(x.rsbuf + 32 + 64);    // [n]
+  x.s_avail = nullptr;
+  x.tid = threadIdx.x; x.lane = x.tid & 31; x.warp = x.tid >> 5; x.fr = x.lane >> 2; x.fk = x.lane & 3;
+}
+
+// rsqrt for the pivot chain: hardware seed (MUFU.RSQ64H) + one third-order step, 4 dependent FP64 operations; relative
+// error <= 2 ulp on the pivots of an SPD block (tools/microbench/chol32.cu: 202 instead of 281 cycles per column).
+__device__ __forceinline__ double kt_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = y * y;
+  const double e = fma(-x, t, 1.0);
+  const double pz = fma(0.375, e, 0.5);
+  const double u = y * e;
+  return fma(pz, u, y);
+}
+
+// (One instance per warp role, NOT inlined: as one function the four roles shared a register allocation at the 255 cap
+// and ptxas serialised every group of loads - consecutive loads into one register - so that staging 64 values took
+// 4.7 k cycles.  Shared-memory pointers are rebuilt from the extern array inside so they keep their address space.)
+template <int ROLE>
+__device__ __noinline__ void kt_chain_role(const KtArgs& a, int eq, uint64_t* colbar /* [32], count 1 */, long long* sprof /* [24] shared */) {
+  extern __shared__ __align__(16) double smem[];
+  KtCtx x;
+  kt_ctx_init(x, smem);
+  constexpr int warp = ROLE;
   const K2Params& p = a.p;
   const int n = p.n, nbk = a.nbk, nrb = a.nrb;
-  const int tid = x.tid, lane = x.lane, warp = x.warp, fr = x.fr, fk = x.fk;
-  double* Lc = x.panel;                       // [32][KT_RS], rows 0..31: columns of the factor (+ identity padding)
-  double* cb = x.panel + 32;                  //              rows 32..63: C, the tile below before its solve
+  const int tid = x.tid, lane = x.lane, fr = x.fr, fk = x.fk;
+  double* Lr = x.lr;                          // [32][KT_LS]  column c of the factor below its diagonal: Lr[c][i] = l(c+1+i, c)
+  double* cb = x.panel + 32;                  //              rows 32..63: originals of the tile below, then C
+  double* pb = x.panel + 64;                  //              rows 64..95: look-ahead product P
+  double* t2 = x.panel + 96;                  //              rows 96..127: L(k+1, k-1)
   double* aux = x.aux;                        // [32][KT_LS]  L(k, k-1), then L(k+1, k)
   double* lv = x.linvT;                       // [32][KT_LS]  Linv of the diagonal block, row-major
-  double* dnb[2] = {x.dn0, x.dn1};            // [32][KT_LS]  diagonal block k (even / odd k): A_kk + D_k
+  double* dnb[2] = {x.dn0, x.dn1};            // [32][KT_LS]  diagonal block k (even / odd k): original entries, then - newest term
+  double* ddb[2] = {x.dd0, x.dd1};            // [32][KT_LS]  its accumulator D_k (k >= 2)
   double* rsbuf = x.rsbuf;
   const int* colb = x.colb;
   double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
@@ -659,34 +441,36 @@ __device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, in
   // (phase cycles accumulate in shared memory - a global read-modify-write per tick cost an L2 round trip itself)
 #define KT_TICK(cond, slot) do { if (cond) { const long long tn = clock64(); sprof[slot] += tn - tp; tp = tn; } } while (0)
 
-  // diagonal block kk into dst: lower triangle of A + D, identity padding of a partial block (one warp)
-  auto load_diag = [&](int kk, double* dst) {
-    const int c0 = kk * KT_NB, w = min(KT_NB, n - c0);
+  // diagonal block kk: original entries -> dA, accumulator D -> dD, 16-byte asynchronous copies of whole 32-row column
+  // segments (no registers: register-staged loads were serialised by the allocator - consecutive loads into one
+  // register - and cost 5 k cycles per block).  Entries outside the lower triangle / the partial block are masked by
+  // the reader (warp 0).  One warp.
+  auto stage_diag = [&](int kk, double* dA, double* dD) {
+    const int c0 = kk * KT_NB;
     const double* Dk = a.D + ((size_t)eq * nbk + kk) * (KT_NB * KT_NB);
-    double va[KT_NB], vd[KT_NB];
+    const int ch = lane & 15, cl = lane >> 4;
+    int cbv[16];
 #pragma unroll
-    for (int c = 0; c < KT_NB; ++c) {
-      const bool in = c < w && lane >= c && lane < w;
-      va[c] = in ? __ldcg(om + colb[min(c0 + c, n - 1)] + c0 + lane) : 0.0;
-      vd[c] = (in && kk >= 2) ? __ldcg(Dk + c * KT_NB + lane) : 0.0;
+    for (int i = 0; i < 16; ++i) cbv[i] = colb[min(c0 + cl + 2 * i, n - 1)];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = cl + 2 * i;
+      cp_async16(dA + c * KT_LS + 2 * ch, om + cbv[i] + c0 + 2 * ch);
+      if (kk >= 2) cp_async16(dD + c * KT_LS + 2 * ch, Dk + c * KT_NB + 2 * ch);
     }
-    KT_TICK(prof3, 22);
-    if (prof3 && va[0] == 12345.678) sprof[23] += 1;   // (forces the first load to have landed)
-    KT_TICK(prof3, 23);
-#pragma unroll
-    for (int c = 0; c < KT_NB; ++c) dst[c * KT_LS + lane] = (c < w) ? va[c] + vd[c] : ((lane == c) ? 1.0 : 0.0);
+    cp_async_commit();
+    cp_async_wait<0>();
   };
 
-  if (warp == 3) {
-    load_diag(0, dnb[0]);
-    kt_bar_arrive(KT_BAR_DN, KT_THREADS);
-  }
+  if (warp == 2) stage_diag(0, dnb[0], ddb[0]);
+  if (warp == 3) kt_bar_arrive(KT_BAR_DN, KT_THREADS);
   for (int k = 0; k < nbk; ++k) {
     const int c0 = k * KT_NB;
     const int w = min(KT_NB, n - c0);
     const int r_lo = kt_rowstart(k + 1, nbk, n), r_hi = kt_rowend(k + 1, nbk, n);   // the tile below: row block k+1
     const int R = r_hi - r_lo;
-    double* dn = dnb[k & 1];
+    double* dn = x.dn0 + (k & 1) * (KT_NB * KT_LS);          // (dn0 / dn1 and dd0 / dd1 are adjacent)
+    const double* dd = x.dd0 + (k & 1) * (KT_NB * KT_LS);
     const uint32_t par = (uint32_t)(k & 1);   // every column barrier completes one phase per block column
     if (warp < 3) {
       kt_bar_sync(KT_BAR_DN, KT_THREADS);     // diagonal block staged (warp 3), L(k,k-1) in aux (warps 1 and 3, previous step)
@@ -723,58 +507,115 @@ __device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, in
       KT_TICK(prof0, 2);
     }
     if (warp == 0) {
-      // ---- factorisation of the diagonal block: lane = row
+      // ---- factorisation of the diagonal block: lane = row.  ONE rolled loop over the columns: the register window slides
+      // one entry per column (wv[i] = a(lane, c + i)), so every register index is static inside a loop body of ~100
+      // instructions.  (The fully unrolled form is 2 700 instructions of straight-line code per warp role; with four
+      // warp roles and the far-tile code streaming different instruction regions through one SM's instruction cache it
+      // ran at HALF the speed it has alone - tools/microbench/icache_multi.cu.)  Column c of the factor goes to shared
+      // memory RELATIVE to the diagonal (Lr[c][i] = l(c+1+i, c)): the loop reads 16 aligned LDS.128 whatever c is.
       int fail = 0;
-      double av[KT_NB];
-#pragma unroll
-      for (int c = 0; c < KT_NB; ++c) av[c] = (c <= lane) ? dn[c * KT_LS + lane] : 0.0;
-      double xx = __shfl_sync(0xffffffffu, av[0], 0);
-      if (!(xx > 0.0) || !isfinite(xx)) { fail = c0 + 1; xx = 1.0; }
-      double rs = rsqrt(xx);
+      double wv[KT_NB];
 #pragma unroll
       for (int c = 0; c < KT_NB; ++c) {
-        const double l = (lane >= c) ? av[c] * rs : 0.0;
-        av[c] = l;
-        Lc[c * KT_RS + lane] = l;
-        if (lane == c) rsbuf[c] = rs;
-        if (c + 1 < KT_NB) {
-          const double dpiv = fma(-l, l, av[c + 1]);          // lane c+1: its own pivot, straight from registers
-          xx = __shfl_sync(0xffffffffu, dpiv, c + 1);
-          if (!(xx > 0.0) || !isfinite(xx)) { if (fail == 0) fail = c0 + c + 2; xx = 1.0; }
-          rs = rsqrt(xx);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&colbar[c]);    // (release.cta: the column and rsbuf[c] are visible to whoever sees the phase flip)
+        // (unconditional loads, masks applied afterwards: a load inside a conditional expression became a branch per
+        // element, and through a pointer picked from an array it was a GENERIC load - 4.7 k cycles for these 64 values)
+        const double raw = dn[c * KT_LS + lane], dvr = dd[c * KT_LS + lane];
+        const double dv = (k >= 2) ? dvr : 0.0;
+        wv[c] = (c <= lane) ? ((c < w && lane < w) ? raw + dv : ((lane == c) ? 1.0 : 0.0)) : 0.0;   // identity padding
+      }
+      // Software-pipelined over the columns: body c applies column c (rank-1 update of the window) and, as soon as the
+      // first updated entry exists, runs the pivot chain of column c+1 (shuffle -> rsqrt -> scale -> store) - the other
+      // 29 DFMAs of the update issue in the shadow of that chain's latency (tools/microbench/chol32_rolled.cu: chain
+      // 124 cycles, update 180 when they run one after the other).
+      double xx = __shfl_sync(0xffffffffu, wv[0], 0);
+      bool ok = (xx > 0.0) && (xx < 1.7e308);
+      fail = ok ? 0 : c0 + 1;
+      double rs = kt_rsqrt(ok ? xx : 1.0);
+      double l = wv[0] * rs;                                   // column 0 (every lane >= 0)
+      if (lane > 0) Lr[lane - 1] = l;
+      if (lane == 0) { rsbuf[0] = rs; rsbuf[KT_NB] = l; }        // (rsbuf[32 + c] = l(c, c))
+      const double l00 = l;
+      __syncwarp();
+      KT_TICK(prof0, 4);
+#pragma unroll 1
+      for (int c = 0; c < KT_NB - 1; ++c) {
+        const double2* lcol = reinterpret_cast<const double2*>(Lr + c * KT_LS);
+        double tl[KT_NB];
 #pragma unroll
-        for (int c2 = c + 1; c2 < KT_NB; ++c2) av[c2] = fma(-l, Lc[c * KT_RS + c2], av[c2]);
+        for (int i = 0; i < KT_NB / 2; ++i) { const double2 v = lcol[i]; tl[2 * i] = v.x; tl[2 * i + 1] = v.y; }
+        const double n0 = fma(-l, tl[0], wv[1]);               // a(lane, c+1), final
+        const double n1 = fma(-l, tl[1], wv[2]);
+        // column c+1: pivot = n0 of lane c+1
+        xx = __shfl_sync(0xffffffffu, n0, c + 1);
+        ok = (xx > 0.0) && (xx < 1.7e308);
+        fail = (!ok && fail == 0) ? c0 + c + 2 : fail;
+        rs = kt_rsqrt(ok ? xx : 1.0);
+        const double ln = (lane > c) ? n0 * rs : 0.0;          // (lane >= c + 1)
+        if (lane > c + 1) Lr[(c + 1) * KT_LS + (lane - c - 2)] = ln;
+        if (lane == c + 1) { rsbuf[c + 1] = rs; rsbuf[KT_NB + c + 1] = ln; }
+        // the rest of column c's update
+#pragma unroll
+        for (int i = 2; i < KT_NB - 1; ++i) wv[i] = fma(-l, tl[i], wv[i + 1]);
+        wv[KT_NB - 1] = 0.0;
+        wv[0] = n0; wv[1] = n1;
+        l = ln;
+        __syncwarp();
+        // hand-off to the inverting warp: columns 0 .. c+1 and their rsbuf entries are in shared memory
+        if (((c + 1) & 7) == 7 && lane == 0) mbar_arrive(&colbar[(c + 1) >> 3]);   // (release.cta)
       }
       KT_TICK(prof0, 3);
+      // L(k,k) out to global memory (off the pivot chain: only the publication of the step waits for it).  Lane r holds
+      // nothing of the finished columns any more, so they are read back: l(r, c) = Lr[c][r-c-1], l(c, c) = rsbuf[32 + c].
+      {
+        const int cbl = colb[min(c0 + lane, n - 1)];
+        double vv[KT_NB];
 #pragma unroll
-      for (int c = 0; c < KT_NB; ++c)
-        if (c < w && lane >= c && lane < w) om[colb[c0 + c] + c0 + lane] = av[c];
+        for (int c = 1; c < KT_NB; ++c) {
+          const double dg = rsbuf[KT_NB + c], od = Lr[c * KT_LS + max(lane - c - 1, 0)];
+          vv[c] = (lane == c) ? dg : od;
+        }
+        vv[0] = l00;
+#pragma unroll
+        for (int c = 0; c < KT_NB; ++c) {
+          const int cbc = __shfl_sync(0xffffffffu, cbl, c);
+          if (c < w && lane >= c && lane < w) om[cbc + c0 + lane] = vv[c];
+        }
+      }
       if (lane == 0 && fail) atomicCAS(&p.status[eq], 0, fail);
       kt_bar_arrive(KT_BAR_PUB, KT_THREADS);
       KT_TICK(prof0, 8);
     } else if (warp == 2) {
       // ---- inverse of the diagonal block, lane = column of Linv, one column behind the factorisation
       double* lwsk = a.lws + ((size_t)eq * nbk + k) * (KT_NB * KT_NB);
-      double sacc[KT_NB];
+      // rolled like the factorisation: sv[j] = entry (kk + j, lane) of the running inverse; row kk is final at step kk
+      double sv[KT_NB];
 #pragma unroll
-      for (int i = 0; i < KT_NB; ++i) sacc[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
+      for (int i = 0; i < KT_NB; ++i) sv[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll 1
       for (int kk = 0; kk < KT_NB; ++kk) {
-        mbar_wait(&colbar[kk], par);
-        const double xk = (kk >= lane) ? sacc[kk] * rsbuf[kk] : 0.0;
-        sacc[kk] = xk;
+        if ((kk & 7) == 0) mbar_wait(&colbar[kk >> 3], par);
+        const double xk = (kk >= lane) ? sv[0] * rsbuf[kk] : 0.0;
+        lv[kk * KT_LS + lane] = xk;                  // row-major Linv[kk][j], lane j
+        lwsk[kk * KT_NB + lane] = xk;
+        const double2* lcol = reinterpret_cast<const double2*>(Lr + kk * KT_LS);
+        double tl[KT_NB];
 #pragma unroll
-        for (int i = kk + 1; i < KT_NB; ++i) sacc[i] = fma(-Lc[kk * KT_RS + i], xk, sacc[i]);
+        for (int i = 0; i < KT_NB / 2; ++i) { const double2 v = lcol[i]; tl[2 * i] = v.x; tl[2 * i + 1] = v.y; }
+#pragma unroll
+        for (int i = 0; i < KT_NB - 1; ++i) sv[i] = fma(-tl[i], xk, sv[i + 1]);
+        sv[KT_NB - 1] = 0.0;
       }
-#pragma unroll
-      for (int i = 0; i < KT_NB; ++i) lv[i * KT_LS + lane] = sacc[i];       // row-major Linv[i][j], lane j
       kt_bar_arrive(KT_BAR_L, 96);
-#pragma unroll
-      for (int i = 0; i < KT_NB; ++i) lwsk[i * KT_NB + lane] = sacc[i];
       kt_bar_arrive(KT_BAR_PUB, KT_THREADS);
+      // the next diagonal block (its accumulator D_{k+1} was published by the look-ahead task of block column k-1)
+      if (k + 1 < nbk) {
+        if (k + 1 >= 2 && lane == 0) {
+          while (kt_ld_acquire(dprog + k + 1) < 1) { }
+          kt_acquire();
+        }
+        __syncwarp();
+        stage_diag(k + 1, dnb[(k + 1) & 1], ddb[(k + 1) & 1]);
+      }
     } else {
       // ---- warps 1 and 3: the tile below.  Warp 3 polls for the far tile of the previous block column first.
       if (warp == 3) {
@@ -791,57 +632,66 @@ __device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, in
       kt_bar_sync(KT_BAR_C, 64);
       KT_TICK(prof1, 13);
       const int mt0 = (warp == 1) ? 0 : 2;
-      // C = A - P - L(k+1,k-1) L(k,k-1)' for m-tiles mt0, mt0+1: every operand straight from L2 into its fragment
-      const double* Pw = a.P + ((size_t)eq * nbk + (k + 1)) * (KT_NB * KT_NB);
-      double ao[2][KT_NB / 4], co[2][4][2], po[2][4][2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        // every load is unconditional on a clamped (always valid) address and masked afterwards: predicated loads made
-        // the compiler split them into branchy groups with the DMMAs in between - several L2 round trips instead of one
-        const int li = 8 * (mt0 + h) + fr;
-        const int lic = r_lo + min(li, R - 1);
+      const int cbk = colb[min(c0 + lane, n - 1)];   // column offsets of this block, handed round by shuffle (stores below)
+      // operands of C = A - P - L(k+1,k-1) L(k,k-1)': the tile's original entries -> cb, P -> pb, L(k+1,k-1) -> t2, by
+      // asynchronous copies of warps 1 and 3 (16-byte column segments for a full row block; the partial last row block
+      // and the right-hand-side row go entry by entry)
+      {
+        const double* Pw = a.P + ((size_t)eq * nbk + (k + 1)) * (KT_NB * KT_NB);
+        const int t64 = lane + (warp == 1 ? 0 : 32);
         const int cprev = max(c0 - KT_NB, 0);
+        if (R == KT_NB) {
+          const int ch = t64 & 15, cl = t64 >> 4;
+          int cbc[8], cbq[8];
 #pragma unroll
-        for (int ks = 0; ks < KT_NB / 4; ++ks) ao[h][ks] = __ldcg(om + colb[cprev + 4 * ks + fk] + lic);
+          for (int i = 0; i < 8; ++i) { cbc[i] = colb[min(c0 + cl + 4 * i, n - 1)]; cbq[i] = colb[cprev + cl + 4 * i]; }
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 8 * nt + 2 * fk + e;
-            co[h][nt][e] = __ldcg(om + colb[min(c0 + c, n - 1)] + lic);
-            po[h][nt][e] = __ldcg(Pw + c * KT_NB + li);
+          for (int i = 0; i < 8; ++i) {
+            const int c = cl + 4 * i;
+            cp_async16(cb + c * KT_RS + 2 * ch, om + cbc[i] + r_lo + 2 * ch);
+            if (k >= 2) cp_async16(pb + c * KT_RS + 2 * ch, Pw + c * KT_NB + 2 * ch);
+            if (k >= 1) cp_async16(t2 + c * KT_RS + 2 * ch, om + cbq[i] + r_lo + 2 * ch);
           }
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int idx = t64 + 64 * i, c = idx >> 5, li = idx & 31;
+            if (li < R && c < w) cp_async8(cb + c * KT_RS + li, om + colb[c0 + c] + r_lo + li);
+            else cb[c * KT_RS + li] = 0.0;
+            if (k >= 2 && li < R) cp_async8(pb + c * KT_RS + li, Pw + idx);
+            else pb[c * KT_RS + li] = 0.0;
+            if (k >= 1 && li < R) cp_async8(t2 + c * KT_RS + li, om + colb[cprev + c] + r_lo + li);
+            else t2[c * KT_RS + li] = 0.0;
+          }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        kt_bar_sync(KT_BAR_C, 64);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const bool rin = 8 * (mt0 + h) + fr < R;
-#pragma unroll
-        for (int ks = 0; ks < KT_NB / 4; ++ks) ao[h][ks] = (k >= 1 && rin) ? ao[h][ks] : 0.0;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) po[h][nt][e] = (k >= 2) ? po[h][nt][e] : 0.0;
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        const int mt = mt0 + h;
         double g[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) g[nt][0] = g[nt][1] = 0.0;
         if (k > 0) {
 #pragma unroll
           for (int ks = 0; ks < KT_NB / 4; ++ks) {
+            const double av = t2[(4 * ks + fk) * KT_RS + 8 * mt + fr];
             const double* bcol = aux + (4 * ks + fk) * KT_LS;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(g[nt][0], g[nt][1], ao[h][ks], bcol[8 * nt + fr]);
+            for (int nt = 0; nt < 4; ++nt) dmma884(g[nt][0], g[nt][1], av, bcol[8 * nt + fr]);
           }
         }
-        const int li = 8 * (mt0 + h) + fr;
+        const int li = 8 * mt + fr;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int c = 8 * nt + 2 * fk + e;
-            cb[c * KT_RS + li] = (li < R && c < w) ? co[h][nt][e] - (po[h][nt][e] + g[nt][e]) : 0.0;
+            double* pc = cb + c * KT_RS + li;
+            const double pv = (k >= 2) ? pb[c * KT_RS + li] : 0.0;
+            *pc = (li < R && c < w) ? *pc - (pv + g[nt][e]) : 0.0;
           }
       }
       KT_TICK(prof1, 14);
@@ -867,7 +717,8 @@ __device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, in
           for (int e = 0; e < 2; ++e) {
             const int c = 8 * nt + 2 * fk + e;
             const bool in = li < R && c < w;
-            if (in) om[colb[c0 + c] + r_lo + li] = xt[nt][e];
+            const int cbc = __shfl_sync(0xffffffffu, cbk, c);
+            if (in) om[cbc + r_lo + li] = xt[nt][e];
             aux[c * KT_LS + li] = in ? xt[nt][e] : 0.0;      // next step's L(k+1, k)
           }
       }
@@ -875,6 +726,7 @@ __device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, in
       if (warp == 1) {
         kt_bar_arrive(KT_BAR_PUB, KT_THREADS);
       } else {
+        if (k + 1 < nbk) kt_bar_arrive(KT_BAR_DN, KT_THREADS);   // aux is complete: the next block column may start
         KT_TICK(prof3, 17);
         kt_bar_sync(KT_BAR_PUB, KT_THREADS);    // warps 0-2 have issued every store of this step
         if (lane == 0) {
@@ -884,31 +736,21 @@ __device__ __forceinline__ void kt_chain_run(const KtArgs& a, const KtCtx& x, in
         }
         __syncwarp();
         KT_TICK(prof3, 18);
-        if (k + 1 < nbk) {
-          if (k + 1 >= 2 && lane == 0) {
-            while (kt_ld_acquire(dprog + k + 1) < 1) { }
-            kt_acquire();
-          }
-          __syncwarp();
-          KT_TICK(prof3, 19);
-          if (prof3) {   // probe: one dependent L2 read (a word another SM wrote a while ago)
-            const long long t0 = clock64();
-            const int v = kt_ld_acquire(dprog + k + 1);
-            if (v < 0) sprof[23] += 1;
-            const long long t1 = clock64();
-            sprof[20] += t1 - t0;
-            tp = clock64();
-          }
-          load_diag(k + 1, dnb[(k + 1) & 1]);
-          KT_TICK(prof3, 21);
-          kt_bar_arrive(KT_BAR_DN, KT_THREADS);
-        }
       }
     }
   }
   __syncthreads();
   if (p.prof != nullptr && blockIdx.x == 0 && tid < 24) p.prof[tid] += sprof[tid];
 #undef KT_TICK
+}
+
+__device__ __forceinline__ void kt_chain_run(const KtArgs& a, int warp, int eq, uint64_t* colbar, long long* sprof) {
+  switch (warp) {
+    case 0: kt_chain_role<0>(a, eq, colbar, sprof); break;
+    case 1: kt_chain_role<1>(a, eq, colbar, sprof); break;
+    case 2: kt_chain_role<2>(a, eq, colbar, sprof); break;
+    default: kt_chain_role<3>(a, eq, colbar, sprof); break;
+  }
 }
 
 // Scheduling.  The diagonal chain of an equation - DIAG(e,0), its first sub-diagonal tile, DIAG(e,1), .. - is latency:
@@ -925,14 +767,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_CTAS) k2_tiled_kernel(const KtA
   __shared__ __align__(8) uint64_t s_colbar[KT_NB];
   __shared__ long long s_prof[24];
   KtCtx x;
-  x.panel = smem;                                        // [32][KT_RS]  panel[c][local row]
-  x.aux = x.panel + KT_NB * KT_RS;                       // [32][KT_LS]  L(k, k-1) / the originals of the tile below
-  x.linvT = x.aux + KT_NB * KT_LS;                       // [32][KT_LS]  Linv of the diagonal block, row-major
-  x.dn0 = x.linvT + KT_NB * KT_LS;                       // [2][32][KT_LS]  diagonal-block staging of the chain (even / odd block column)
-  x.dn1 = x.dn0 + KT_NB * KT_LS;
-  x.rsbuf = x.dn1 + KT_NB * KT_LS;                       // [32]
-  x.colbuf = x.rsbuf + 32;                               // [2][32]
-  x.colb = reinterpret_cast<int*>(x.colbuf + 64);        // [n]
+  kt_ctx_init(x, smem);
   x.s_avail = &s_avail;
   x.tid = threadIdx.x; x.lane = x.tid & 31; x.warp = x.tid >> 5; x.fr = x.lane >> 2; x.fk = x.lane & 3;
   const K2Params& p = a.p;
@@ -942,16 +777,13 @@ __global__ void __launch_bounds__(KT_THREADS, KT_CTAS) k2_tiled_kernel(const KtA
   __syncthreads();
 
   if ((int)blockIdx.x < a.ncrit) {
-    if (p.M <= a.ncrit) {                // one equation per chain CTA: the warp-specialised walk
-      if (tid < KT_NB) mbar_init(&s_colbar[tid], 1);
-      if (tid < 24) s_prof[tid] = 0;
-      mbar_fence_init();
-      __syncthreads();
-      kt_chain_run(a, x, blockIdx.x, s_colbar, s_prof);
-    } else {
-      for (int k = 0; k < a.nbk; ++k)
-        for (int e = blockIdx.x; e < p.M; e += a.ncrit) kt_chain_step(a, x, e, k, false);
-    }
+    // one equation per chain CTA (the launch guarantees ncrit == M)
+    if (tid < KT_NB) mbar_init(&s_colbar[tid], 1);
+    if (tid < 24) s_prof[tid] = 0;
+    for (int i = tid; i < KT_NB * KT_LS; i += KT_THREADS) x.lr[i] = 0.0;   // (entries past a column's end are read, never used)
+    mbar_fence_init();
+    __syncthreads();
+    kt_chain_run(a, x.warp, blockIdx.x, s_colbar, s_prof);
   }
   for (;;) {
     if (tid == 0) s_task = atomicAdd(a.head, 1);
@@ -1139,7 +971,7 @@ void kt_build_tasks(std::vector<KtTask>& out, int n, int M) {
 }  // namespace
 
 size_t k2_tiled_smem_bytes(int n) {
-  return ((size_t)KT_NB * KT_RS + 4 * (size_t)KT_NB * KT_LS + 32 + 64) * sizeof(double) + (size_t)(n + 4) * sizeof(int);
+  return ((size_t)KT_NB * KT_RS + 7 * (size_t)KT_NB * KT_LS + 32 + 64) * sizeof(double) + (size_t)(n + 4) * sizeof(int);
 }
 
 // mode 0: factor + forward solve + back-solve / draw; mode 1: factor (+ forward solve) only.
@@ -1197,7 +1029,8 @@ cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s) {
   if (cap > 0 && cap < occ) occ = cap;
   const int resident = occ * num_sms[dev];
   // chain CTAs: one per equation while that leaves two thirds of the grid to the bulk queue
-  const int ncrit = (p.M <= resident / 2) ? p.M : std::max(1, std::min(p.M, resident / 3));
+  if (2 * p.M > resident) return cudaErrorNotSupported;   // every equation needs its own chain CTA next to at least as many far-tile CTAs
+  const int ncrit = p.M;
   const int grid = std::max(ncrit + 1, std::min(ncrit + C.ntasks, resident));
   KtArgs a{};
   a.ncrit = ncrit;

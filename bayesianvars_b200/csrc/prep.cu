@@ -27,7 +27,7 @@ void make_pair_geom(PairGeom& g, int T, int n) {
     g.colbase[c] = (int)(start - c);
     start += (n + 1 - c);
   }
-  g.ldo = ((start + 2 + 15) / 16) * 16;  // slack for the 16-byte over-read, 128-byte rows
+  g.ldo = ((start + 32 + 15) / 16) * 16;  // slack: K2's copies read whole 32-row segments of the last columns; 128-byte rows
   g.lut.assign(g.nArows, make_int2(-1, -1));
   g.pairs.assign(g.nArows, make_int2(-1, -1));
   int row = 0;
