@@ -1049,29 +1049,55 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
   // ---- back-solve  L^T phi = y + z ------------------------------------------------
   for (int i = tid; i < n; i += NTHREADS) ysol[i] += p.z[(size_t)eq * p.ldz + i];
   __syncthreads();
+  // Every load of a block column is in flight before the first use (<= 12 values per lane and column at n <= 407;
+  // the rolled form took one L2 round trip per four rows), and warp 0 fetches Linv_k before the dot products instead
+  // of after the barrier behind them: 5 k -> 2 k cycles per block column.
   for (int k = nbk - 1; k >= 0; --k) {
     const int c0 = k * K2_NB;
     const int w = min(K2_NB, n - c0);
-    const int kb_end = c0 + w;
-    for (int c = warp; c < K2_NB; c += NWARPS) {
-      double s = 0.0;
-      if (c < w) {
-        const double* colp = om + colb[c0 + c];
-        for (int i = kb_end + lane; i < n; i += 32) s = fma(colp[i], ysol[i], s);
-        s = warp_sum(s);
-      }
-      if (lane == 0) sblk[c] = (c < w) ? ysol[c0 + c] - s : 0.0;
+    const int rb = c0 + K2_NB;
+    double lk[K2_NB];
+    if (warp == 0) {
+      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
+#pragma unroll
+      for (int c = 0; c < K2_NB; ++c) lk[c] = wsk[c * K2_NB + lane];
+    }
+    constexpr int MAXR = 12;                                 // rows below a block: <= 407 - 32 = 375 < 12 * 32
+    double v0[MAXR], v1[MAXR];
+    const int ca = 2 * warp, cb2 = 2 * warp + 1;             // NWARPS = 16: two columns of the block per warp
+    const double* pa = om + colb[min(c0 + ca, n - 1)];
+    const double* pb = om + colb[min(c0 + cb2, n - 1)];
+#pragma unroll
+    for (int j = 0; j < MAXR; ++j) {
+      const int i = min(rb + lane + 32 * j, n - 1);          // (clamped: always a valid address, masked below)
+      v0[j] = pa[i];
+      v1[j] = pb[i];
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXR; ++j) {
+      const int i = rb + lane + 32 * j;
+      const double yi = (i < n) ? ysol[min(i, n - 1)] : 0.0;
+      s0 = fma(v0[j], yi, s0);
+      s1 = fma(v1[j], yi, s1);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      sblk[ca] = (ca < w) ? ysol[c0 + ca] - s0 : 0.0;
+      sblk[cb2] = (cb2 < w) ? ysol[c0 + cb2] - s1 : 0.0;
     }
     __syncthreads();
     if (warp == 0) {
-      const double* wsk = lws + (size_t)k * (K2_NB * K2_NB);
-      double xv0 = 0.0, xv1 = 0.0;
+      double xv0 = 0.0, xv1 = 0.0, xv2 = 0.0, xv3 = 0.0;
 #pragma unroll
-      for (int cp = 0; cp < K2_NB; cp += 2) {
-        xv0 = fma(wsk[cp * K2_NB + lane], sblk[cp], xv0);
-        xv1 = fma(wsk[(cp + 1) * K2_NB + lane], sblk[cp + 1], xv1);
+      for (int cp = 0; cp < K2_NB; cp += 4) {
+        xv0 = fma(lk[cp], sblk[cp], xv0);
+        xv1 = fma(lk[cp + 1], sblk[cp + 1], xv1);
+        xv2 = fma(lk[cp + 2], sblk[cp + 2], xv2);
+        xv3 = fma(lk[cp + 3], sblk[cp + 3], xv3);
       }
-      if (lane < w) ysol[c0 + lane] = xv0 + xv1;
+      if (lane < w) ysol[c0 + lane] = (xv0 + xv1) + (xv2 + xv3);
     }
     __syncthreads();
   }

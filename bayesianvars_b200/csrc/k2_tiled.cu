@@ -926,6 +926,82 @@ __global__ void __launch_bounds__(KTF_THREADS, 1) k2_tiled_backsolve_fast(const 
   }
 }
 
+// Left-looking form for n <= 416 (default).  The right-looking kernel above gives every thread a COLUMN of the current
+// block row: 32 consecutive rows of one column per thread, i.e. every warp-wide load touches 32 different 32-byte
+// sectors for 8 useful bytes each - 51 us per launch whatever the number of equations (ncu, warm cache), a quarter of
+// the tiled K2.  Here block column k is read the way it is stored: warp w owns columns 2w, 2w+1 of the block, its lanes
+// stride over the rows below the block (coalesced 256-byte requests, <= 12 values per lane and column, all in flight
+// at once), the two dot products with the already solved part of x are reduced by shuffle, and warp 0 applies
+// Linv_k' (prefetched while the dot products run).  Two CTA barriers per block column.
+constexpr int KTL_WARPS = 16, KTL_THREADS = KTL_WARPS * 32, KTL_MAXN = 416, KTL_MAXR = (KTL_MAXN - KT_NB) / 32;
+__global__ void __launch_bounds__(KTL_THREADS, 1) k2_tiled_backsolve_ll(const K2Params p, const double* __restrict__ lws, int nbk) {
+  __shared__ double y[KTL_MAXN + 32];
+  __shared__ double sblk[KT_NB];
+  __shared__ int colb[KTL_MAXN];
+  const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, eq = blockIdx.x;
+  const double* __restrict__ om = p.omega + (size_t)eq * p.ldo;
+  const double* __restrict__ lwe = lws + (size_t)eq * nbk * (KT_NB * KT_NB);
+  for (int i = tid; i < n; i += KTL_THREADS) colb[i] = p.colbase[i];
+  __syncthreads();
+  for (int i = tid; i < KTL_MAXN + 32; i += KTL_THREADS)
+    y[i] = (i < n) ? __ldcg(om + colb[i] + n) + p.z[(size_t)eq * p.ldz + i] : 0.0;   // row n of L = the forward-solved rhs
+  __syncthreads();
+  bool bad = false;
+  for (int k = nbk - 1; k >= 0; --k) {
+    const int c0 = k * KT_NB, w = min(KT_NB, n - c0), rb = c0 + KT_NB;
+    double lk[KT_NB];
+    if (warp == 0) {
+      const double* wsk = lwe + (size_t)k * (KT_NB * KT_NB);
+#pragma unroll
+      for (int c = 0; c < KT_NB; ++c) lk[c] = __ldcg(wsk + c * KT_NB + lane);
+    }
+    double v0[KTL_MAXR], v1[KTL_MAXR];
+    const int ca = 2 * warp, cb2 = 2 * warp + 1;
+    const double* pa = om + colb[min(c0 + ca, n - 1)];
+    const double* pb = om + colb[min(c0 + cb2, n - 1)];
+#pragma unroll
+    for (int j = 0; j < KTL_MAXR; ++j) {
+      const int i = min(rb + lane + 32 * j, n - 1);          // (clamped: always a valid address, masked below)
+      v0[j] = __ldcg(pa + i);
+      v1[j] = __ldcg(pb + i);
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < KTL_MAXR; ++j) {
+      const int i = rb + lane + 32 * j;
+      const double yi = (i < n) ? y[min(i, KTL_MAXN + 31)] : 0.0;
+      s0 = fma(v0[j], yi, s0);
+      s1 = fma(v1[j], yi, s1);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      sblk[ca] = (ca < w) ? y[c0 + ca] - s0 : 0.0;
+      sblk[cb2] = (cb2 < w) ? y[c0 + cb2] - s1 : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+      for (int c = 0; c < KT_NB; c += 4) {
+        x0 = fma(lk[c], sblk[c], x0);
+        x1 = fma(lk[c + 1], sblk[c + 1], x1);
+        x2 = fma(lk[c + 2], sblk[c + 2], x2);
+        x3 = fma(lk[c + 3], sblk[c + 3], x3);
+      }
+      const double xv = (lane < w) ? (x0 + x1) + (x2 + x3) : 0.0;
+      y[c0 + lane] = xv;
+      if (lane < w) { p.phi[(size_t)eq * p.ldphi + c0 + lane] = xv; bad |= !isfinite(xv); }
+    }
+    __syncthreads();
+  }
+  const int anybad = __syncthreads_or(bad ? 1 : 0);
+  if (tid == 0) {
+    if (anybad) atomicCAS(&p.status[eq], 0, -1);
+    bvb_stamp_end(p.tstamp);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 namespace {
 // Per-shape launch state (task list, queue head + progress counters, diagonal accumulators).  Entries are never
@@ -1042,7 +1118,11 @@ cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s) {
   e = cudaGetLastError();
   if (e != cudaSuccess || p.mode == 1) return e;
   static int fastbs = -1;
-  if (fastbs < 0) { const char* ev = getenv("BVB_K2T_FASTBS"); fastbs = ev ? atoi(ev) : 1; }
+  if (fastbs < 0) { const char* ev = getenv("BVB_K2T_FASTBS"); fastbs = ev ? atoi(ev) : 2; }   // 2: left-looking (default), 1: right-looking, 0: generic
+  if (fastbs == 2 && p.n <= KTL_MAXN) {
+    k2_tiled_backsolve_ll<<<p.M, KTL_THREADS, 0, s>>>(p, lws, nbk);
+    return cudaGetLastError();
+  }
   if (fastbs && KT_NB * (nbk - 1) <= KTF_THREADS) {
     const size_t fsmem = ((size_t)nbk * KT_NB * KT_NB + (size_t)nbk * KT_NB + 64) * sizeof(double) + (size_t)(p.n + 4) * sizeof(int);
     if (fsmem <= (size_t)227 * 1024) {
