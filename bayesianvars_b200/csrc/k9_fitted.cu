@@ -81,6 +81,67 @@ __global__ void __launch_bounds__(128) vcov_kernel(double* __restrict__ out, con
   out[(size_t)t + (size_t)T * (a + (size_t)M * (b + (size_t)M * i))] = v;  // cube (T, M, M) flattened to (T*M, M) (:448-449)
 }
 
+// Factor structure, n_factors <= 8 (the usual case): thread = one (or two consecutive) time points of draw i, CTA
+// column block = BCH columns b of Sigma_t; the thread walks every row a.  The exponentials are taken ONCE per thread
+// (n_factors + BCH of them) instead of once per output element - the element-wise kernel above spends 40+ FP64
+// instructions on exp() per 8-byte store and is compute-bound at 1.24 TB/s - and the output leaves in 16-byte
+// streaming stores, contiguous in t across the warp.  Sigma(a, b) = sum_k L(a,k) L(b,k) e^{h_fk} (+ e^{h_a} on the diagonal).
+template <int NF, bool VEC2>
+__global__ void __launch_bounds__(128) vcov_factor_kernel(double* __restrict__ out, const double* __restrict__ facload,
+                                                          const double* __restrict__ logvar, int T, int M, int bch) {
+  extern __shared__ double Ls[];                                            // [NF][M] loadings of draw i
+  const int i = blockIdx.z, b0 = blockIdx.y * bch;
+  const int S = M + NF;
+  for (int q = threadIdx.x; q < NF * M; q += blockDim.x) Ls[q] = facload[(size_t)i * M * NF + q];
+  __syncthreads();
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) * (VEC2 ? 2 : 1);
+  if (t >= T) return;
+  const double* lv = logvar + (size_t)i * T * S + t;
+  double ef0[NF], ef1[NF];
+#pragma unroll
+  for (int k = 0; k < NF; ++k) {
+    ef0[k] = exp(lv[(size_t)(M + k) * T]);
+    ef1[k] = VEC2 ? exp(lv[(size_t)(M + k) * T + 1]) : 0.0;
+  }
+  double* obase = out + (size_t)t + (size_t)T * M * M * i;
+  for (int b = b0; b < min(b0 + bch, M); ++b) {
+    const double d0 = exp(lv[(size_t)b * T]);
+    const double d1 = VEC2 ? exp(lv[(size_t)b * T + 1]) : 0.0;
+    double lb[NF];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) lb[k] = Ls[k * M + b];
+    double* ocol = obase + (size_t)T * M * b;
+#pragma unroll 4
+    for (int a = 0; a < M; ++a) {
+      double v0 = (a == b) ? d0 : 0.0, v1 = (a == b) ? d1 : 0.0;
+#pragma unroll
+      for (int k = 0; k < NF; ++k) {
+        const double c = Ls[k * M + a] * lb[k];
+        v0 = fma(c, ef0[k], v0);
+        v1 = fma(c, ef1[k], v1);
+      }
+      if (VEC2) __stcs(reinterpret_cast<double2*>(ocol + (size_t)T * a), make_double2(v0, v1));
+      else __stcs(ocol + (size_t)T * a, v0);
+    }
+  }
+}
+
+template <int NF>
+static cudaError_t launch_vcov_factor(double* out, const double* facload, const double* logvar, int T, int M, int R, cudaStream_t s) {
+  const int bch = 4;
+  const bool vec2 = (T % 2) == 0;
+  const int tthreads = vec2 ? T / 2 : T;
+  for (int r0 = 0; r0 < R; r0 += 65535) {
+    const int rc = R - r0 < 65535 ? R - r0 : 65535;
+    dim3 grid((unsigned)((tthreads + 127) / 128), (unsigned)((M + bch - 1) / bch), (unsigned)rc);
+    const size_t sm = sizeof(double) * NF * M;
+    const size_t S = (size_t)M + NF;
+    if (vec2) vcov_factor_kernel<NF, true><<<grid, 128, sm, s>>>(out + (size_t)r0 * T * M * M, facload + (size_t)r0 * M * NF, logvar + (size_t)r0 * T * S, T, M, bch);
+    else vcov_factor_kernel<NF, false><<<grid, 128, sm, s>>>(out + (size_t)r0 * T * M * M, facload + (size_t)r0 * M * NF, logvar + (size_t)r0 * T * S, T, M, bch);
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace bvb
 
 using namespace bvb;
@@ -164,8 +225,24 @@ extern "C" int bvb_vcov(bvb_handle* h, int factor, int T, int M, int n_factors, 
   K9_TRY(cudaMalloc(&dout, d * nout)); allocs.push_back(dout);
   K9_TRY(cudaEventRecord(h->ev[0], s));
   if (!factor) vcov_uinv_kernel<<<R, 128, 0, s>>>(dui, du, M, (int)nU, R);
+  bool done_fast = false;
+  if (factor && nf >= 1 && nf <= 8 && (size_t)nf * M * sizeof(double) <= 48 * 1024 && !getenv("BVB_VCOV_ELEMENTWISE")) {
+    cudaError_t fe = cudaSuccess;
+    switch (nf) {
+      case 1: fe = launch_vcov_factor<1>(dout, dfl, dl, T, M, R, s); break;
+      case 2: fe = launch_vcov_factor<2>(dout, dfl, dl, T, M, R, s); break;
+      case 3: fe = launch_vcov_factor<3>(dout, dfl, dl, T, M, R, s); break;
+      case 4: fe = launch_vcov_factor<4>(dout, dfl, dl, T, M, R, s); break;
+      case 5: fe = launch_vcov_factor<5>(dout, dfl, dl, T, M, R, s); break;
+      case 6: fe = launch_vcov_factor<6>(dout, dfl, dl, T, M, R, s); break;
+      case 7: fe = launch_vcov_factor<7>(dout, dfl, dl, T, M, R, s); break;
+      default: fe = launch_vcov_factor<8>(dout, dfl, dl, T, M, R, s); break;
+    }
+    K9_TRY(fe);
+    done_fast = true;
+  }
   // draws in slabs of <= 65535 (grid.z)
-  for (int r0 = 0; r0 < R; r0 += 65535) {
+  for (int r0 = 0; r0 < R && !done_fast; r0 += 65535) {
     const int rc = R - r0 < 65535 ? R - r0 : 65535;
     dim3 grid((unsigned)((T + 127) / 128), (unsigned)(M * M), (unsigned)rc);
     vcov_kernel<<<grid, 128, 0, s>>>(dout + (size_t)r0 * T * M * M, dfl ? dfl + (size_t)r0 * M * nf : nullptr,

@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("T,M,r,R,factor", [(7, 5, 2, 4, True), (130, 6, 1, 3, True), (9, 4, 0, 2, True), (11, 5, 0, 3, False),
-                                            (200, 13, 0, 2, False), (3, 1, 0, 2, False)])
+                                            (200, 13, 0, 2, False), (3, 1, 0, 2, False),
+                                            (64, 9, 8, 2, True), (33, 7, 9, 2, True), (250, 23, 3, 2, True)])   # (r <= 8: the column-block kernel; r = 9: element-wise)
 def test_vcov_matches_oracle(handle, T, M, r, R, factor):
     rng = np.random.default_rng(T + M)
     fl = rng.standard_normal((M, r, R)) if factor else np.zeros((0, 0, 0))
