@@ -461,6 +461,12 @@ static cudaError_t enqueue_k1rhs(Gibbs& G, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// Does the sweep graph of this chain run in its rotated form (the NEXT sweep's K1 Z tiles under this sweep's tail)?
+static bool gibbs_rotates(const Gibbs& G) {
+  return getenv("BVB_NO_ROTATE") == nullptr && G.K > 0 && G.sigma_type != BVB_SIGMA_CHOLESKY && !G.huge && G.side != nullptr &&
+         G.ev_series != nullptr && G.ev_k1z != nullptr;
+}
+
 // One sweep's worth of launches on h->stream (captured into a graph by the caller).
 static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   cudaStream_t s = h->stream;
@@ -538,9 +544,7 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
   const bool has_hyper = !dbg_skip_hyper && G.hphi.d.n > 0 && G.hphi.d.prior != BVB_PRIOR_NORMAL && G.hphi.d.prior != BVB_PRIOR_NOTHING;
   static const bool dbg_fork_timing = getenv("BVB_DEBUG_FORK_TIMING") != nullptr;
   const bool forked = has_hyper && (!timing || dbg_fork_timing) && G.side != nullptr;
-  const bool no_rotate = getenv("BVB_NO_ROTATE") != nullptr;     // (read per enqueue: tests compare both forms)
-  const bool rotate = !no_rotate && K > 0 && G.sigma_type != BVB_SIGMA_CHOLESKY && !G.huge && G.side != nullptr &&
-                      G.ev_series != nullptr && G.ev_k1z != nullptr;
+  const bool rotate = gibbs_rotates(G);                          // (read per enqueue: tests compare both forms)
   const bool no_ng_side = getenv("BVB_NG_INLINE") != nullptr;
   const bool ng_side = forked && !no_ng_side && G.sigma_type != BVB_SIGMA_CHOLESKY && fsv_has_ng(G.fsv) && G.ev_ng != nullptr;
   {
@@ -1234,11 +1238,24 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
       fprintf(stderr, "[bvb run ] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
       t0 = t;
     };
-    int rc = run_eager_sweep(h, G, false);
-    if (rc) return rc;
-    mark("eager first sweep");
-    todo -= 1;
-    ran += 1;
+    int rc;
+    const bool recycled = G.graph_exec != nullptr && G.graph_stale;
+    if (!recycled) {
+      rc = run_eager_sweep(h, G, false);
+      if (rc) return rc;
+      mark("eager first sweep");
+      todo -= 1;
+      ran += 1;
+    } else if (gibbs_rotates(G) && !G.k1z_valid) {
+      // A recycled chain (same shape as the one before: workspaces sized, kernel attributes set) needs no eager sweep:
+      // what the first sweep does ahead of the steady-state graph - W, normals, the K1 Z tiles and right-hand sides -
+      // is launched here, and every sweep including the first replays the patched graph (0.5 ms per chain).
+      GB_TRY(enqueue_prep(h, G, s, 1));
+      GB_TRY(enqueue_k1z(G, s));
+      GB_TRY(enqueue_k1rhs(G, s));
+      G.k1z_valid = true;
+      mark("first-sweep prologue");
+    }
     cudaGraph_t graph;
     GB_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     rc = enqueue_sweep(h, G);

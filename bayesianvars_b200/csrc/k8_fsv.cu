@@ -24,32 +24,6 @@ namespace bvb {
 constexpr uint32_t STREAM_SV_ELEM = 0x100, STREAM_SV_SERIES = 0x101, STREAM_FSV_NG = 0x102,
                    STREAM_FSV_LOAD = 0x103, STREAM_FSV_IW = 0x104, STREAM_FSV_FAC = 0x105;
 
-// ystar, mixture indicators (from the current h) and the AWOL normals.
-// Series-major scratch: ystar / mixind [s*T + t], eps [s*(T+1) + t].
-__global__ void fsv_elem_kernel(const FsvDev d, uint64_t seed, const uint32_t* sweep_p) {
-  const uint32_t sweep = *sweep_p;
-  const int S = d.M + d.r;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)(d.T + 1) * S) return;
-  const int s = (int)(idx / (d.T + 1)), t = (int)(idx % (d.T + 1));
-  RngStream rng(seed, STREAM_SV_ELEM, (uint32_t)idx, sweep);
-  d.eps[idx] = rng.normal();
-  d.scratch[idx] = rng.normal();   // the Box-Muller partner: the second noise vector of the parallel state draw
-  if (t >= d.T) return;
-  double ys;
-  if (s < d.M) {
-    double e = d.resid[(size_t)s * d.T + t];
-    for (int k = 0; k < d.r; ++k) e -= d.facload[(size_t)k * d.M + s] * d.fac[(size_t)t * d.r + k];
-    d.eidi[(size_t)s * d.T + t] = e;
-    ys = log(e * e + d.offset[s]);
-  } else {
-    const double f = d.fac[(size_t)t * d.r + (s - d.M)];
-    ys = log(f * f);
-  }
-  d.ystar[(size_t)s * d.T + t] = ys;
-  d.mixind[(size_t)s * d.T + t] = (unsigned char)sv_draw_indicator(ys - d.logvar[(size_t)s * d.T + t], rng.uniform());
-}
-
 constexpr int SV_THREADS = 512;   // one row of the T+1 = 501 state equations per thread at the headline shape
 constexpr int SV_PCR = SV_THREADS - 32;   // threads of the cyclic reduction (the last warp draws the parameter variates meanwhile)
 
@@ -174,7 +148,11 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
     if (s < d.M) {
       // homoskedastic idiosyncratic variance: inverse gamma (factorstochvol; bvar_cpp.cpp:728-732 analogue)
       double ss[1] = {0.0};
-      for (int t = tid; t < T; t += SV_THREADS) { const double e = d.eidi[(size_t)s * T + t]; ss[0] += e * e; }
+      for (int t = tid; t < T; t += SV_THREADS) {
+        double e = d.resid[(size_t)s * T + t];
+        for (int k = 0; k < d.r; ++k) e -= d.facload[(size_t)k * d.M + s] * d.fac[(size_t)t * d.r + k];
+        ss[0] += e * e;
+      }
       block_sum<1>(ss, red);
       if (tid == 0) {
         RngStream rng(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
@@ -203,15 +181,33 @@ __global__ void __launch_bounds__(SV_THREADS) fsv_series_kernel(const FsvDev d, 
   pr.h0_var = d.priorh0[s];
   pr.mu_const = (s >= d.M) ? 1 : 0;
   double mu = pr.mu_const ? 0.0 : d.sv_para[3 * s + 0], phi = d.sv_para[3 * s + 1], sigma = d.sv_para[3 * s + 2];
-  for (int t = tid; t < T; t += SV_THREADS) {
-    ys[t] = d.ystar[(size_t)s * T + t];
-    rr[t] = d.mixind[(size_t)s * T + t];
+  // y*_t = log(e_t^2 + offset), the mixture indicators given the current h, and the two noise vectors of the state draw
+  // (this was a kernel of its own, one thread per (t, series), with its results going through global memory: 10 us plus
+  // a launch boundary on the critical path of the sweep; the Philox counters are the same, so is the chain)
+  double* e2s = sm + 5 * (size_t)(T + 1);   // [T+1] second noise vector; consumed before the cyclic reduction claims the buffer
+  for (int t = tid; t <= T; t += SV_THREADS) {
+    const size_t idx = (size_t)s * (T + 1) + t;
+    RngStream rng(seed, STREAM_SV_ELEM, (uint32_t)idx, sweep);
+    ep[t] = rng.normal();
+    e2s[t] = rng.normal();   // the Box-Muller partner
+    if (t < T) {
+      double ysv;
+      if (s < d.M) {
+        double e = d.resid[(size_t)s * T + t];
+        for (int k = 0; k < d.r; ++k) e -= d.facload[(size_t)k * d.M + s] * d.fac[(size_t)t * d.r + k];
+        ysv = log(e * e + d.offset[s]);
+      } else {
+        const double f = d.fac[(size_t)t * d.r + (s - d.M)];
+        ysv = log(f * f);
+      }
+      ys[t] = ysv;
+      rr[t] = (unsigned char)sv_draw_indicator(ysv - h[t], rng.uniform());
+    }
   }
-  for (int t = tid; t <= T; t += SV_THREADS) ep[t] = d.eps[(size_t)s * (T + 1) + t];
   __syncthreads();
   SV_TICK(0);
   // (a) tridiagonal system and state draw (parallel "all without a loop")
-  sv_state_draw_parallel(T, tid, sm, ys, rr, d.scratch + (size_t)s * (T + 1), mu, phi, sigma, pr.h0_var, [&](int l3) {
+  sv_state_draw_parallel(T, tid, sm, ys, rr, e2s, mu, phi, sigma, pr.h0_var, [&](int l3) {
     // last warp: the variates of the parameter updates (they do not depend on the state); disjoint counter ranges
     if (l3 < 5) {
       RngStream gq(seed, STREAM_SV_SERIES, (uint32_t)s, sweep);
@@ -759,8 +755,6 @@ cudaError_t launch_fsv_ng(const FsvDev& d, uint64_t seed, const uint32_t* sweep,
 // what lets the Gibbs loop start the next sweep's pair-GEMM here.
 cudaError_t launch_fsv_series(const FsvDev& d, uint64_t seed, const uint32_t* sweep, cudaStream_t s) {
   const int S = d.M + d.r;
-  const size_t nel = (size_t)(d.T + 1) * S;
-  fsv_elem_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(d, seed, sweep);
   const size_t smem = (size_t)(12 * (d.T + 1) + d.T) * sizeof(double) + (size_t)d.T + 16;
   if (smem > 48 * 1024) cudaFuncSetAttribute(fsv_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fsv_series_kernel<<<S, SV_THREADS, smem, s>>>(d, seed, sweep);
