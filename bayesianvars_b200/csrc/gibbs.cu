@@ -364,7 +364,21 @@ template <typename T>
 int upload(bvb_handle* h, GBuf<T>& b, const T* src, size_t n) {
   if (n == 0) return BVB_OK;
   GB_TRY(b.ensure(n));
-  if (src) GB_TRY(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  if (src) {
+    // through the chain's pinned staging arena when it fits: a copy from pageable memory is staged by the runtime
+    // synchronously, 10-20 us apiece for the ~45 small arrays of a chain set-up plus 0.3 ms for X; from pinned memory the
+    // calls return at once and the transfers overlap the rest of the set-up.  (The arena is rewound at the next
+    // bvb_gibbs_init, after a stream synchronisation.)
+    Gibbs* G = static_cast<Gibbs*>(h->gibbs);
+    const size_t bytes = n * sizeof(T), al = (bytes + 255) & ~(size_t)255;
+    if (G && G->stage && G->stage_off + al <= G->stage_cap) {
+      memcpy(G->stage + G->stage_off, src, bytes);
+      GB_TRY(cudaMemcpyAsync(b.p, G->stage + G->stage_off, bytes, cudaMemcpyHostToDevice, h->stream));
+      G->stage_off += al;
+    } else {
+      GB_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
   return BVB_OK;
 }
 
@@ -628,6 +642,7 @@ static void gibbs_free(bvb_handle* h) {
   Gibbs* G = static_cast<Gibbs*>(h->gibbs);
   if (G->fsv.prof) fsv_print_profile();
   if (G->graph_exec) cudaGraphExecDestroy(G->graph_exec);
+  if (G->stage) cudaFreeHost(G->stage);
   for (auto& e : G->ev) if (e) cudaEventDestroy(e);
   if (G->ev_fork) cudaEventDestroy(G->ev_fork);
   if (G->ev_join) cudaEventDestroy(G->ev_join);
@@ -711,6 +726,12 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   init_mark(reuse ? "previous chain recycled" : "free previous chain");
   gbuf_stream() = h->stream;
   Gibbs& G = *Gp;
+  if (!G.stage) {
+    const size_t cap = (size_t)16 << 20;
+    if (cudaMallocHost(reinterpret_cast<void**>(&G.stage), cap) == cudaSuccess) G.stage_cap = cap;
+    else { G.stage = nullptr; G.stage_cap = 0; cudaGetLastError(); }
+  }
+  G.stage_off = 0;   // (the stream was synchronised above when the chain is recycled; a new Gibbs has a new arena)
   G.M = M; G.T = T; G.K = K; G.Kp = Kp; G.intercept = intercept ? 1 : 0; G.r = r; G.S = M + r;
   G.draws = draws; G.burnin = burnin; G.thin = thin; G.tvp_all = tvp_keep_all ? 1 : 0;
   G.nsave = draws / thin; G.PHI_tol = PHI_tol; G.L_tol = L_tol; G.out = *out;
@@ -743,10 +764,14 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     if ((rc = upload(h, G.PHI0, PHI0, (size_t)Kp * M))) return rc;
     GB_TRY(G.PHI.ensure((size_t)Kp * std::max(M, G.nloc_max * G.world)));
     if ((rc = upload(h, G.PHI, sv->PHI, (size_t)Kp * M))) return rc;
-    make_pair_geom(G.geom, T, Kp);
-    if ((rc = upload(h, G.lut, G.geom.lut.data(), G.geom.nArows))) return rc;
-    if ((rc = upload(h, G.pairs, G.geom.pairs.data(), G.geom.nArows))) return rc;
-    if ((rc = upload(h, G.colbase, G.geom.colbase.data(), G.geom.colbase.size()))) return rc;
+    // the pair geometry (80 k pairs at the headline shape: 0.4 ms of host loops and 1.3 MB of tables) only depends on
+    // (T, Kp): a recycled chain keeps it, on the host and on the device
+    if (!reuse || G.geom.T != T || G.geom.n != Kp) {
+      make_pair_geom(G.geom, T, Kp);
+      if ((rc = upload(h, G.lut, G.geom.lut.data(), G.geom.nArows))) return rc;
+      if ((rc = upload(h, G.pairs, G.geom.pairs.data(), G.geom.nArows))) return rc;
+      if ((rc = upload(h, G.colbase, G.geom.colbase.data(), G.geom.colbase.size()))) return rc;
+    }
     if (!use_huge) GB_TRY(G.A.ensure((size_t)G.geom.nArows * G.geom.Tp));
     const int Nalloc = ((M + 7) / 8) * 8 + K1_NMAX;
     GB_TRY(G.W.ensure((size_t)Nalloc * G.geom.Tp, true));
@@ -1278,7 +1303,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
     cudaGraphDestroy(graph);
     mark(patched ? "graph exec update" : "graph instantiate");
   }
-  // Sub-chunks of <= 32 sweeps that store <= half a ring.  The two ring halves alternate: the D2H copy of a sub-chunk's
+  // Sub-chunks of <= 8 sweeps that store <= half a ring.  The two ring halves alternate: the D2H copy of a sub-chunk's
   // stored draws runs on the copy stream (behind an event, off the sampler stream) while the next sub-chunk fills the
   // other half, and the host scatters the PREVIOUS sub-chunk into the caller's arrays meanwhile.
   const int half = std::max(1, G.store.ring_slots / 2);
@@ -1297,7 +1322,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   bool used[2] = {false, false};
   while (todo > 0) {
     const int stored_before = stored_count(G, G.rep);
-    int nsw = std::min(todo, 32);
+    int nsw = std::min(todo, 8);   // (short sub-chunks: the copy-out and the host-side scatter of a sub-chunk hide behind the next one, only the last is exposed)
     while (nsw > 1 && stored_count(G, G.rep + nsw) - stored_before > half) --nsw;
     // ring half `flip` is free once the copy that last read it is done
     if (used[flip]) GB_TRY(cudaStreamWaitEvent(s, G.ev_pin[flip], 0));

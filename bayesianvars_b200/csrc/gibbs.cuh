@@ -116,6 +116,8 @@ struct Gibbs {
   int hyper_rows = 0;
   // execution
   cudaGraphExec_t graph_exec = nullptr;
+  char* stage = nullptr;                 // pinned staging arena of the set-up uploads
+  size_t stage_cap = 0, stage_off = 0;
   bool graph_stale = false;   // chain recycled: re-capture and cudaGraphExecUpdate before the next replay
   bool timing_pass = false, timed = false;
   cudaEvent_t ev[9] = {};
