@@ -80,6 +80,12 @@ def _register_gibbs_signatures():
         "bvb_gibbs_state": (C.c_int, [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
         "bvb_comm_unique_id": (C.c_int, [C.c_char_p]),
         "bvb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
+        "bvb_create_multi": (C.c_int, [C.c_int, _ip, C.c_uint64, C.POINTER(vp)]),
+        "bvb_gibbs_init_multi": (C.c_int, [C.c_int, C.POINTER(vp), _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, _dp, _dp, C.POINTER(PriorPhi), C.POINTER(PriorSigma),
+                                           C.POINTER(StartVals), _ip, C.c_double, C.c_double, C.c_int, C.POINTER(Draws)]),
+        "bvb_gibbs_run_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.c_int, _ip]),
+        "bvb_destroy_multi": (None, [C.c_int, C.POINTER(vp)]),
     })
 
 
@@ -555,6 +561,48 @@ def marshal_prior_sigma(cpp, keep):
     return s
 
 
+class MultiHandle:
+    """n GPUs driven from THIS process (bvb_create_multi): the equation-sharded chain without a launcher.  Pass it to
+    Sampler / bvar() in place of a Handle; rank 0's arrays receive the draws."""
+
+    def __init__(self, devices, seed=0):
+        from ._lib import load
+        self._lib = load()
+        self.n = len(devices)
+        self.seed = int(seed)
+        dv = (C.c_int * self.n)(*[int(d) for d in devices])
+        self._hs = (C.c_void_p * self.n)()
+        rc = self._lib.bvb_create_multi(self.n, dv, C.c_uint64(self.seed), self._hs)
+        if rc:
+            from ._lib import BvbError
+            raise BvbError(rc, "bvb_create_multi failed (needs %d sm_100 devices and libnccl.so.2)" % self.n)
+        self._h = self._hs[0]
+
+    def _check(self, rc):
+        if rc:
+            from ._lib import BvbError
+            last = None
+            for i in range(self.n):     # the failing rank carries the message
+                step, sweep, eq = C.c_int(), C.c_int(), C.c_int()
+                buf = C.create_string_buffer(512)
+                self._lib.bvb_last_error(self._hs[i], C.byref(step), C.byref(sweep), C.byref(eq), buf, 512)
+                if buf.value:
+                    last = BvbError(rc, "rank %d: %s" % (i, buf.value.decode()), step.value, sweep.value, eq.value)
+                    break
+            raise last or BvbError(rc, "multi-GPU call failed")
+
+    def close(self):
+        if getattr(self, "_hs", None) is not None and self.n:
+            self._lib.bvb_destroy_multi(self.n, self._hs)
+            self.n = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Sampler:
     """A chain set up on the device (bvb_gibbs_init); `run(n)` advances it."""
 
@@ -603,8 +651,10 @@ class Sampler:
                 setattr(st, k, self.keep.d(sv[k]))
         pp = marshal_prior_phi(pcpp, self.keep)
         ps = marshal_prior_sigma(scpp, self.keep)
-        rc = self.lib.bvb_gibbs_init(
-            self.h._h, self.keep.d(prep["Y"]), self.keep.d(prep["X"]) if Kp else None, M, T, K, draws, burnin, thin,
+        multi = isinstance(handle, MultiHandle)
+        init = (lambda *a: self.lib.bvb_gibbs_init_multi(handle.n, handle._hs, *a)) if multi else (lambda *a: self.lib.bvb_gibbs_init(self.h._h, *a))
+        rc = init(
+            self.keep.d(prep["Y"]), self.keep.d(prep["X"]) if Kp else None, M, T, K, draws, burnin, thin,
             1 if sv_keep == "all" else 0, prep["intercept"], self.keep.d(prep["priorIntercept"]) if prep["intercept"] else None,
             self.keep.d(prep["PHI0"]) if Kp else None, C.byref(pp), C.byref(ps), C.byref(st), self.keep.i(prep["i_vec"]) if K else None,
             float(prior_phi["general_settings"]["PHI_tol"]), float(prior_sigma["general_settings"]["cholesky_U_tol"]),
@@ -616,7 +666,10 @@ class Sampler:
         tot = self.draws + self.burnin
         n = tot - self.done if n_sweeps is None else n_sweeps
         done = C.c_int(0)
-        rc = self.lib.bvb_gibbs_run(self.h._h, int(n), C.byref(done))
+        if isinstance(self.h, MultiHandle):
+            rc = self.lib.bvb_gibbs_run_multi(self.h.n, self.h._hs, int(n), C.byref(done))
+        else:
+            rc = self.lib.bvb_gibbs_run(self.h._h, int(n), C.byref(done))
         self.h._check(rc)
         self.done = done.value
         return self.done

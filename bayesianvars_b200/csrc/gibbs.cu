@@ -12,6 +12,7 @@
 // unchanged; all Philox streams are keyed by (purpose, element, sweep).
 #include "gibbs.cuh"
 #include <chrono>
+#include <thread>
 #include "chol.cuh"
 
 #include <nccl.h>
@@ -1246,6 +1247,7 @@ int bvb_gibbs_run(bvb_handle* h, int max_sweeps, int* done) {
   Gibbs& G = *static_cast<Gibbs*>(h->gibbs);
   if (!G.ready) return BVB_ERR_ARG;
   GB_TRY(cudaSetDevice(h->device));
+  gbuf_stream() = h->stream;   // (thread-local: bvb_gibbs_run_multi drives every rank from its own thread)
   cudaStream_t s = h->stream;
   const int tot = G.draws + G.burnin;
   int todo = std::min(max_sweeps, tot - G.rep);
@@ -1500,6 +1502,58 @@ int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128)
   if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
   h->comm = comm;
   return BVB_OK;
+}
+
+// ---- one process, several GPUs (the R package is a single process: no launcher, no MPI) ----------------------------
+// n handles on n devices with ranks 0..n-1 and an in-process NCCL communicator; the equation-sharded sweep is the same
+// code as in the process-per-GPU form, each rank driven by its own host thread inside bvb_gibbs_run_multi.
+int bvb_create_multi(int n, const int* devices, uint64_t seed, bvb_handle** handles) {
+  if (n < 1 || !devices || !handles) return BVB_ERR_ARG;
+  for (int i = 0; i < n; ++i) handles[i] = nullptr;
+  char id[128];
+  if (n > 1) { const int rc = bvb_comm_unique_id(id); if (rc) return rc; }
+  for (int i = 0; i < n; ++i) {
+    const int rc = bvb_create(&handles[i], devices[i], seed);
+    if (rc) { for (int j = 0; j < i; ++j) { bvb_destroy(handles[j]); handles[j] = nullptr; } return rc; }
+  }
+  std::vector<int> rcs((size_t)n, BVB_OK);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n; ++i) th.emplace_back([&, i]() { rcs[i] = bvb_comm_init(handles[i], i, n, n > 1 ? id : nullptr); });   // (ncclCommInitRank blocks until every rank has joined)
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rcs[i]) { const int rc = rcs[i]; for (int j = 0; j < n; ++j) { bvb_destroy(handles[j]); handles[j] = nullptr; } return rc; }
+  return BVB_OK;
+}
+
+int bvb_gibbs_init_multi(int n, bvb_handle** handles, const double* Y, const double* X, int M, int T, int K, int draws, int burnin,
+                         int thin, int tvp_keep_all, int intercept, const double* priorIntercept, const double* PHI0,
+                         const bvb_prior_phi* prior_phi, const bvb_prior_sigma* prior_sigma, const bvb_startvals* startvals,
+                         const int* i_vec, double PHI_tol, double L_tol, int huge, const bvb_draws* out) {
+  if (n < 1 || !handles) return BVB_ERR_ARG;
+  for (int i = 0; i < n; ++i) {   // (no collective in the set-up: one rank after the other, rank 0 owns the output arrays)
+    if (!handles[i]) return BVB_ERR_ARG;
+    const int rc = bvb_gibbs_init(handles[i], Y, X, M, T, K, draws, burnin, thin, tvp_keep_all, intercept, priorIntercept, PHI0, prior_phi,
+                                  prior_sigma, startvals, i_vec, PHI_tol, L_tol, huge, out);
+    if (rc) return rc;
+  }
+  return BVB_OK;
+}
+
+int bvb_gibbs_run_multi(int n, bvb_handle** handles, int max_sweeps, int* done) {
+  if (n < 1 || !handles) return BVB_ERR_ARG;
+  if (n == 1) return bvb_gibbs_run(handles[0], max_sweeps, done);
+  std::vector<int> rcs((size_t)n, BVB_OK), dn((size_t)n, 0);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n; ++i) th.emplace_back([&, i]() { rcs[i] = bvb_gibbs_run(handles[i], max_sweeps, &dn[i]); });
+  for (auto& t : th) t.join();
+  if (done) *done = dn[0];
+  for (int i = 0; i < n; ++i) if (rcs[i]) return rcs[i];   // (the failing rank's message: bvb_last_error(handles[i]))
+  return BVB_OK;
+}
+
+void bvb_destroy_multi(int n, bvb_handle** handles) {
+  if (!handles) return;
+  for (int i = 0; i < n; ++i) { if (handles[i]) bvb_destroy(handles[i]); handles[i] = nullptr; }
 }
 
 }  // extern "C"

@@ -1113,17 +1113,20 @@ __global__ void __launch_bounds__(K2_NWARPS * 32, 1) k2_cholsolve_v2(const K2Par
   if (tid == 0 && (fail || anybad)) atomicCAS(&p.status[eq], 0, fail ? fail : -1);
 }
 
-static double* g_linv_ws = nullptr;
-static size_t g_linv_ws_bytes = 0;
+// The [M][nbk][32 x 32] inverses of the diagonal blocks, shared by every K2 form and by the solve-only kernel; one
+// workspace per device (a process may drive several GPUs: bvb_create_multi).
+static double* g_linv_ws[16] = {nullptr};
+static size_t g_linv_ws_bytes[16] = {0};
 
-// The [M][nbk][32 x 32] inverses of the diagonal blocks, shared by every K2 form and by the solve-only kernel.
 double* k2_linv_workspace(size_t need) {
-  if (need > g_linv_ws_bytes) {
-    if (g_linv_ws) cudaFree(g_linv_ws);
-    if (cudaMalloc(&g_linv_ws, need) != cudaSuccess) { g_linv_ws = nullptr; g_linv_ws_bytes = 0; return nullptr; }
-    g_linv_ws_bytes = need;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (need > g_linv_ws_bytes[dev]) {
+    if (g_linv_ws[dev]) cudaFree(g_linv_ws[dev]);
+    if (cudaMalloc(&g_linv_ws[dev], need) != cudaSuccess) { g_linv_ws[dev] = nullptr; g_linv_ws_bytes[dev] = 0; return nullptr; }
+    g_linv_ws_bytes[dev] = need;
   }
-  return g_linv_ws;
+  return g_linv_ws[dev];
 }
 
 cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s);   // k2_tiled.cu
@@ -1131,7 +1134,8 @@ cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s);   // k2_tiled.cu
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
   const int nbk = k2_nblocks(p.n);
   const size_t need = (size_t)p.M * nbk * K2_NB * K2_NB * sizeof(double);
-  if (!k2_linv_workspace(need)) return cudaErrorMemoryAllocation;
+  double* const linv_ws = k2_linv_workspace(need);
+  if (!linv_ws) return cudaErrorMemoryAllocation;
   {
     // The tile-queue form (k2_tiled.cu) when the equations alone cannot fill the chip: measured at n = 401 on 148 SMs,
     // tiled / one-CTA-per-equation: 13 equations 242 / 303 us, 25: 250 / 307, 50: 277 / 334, 100: 483 / 338 (the look-ahead
@@ -1184,7 +1188,7 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k2_cholsolve<true>, p, g_linv_ws, rtc, cs);
+        return cudaLaunchKernelEx(&cfg, k2_cholsolve<true>, p, linv_ws, rtc, cs);
       }
     }
   }
@@ -1196,7 +1200,7 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
     if (e2 != cudaSuccess) return e2;
     K2Params q = p;
     { const char* ed = getenv("BVB_K2_DIRECT"); if (ed) q.direct = atoi(ed); }
-    k2_cholsolve_v2<<<q.M, K2_NWARPS * 32, smem2, s>>>(q, g_linv_ws, (int)ring);
+    k2_cholsolve_v2<<<q.M, K2_NWARPS * 32, smem2, s>>>(q, linv_ws, (int)ring);
     return cudaGetLastError();
   }
   const int rt = k2_pick_rt(p.n);
@@ -1204,14 +1208,15 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
   const size_t smem = k2_smem_bytes_rt(p.n, rt);
   cudaError_t e = cudaFuncSetAttribute(k2_cholsolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k2_cholsolve<false><<<p.M, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws, rt, 1);
+  k2_cholsolve<false><<<p.M, K2_NWARPS * 32, smem, s>>>(p, linv_ws, rt, 1);
   return cudaGetLastError();
 }
 
 // Solve `count` already-factorised equations eq0..eq0+count-1 (p.omega / status are
 // the batch arrays; p.z, p.phi and bvec are indexed from the first solved equation).
 cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s) {
-  if (!g_linv_ws) return cudaErrorInvalidValue;
+  double* const linv_ws = k2_linv_workspace(0);      // (sized by the factorisation that came before)
+  if (!linv_ws) return cudaErrorInvalidValue;
   const int nbk = k2_nblocks(p.n);
   const size_t smem = ((size_t)K2S_STAGES * K2_NB * K2S_RCS + (size_t)(nbk * K2_NB + 32) + 64) * sizeof(double) +
                       (size_t)(p.n + 4) * sizeof(int);
@@ -1220,7 +1225,7 @@ cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int 
     cudaError_t e = cudaFuncSetAttribute(k2_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k2_solve_kernel<<<count, K2_NWARPS * 32, smem, s>>>(p, g_linv_ws, bvec, eq0);
+  k2_solve_kernel<<<count, K2_NWARPS * 32, smem, s>>>(p, linv_ws, bvec, eq0);
   return cudaGetLastError();
 }
 

@@ -265,6 +265,21 @@ int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,
 int bvb_comm_unique_id(char* unique_id_128);
 int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128);
 
+/* One process, several GPUs (what an R session is: no launcher, no MPI).  bvb_create_multi makes n handles on the
+ * given devices with ranks 0..n-1 and an in-process NCCL communicator; bvb_gibbs_init_multi sets the same chain up on
+ * every rank (identical arguments, rank 0's bvb_draws receives the stored draws); bvb_gibbs_run_multi advances all
+ * ranks together (one host thread per rank for the duration of the call) - the multi-GPU form of the bvar_cpp() loop
+ * (src/bvar_cpp.cpp:498-845) behind the same chunked, interruptible call as bvb_gibbs_run.  n = 1 is the plain path. */
+int bvb_create_multi(int n, const int* devices, uint64_t seed, bvb_handle** handles);
+int bvb_gibbs_init_multi(int n, bvb_handle** handles, const double* Y, const double* X, int M, int T, int K,
+                         int draws, int burnin, int thin, int tvp_keep_all, int intercept,
+                         const double* priorIntercept, const double* PHI0,
+                         const bvb_prior_phi* prior_phi, const bvb_prior_sigma* prior_sigma,
+                         const bvb_startvals* startvals, const int* i_vec,
+                         double PHI_tol, double L_tol, int huge, const bvb_draws* out);
+int bvb_gibbs_run_multi(int n, bvb_handle** handles, int max_sweeps, int* done);
+void bvb_destroy_multi(int n, bvb_handle** handles);
+
 /* ---- a14: irf_cpp (src/irf.cpp:468-524) -------------------------------------------
  * Impulse responses for R stored posterior draws.  coefficients Kp x M x R;
  * factor_loadings M x n_factors x R (n_factors = 0: NULL); U_vecs n_U x R

@@ -25,6 +25,8 @@ using namespace Rcpp;
 
 namespace {
 
+uint64_t g_call_seed = 0;   // the Philox key of the current entry point (drawn from R's RNG in the_handle())
+
 bvb_handle* the_handle() {
   static bvb_handle* h = nullptr;
   if (!h) {
@@ -39,7 +41,37 @@ bvb_handle* the_handle() {
   const double u1 = R::unif_rand(), u2 = R::unif_rand();
   const uint64_t seed = ((uint64_t)(u1 * 4294967296.0) << 32) | (uint64_t)(u2 * 4294967296.0);
   bvb_set_seed(h, seed);
+  g_call_seed = seed;
   return h;
+}
+
+// BVB_DEVICES="0,1,2,3": bvar() with the factor structure shards its equations over these GPUs from this one R process
+// (bvb_create_multi: one handle per device, an in-process NCCL communicator); unset or one device = the plain path.
+struct MultiGpu { int n = 0; std::vector<bvb_handle*> h; };
+MultiGpu& the_gpus() {
+  static MultiGpu g;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    std::vector<int> devs;
+    if (const char* e = std::getenv("BVB_DEVICES")) {
+      std::string s(e);
+      size_t pos = 0;
+      while (pos < s.size()) {
+        const size_t c = s.find(',', pos);
+        const std::string tok = s.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+        if (!tok.empty()) devs.push_back(std::atoi(tok.c_str()));
+        if (c == std::string::npos) break;
+        pos = c + 1;
+      }
+    }
+    if (devs.size() > 1) {
+      g.h.assign(devs.size(), nullptr);
+      if (bvb_create_multi((int)devs.size(), devs.data(), 0, g.h.data()) == BVB_OK) g.n = (int)devs.size();
+      else { g.h.clear(); Rcpp::warning("bayesianVARs: BVB_DEVICES could not be opened together, using one GPU"); }
+    }
+  }
+  return g;
 }
 
 void check(bvb_handle* h, int rc) {
@@ -209,6 +241,14 @@ List bvar_cpp(const NumericMatrix& Y, const NumericMatrix& X, const int& M, cons
   out.U = (n_U && nsave) ? U_draws.begin() : nullptr;
   out.u_hyperparameter = (u_rows && nsave && priorU != "normal") ? u_hyper.begin() : nullptr;
 
+  // several GPUs (factor structure only: the cholesky structure is sequential over the equations)
+  MultiGpu& mg = the_gpus();
+  const bool multi = mg.n > 1 && fac_on && !huge && K > 0;
+  if (multi) {
+    for (int i = 0; i < mg.n; ++i) bvb_set_seed(mg.h[i], g_call_seed);
+    check(mg.h[0], bvb_gibbs_init_multi(mg.n, mg.h.data(), Y.begin(), X.begin(), M, T, K, draws, burnin, thin, all ? 1 : 0, intercept,
+                                        priorIntercept.begin(), PHI0.begin(), &pp, &ps, &sv, i_vec.begin(), PHI_tol, L_tol, 0, &out));
+  } else
   check(h, bvb_gibbs_init(h, Y.begin(), X.begin(), M, T, K, draws, burnin, thin, all ? 1 : 0, intercept,
                           priorIntercept.begin(), PHI0.begin(), &pp, &ps, &sv, i_vec.begin(), PHI_tol, L_tol,
                           huge ? 1 : 0, &out));
@@ -218,7 +258,8 @@ List bvar_cpp(const NumericMatrix& Y, const NumericMatrix& X, const int& M, cons
   if (progressbar) Rprintf("\r###  %i / %i ### (%3.0f%%) ###", 0, tot, 0.);
   while (done < tot) {
     Rcpp::checkUserInterrupt();                       // every 256 sweeps, as bvar_cpp.cpp:501-503
-    check(h, bvb_gibbs_run(h, 256, &done));
+    if (multi) check(mg.h[0], bvb_gibbs_run_multi(mg.n, mg.h.data(), 256, &done));
+    else check(h, bvb_gibbs_run(h, 256, &done));
     if (progressbar) Rprintf("\r###  %i / %i ### (%3.0f%%) ###", done, tot, 100. * done / tot);
   }
   return List::create(Named("PHI") = PHI_draws, Named("U") = U_draws, Named("logvar") = logvar_draws,

@@ -33,6 +33,14 @@ inline void stop(const char* fmt, ...) {
   va_end(ap);
   throw exception(buf);
 }
+inline void warning(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "Warning: ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
 inline void checkUserInterrupt() {}
 
 struct RObj;
