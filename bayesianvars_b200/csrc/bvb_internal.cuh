@@ -23,6 +23,8 @@ struct bvb_handle {
   void* gibbs = nullptr;    // owned by gibbs.cu (bvb::Gibbs)
   int rank = 0, world = 1;
   void* comm = nullptr;     // ncclComm_t
+  int inproc = 0;           // created by bvb_create_multi: the peers live in this process (direct peer pointers, no IPC)
+  unsigned long long p2p_epoch = 0;   // chains set up on this handle (stamps the flags of the peer exchange)
   void* pin[2] = {nullptr, nullptr};   // pinned staging of the stored draws, kept across bvb_gibbs_init calls
   size_t pin_bytes[2] = {0, 0};
 };
@@ -77,6 +79,18 @@ struct K1Params {
 };
 cudaError_t launch_k1(const K1Params& p, cudaStream_t s);
 
+// Peer exchange fused into the K2 back-solve (multi-GPU, equation-sharded sweep): the CTA that has just solved an
+// equation writes its PHI column to every peer's exchange buffer as well, the last CTA of the launch stamps the flags.
+struct K2Xch {
+  double* const* peer_xbuf = nullptr;            // [world] (device table)
+  unsigned long long* const* peer_xflag = nullptr;
+  int* cnt = nullptr;                            // CTAs of this launch that are done (self-resetting)
+  int rank = 0, world = 1;
+  size_t blk = 0;                                // doubles per rank block
+  unsigned long long epoch_base = 0;
+  const unsigned int* sweep_p = nullptr;
+};
+
 struct K2Params {
   double* omega;        // [M][ldo] in: packed augmented system; out: its Cholesky factor
   const int* colbase;   // [n]
@@ -91,6 +105,8 @@ struct K2Params {
   int debug_mode = 0;         // 1: skip the DMMA of the update loop, 2: skip its loads (timing experiments only)
   int direct = 1;             // look-ahead kernel: operands of the update straight from L2 into registers (BVB_K2_DIRECT)
   unsigned long long* tstamp = nullptr;  // optional [2]: %globaltimer of the first CTA start / last CTA end
+  K2Xch xch;                  // world > 1: push the solved columns to the peers (honoured by the tiled form's back-solve)
+  bool* xch_fused = nullptr;  // host: set to true by launch_k2 when the launch it chose does the push itself
 };
 cudaError_t launch_k2(const K2Params& p, cudaStream_t s);
 cudaError_t launch_k2_solve(const K2Params& p, const double* bvec, int eq0, int count, cudaStream_t s);

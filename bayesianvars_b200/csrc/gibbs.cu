@@ -476,6 +476,63 @@ static cudaError_t enqueue_k1rhs(Gibbs& G, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// ---- peer exchange of the freshly drawn PHI columns -------------------------------------------------------------------
+// Every rank owns a contiguous block of columns.  push: CTA b copies this rank's block straight into peer p's exchange
+// buffer (remote stores over NVLink), every thread fences at system scope, then one thread stamps p's flag for this rank
+// with (epoch << 32 | sweep + 1).  pull: CTA b spins on the flag of source p (acquire at system scope, bounded), then
+// copies p's block from the local exchange buffer into PHI.  The buffer is double-buffered by sweep parity: a peer can
+// be at most one sweep ahead (its next K2 needs THIS rank's push), so it never overwrites a block still being read; and
+// by the parity of the chain count, so the first sweep of a recycled chain cannot touch the last sweep of the previous one.
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr int XCH_SLICES = 8;    // CTAs per peer: one CTA pushing 160 KB of 8-byte remote stores took 30 us
+__global__ void __launch_bounds__(512) gibbs_push_kernel(const double* __restrict__ mine, size_t blk, double* const* __restrict__ peer_xbuf,
+                                                         unsigned long long* const* __restrict__ peer_xflag, int* __restrict__ cnt, int rank,
+                                                         int world, unsigned long long epoch_base, const uint32_t* __restrict__ sweep_p) {
+  const uint32_t sweep = *sweep_p;
+  const int pi = (int)blockIdx.x / XCH_SLICES, sl = (int)blockIdx.x % XCH_SLICES;
+  const int p = pi < rank ? pi : pi + 1;
+  double* dst = peer_xbuf[p] + (((epoch_base >> 32) & 1ull) * 2 + (sweep & 1u)) * (size_t)world * blk + (size_t)rank * blk;
+  const size_t per = (blk + XCH_SLICES - 1) / XCH_SLICES, i0 = (size_t)sl * per, i1 = i0 + per < blk ? i0 + per : blk;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = mine[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(cnt + pi, 1);
+    __threadfence();
+    if (old == XCH_SLICES - 1) {                      // last slice for this peer: everything is out, stamp its flag
+      cnt[pi] = 0;
+      __threadfence_system();
+      st_release_sys_u64(peer_xflag[p] + rank, epoch_base + sweep + 1ull);
+    }
+  }
+}
+__global__ void __launch_bounds__(512) gibbs_pull_kernel(double* __restrict__ PHI, const double* __restrict__ xbuf,
+                                                         const unsigned long long* __restrict__ xflag, size_t blk, int rank, int world,
+                                                         unsigned long long epoch_base, const uint32_t* __restrict__ sweep_p, int* status) {
+  const uint32_t sweep = *sweep_p;
+  const int pi = (int)blockIdx.x / XCH_SLICES, sl = (int)blockIdx.x % XCH_SLICES;
+  const int p = pi < rank ? pi : pi + 1;
+  if (threadIdx.x == 0) {
+    const unsigned long long want = epoch_base + sweep + 1ull;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(xflag + p) < want) {
+      if (clock64() - t0 > (4ll << 30)) { atomicExch(status + 3, 1 + p); break; }   // ~2 s: a peer is gone; reported, not hung
+    }
+  }
+  __syncthreads();
+  const double* src = xbuf + (((epoch_base >> 32) & 1ull) * 2 + (sweep & 1u)) * (size_t)world * blk + (size_t)p * blk;
+  double* dst = PHI + (size_t)p * blk;
+  const size_t per = (blk + XCH_SLICES - 1) / XCH_SLICES, i0 = (size_t)sl * per, i1 = i0 + per < blk ? i0 + per : blk;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = __ldcg(src + i);   // (written by a peer: never through L1)
+}
+
 // Does the sweep graph of this chain run in its rotated form (the NEXT sweep's K1 Z tiles under this sweep's tail)?
 static bool gibbs_rotates(const Gibbs& G) {
   return getenv("BVB_NO_ROTATE") == nullptr && G.K > 0 && G.sigma_type != BVB_SIGMA_CHOLESKY && !G.huge && G.side != nullptr &&
@@ -531,14 +588,29 @@ static int enqueue_sweep(bvb_handle* h, Gibbs& G) {
     k2.omega = G.omega.p; k2.colbase = G.colbase.p; k2.z = G.Zn.p; k2.phi = G.PHI.p + (size_t)G.j0 * Kp;
     k2.status = G.eqstatus.p + G.j0; k2.n = Kp; k2.M = G.nloc; k2.ldo = G.geom.ldo; k2.ldz = Kp; k2.ldphi = Kp;
     k2.tstamp = G.ktime.p + 2;
+    bool xch_fused = false;
+    if (G.world > 1 && G.p2p && G.nloc > 0) {
+      k2.xch.peer_xbuf = G.peer_xbuf.p; k2.xch.peer_xflag = G.peer_xflag.p; k2.xch.cnt = G.xcnt.p + G.world;   // (own counter word)
+      k2.xch.rank = G.rank; k2.xch.world = G.world; k2.xch.blk = (size_t)G.nloc_max * Kp;
+      k2.xch.epoch_base = G.epoch_base; k2.xch.sweep_p = sw;
+      k2.xch_fused = &xch_fused;
+    }
     GB_TRY(launch_k2(k2, s));
     mark(3);
     if (G.world > 1) {
       // ranks own contiguous blocks of nloc_max columns (PHI is padded to world*nloc_max
       // columns), so the gather is in place: sendbuff == recvbuff + rank*count
-      ncclResult_t nr = nccl_api().AllGather(G.PHI.p + (size_t)G.rank * G.nloc_max * Kp, G.PHI.p, (size_t)G.nloc_max * Kp,
-                                             ncclDouble, (ncclComm_t)G.comm, s);
-      if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather: %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
+      const size_t blk = (size_t)G.nloc_max * Kp;
+      if (G.p2p) {
+        const unsigned xg = (unsigned)((G.world - 1) * XCH_SLICES);
+        // (the tiled K2's back-solve pushes the columns itself; the stand-alone push serves the other K2 forms)
+        if (!xch_fused) gibbs_push_kernel<<<xg, 512, 0, s>>>(G.PHI.p + (size_t)G.rank * blk, blk, G.peer_xbuf.p, G.peer_xflag.p, G.xcnt.p, G.rank, G.world,
+                                             G.epoch_base, sw);
+        gibbs_pull_kernel<<<xg, 512, 0, s>>>(G.PHI.p, G.xbuf.p, G.xflag.p, blk, G.rank, G.world, G.epoch_base, sw, G.status.p);
+      } else {
+        ncclResult_t nr = nccl_api().AllGather(G.PHI.p + (size_t)G.rank * blk, G.PHI.p, blk, ncclDouble, (ncclComm_t)G.comm, s);
+        if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather: %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
+      }
     }
     mark(4);
     const size_t nphi = (size_t)Kp * M;
@@ -644,6 +716,7 @@ static void gibbs_free(bvb_handle* h) {
   if (G->fsv.prof) fsv_print_profile();
   if (G->graph_exec) cudaGraphExecDestroy(G->graph_exec);
   if (G->stage) cudaFreeHost(G->stage);
+  for (void* q : G->ipc_opened) cudaIpcCloseMemHandle(q);
   for (auto& e : G->ev) if (e) cudaEventDestroy(e);
   if (G->ev_fork) cudaEventDestroy(G->ev_fork);
   if (G->ev_join) cudaEventDestroy(G->ev_join);
@@ -664,6 +737,41 @@ static void gibbs_free(bvb_handle* h) {
 void bvb_gibbs_release(bvb_handle* h) { gibbs_free(h); }
 
 extern "C" {
+
+// Multi-process form: the peers' exchange buffers are opened through CUDA IPC; the 128 bytes of handles per rank travel
+// through one NCCL allgather at set-up (NCCL stays the bootstrap, it is no longer in the sweep).
+static int p2p_bootstrap_ipc(bvb_handle* h, Gibbs& G) {
+  for (void* q : G.ipc_opened) cudaIpcCloseMemHandle(q);
+  G.ipc_opened.clear();
+  struct Pack { cudaIpcMemHandle_t x, f; };
+  static_assert(sizeof(Pack) == 128, "two IPC handles");
+  cudaStream_t s = h->stream;
+  GBuf<double> send, recv;
+  GB_TRY(send.ensure(16)); GB_TRY(recv.ensure((size_t)16 * G.world));
+  Pack mine;
+  GB_TRY(cudaIpcGetMemHandle(&mine.x, G.xbuf.p));
+  GB_TRY(cudaIpcGetMemHandle(&mine.f, G.xflag.p));
+  GB_TRY(cudaMemcpyAsync(send.p, &mine, sizeof(Pack), cudaMemcpyHostToDevice, s));
+  ncclResult_t nr = nccl_api().AllGather(send.p, recv.p, 16, ncclDouble, (ncclComm_t)G.comm, s);
+  if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather (set-up): %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
+  GB_TRY(cudaStreamSynchronize(s));
+  std::vector<Pack> all((size_t)G.world);
+  GB_TRY(cudaMemcpy(all.data(), recv.p, sizeof(Pack) * G.world, cudaMemcpyDeviceToHost));
+  std::vector<double*> px((size_t)G.world);
+  std::vector<unsigned long long*> pf((size_t)G.world);
+  for (int p = 0; p < G.world; ++p) {
+    if (p == G.rank) { px[p] = G.xbuf.p; pf[p] = G.xflag.p; continue; }
+    void *a = nullptr, *b = nullptr;
+    GB_TRY(cudaIpcOpenMemHandle(&a, all[p].x, cudaIpcMemLazyEnablePeerAccess));
+    G.ipc_opened.push_back(a);
+    GB_TRY(cudaIpcOpenMemHandle(&b, all[p].f, cudaIpcMemLazyEnablePeerAccess));
+    G.ipc_opened.push_back(b);
+    px[p] = static_cast<double*>(a); pf[p] = static_cast<unsigned long long*>(b);
+  }
+  GB_TRY(cudaMemcpy(G.peer_xbuf.p, px.data(), sizeof(double*) * G.world, cudaMemcpyHostToDevice));
+  GB_TRY(cudaMemcpy(G.peer_xflag.p, pf.data(), sizeof(unsigned long long*) * G.world, cudaMemcpyHostToDevice));
+  return BVB_OK;
+}
 
 int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T, int K, int draws, int burnin,
                    int thin, int tvp_keep_all, int intercept, const double* priorIntercept, const double* PHI0,
@@ -765,6 +873,24 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     if ((rc = upload(h, G.PHI0, PHI0, (size_t)Kp * M))) return rc;
     GB_TRY(G.PHI.ensure((size_t)Kp * std::max(M, G.nloc_max * G.world)));
     if ((rc = upload(h, G.PHI, sv->PHI, (size_t)Kp * M))) return rc;
+    // peer exchange instead of the per-sweep NCCL allgather (BVB_NCCL_EXCHANGE=1 keeps the collective)
+    G.p2p = false; G.p2p_wanted = false;
+    if (G.world > 1 && ps->type != BVB_SIGMA_CHOLESKY && !use_huge && !getenv("BVB_NCCL_EXCHANGE")) {
+      const size_t blk = (size_t)G.nloc_max * Kp;
+      const double* old_x = G.xbuf.p;
+      const unsigned long long* old_f = G.xflag.p;
+      GB_TRY(G.xbuf.ensure((size_t)4 * G.world * blk));
+      GB_TRY(G.xflag.ensure((size_t)G.world));
+      GB_TRY(G.peer_xbuf.ensure((size_t)G.world)); GB_TRY(G.peer_xflag.ensure((size_t)G.world));
+      GB_TRY(G.xcnt.ensure((size_t)G.world + 1, true));
+      h->p2p_epoch += 1;                       // (every rank sets up the same chains in the same order)
+      G.epoch_base = h->p2p_epoch << 32;
+      G.p2p_wanted = true;
+      if (!h->inproc) {
+        if (old_x != G.xbuf.p || old_f != G.xflag.p || G.ipc_opened.empty()) { if ((rc = p2p_bootstrap_ipc(h, G))) return rc; }
+        G.p2p = true;
+      }                                        // (in-process ranks are wired by bvb_gibbs_init_multi)
+    }
     // the pair geometry (80 k pairs at the headline shape: 0.4 ms of host loops and 1.3 MB of tables) only depends on
     // (T, Kp): a recycled chain keeps it, on the host and on the device
     if (!reuse || G.geom.T != T || G.geom.n != Kp) {
@@ -1234,6 +1360,11 @@ static int check_status(bvb_handle* h, Gibbs& G) {
                   hst[1] == 1 ? "loadings" : "factors");
     return BVB_ERR_NUMERIC;
   }
+  if (hst[3] != 0) {
+    h->err_step = 1; h->err_sweep = G.rep;
+    bvb_set_error(h, BVB_ERR_COMM, "peer exchange: no PHI block from rank %i within 2 s (run <= %i)", hst[3] - 1, G.rep);
+    return BVB_ERR_COMM;
+  }
   if (hst[2] != 0) {
     h->err_step = 2; h->err_sweep = G.rep;
     bvb_set_error(h, BVB_ERR_NUMERIC, "GIG sampler: rejection loop exhausted in run <= %i (parameters outside the sampler's range)", G.rep);
@@ -1518,6 +1649,7 @@ int bvb_create_multi(int n, const int* devices, uint64_t seed, bvb_handle** hand
   }
   std::vector<int> rcs((size_t)n, BVB_OK);
   std::vector<std::thread> th;
+  for (int i = 0; i < n; ++i) handles[i]->inproc = (n > 1) ? 1 : 0;
   for (int i = 0; i < n; ++i) th.emplace_back([&, i]() { rcs[i] = bvb_comm_init(handles[i], i, n, n > 1 ? id : nullptr); });   // (ncclCommInitRank blocks until every rank has joined)
   for (auto& t : th) t.join();
   for (int i = 0; i < n; ++i)
@@ -1535,6 +1667,30 @@ int bvb_gibbs_init_multi(int n, bvb_handle** handles, const double* Y, const dou
     const int rc = bvb_gibbs_init(handles[i], Y, X, M, T, K, draws, burnin, thin, tvp_keep_all, intercept, priorIntercept, PHI0, prior_phi,
                                   prior_sigma, startvals, i_vec, PHI_tol, L_tol, huge, out);
     if (rc) return rc;
+  }
+  // peer exchange: the ranks live in this process, so the tables hold plain peer pointers (peer access enabled once)
+  bool wire = n > 1;
+  for (int i = 0; i < n && wire; ++i) {
+    const Gibbs* Gi = static_cast<const Gibbs*>(handles[i]->gibbs);
+    wire = Gi && Gi->p2p_wanted && Gi->world == n;
+  }
+  if (wire) {
+    std::vector<double*> px((size_t)n);
+    std::vector<unsigned long long*> pf((size_t)n);
+    for (int j = 0; j < n; ++j) { Gibbs* Gj = static_cast<Gibbs*>(handles[j]->gibbs); px[j] = Gj->xbuf.p; pf[j] = Gj->xflag.p; }
+    for (int i = 0; i < n && wire; ++i) {
+      if (cudaSetDevice(handles[i]->device) != cudaSuccess) { wire = false; break; }
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(handles[j]->device, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (pe != cudaSuccess) { cudaGetLastError(); wire = false; break; }
+      }
+      Gibbs* Gi = static_cast<Gibbs*>(handles[i]->gibbs);
+      if (wire && (cudaMemcpy(Gi->peer_xbuf.p, px.data(), sizeof(double*) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+                   cudaMemcpy(Gi->peer_xflag.p, pf.data(), sizeof(unsigned long long*) * n, cudaMemcpyHostToDevice) != cudaSuccess)) wire = false;
+    }
+    for (int i = 0; i < n; ++i) static_cast<Gibbs*>(handles[i]->gibbs)->p2p = wire;   // (all or none: otherwise the NCCL allgather)
   }
   return BVB_OK;
 }

@@ -1,5 +1,6 @@
 // Sampler state of one Gibbs chain (device buffers + host bookkeeping).
 #pragma once
+#include <vector>
 #include "bvb_internal.cuh"
 #include "hyper.cuh"
 #include "fsv.cuh"
@@ -116,6 +117,15 @@ struct Gibbs {
   int hyper_rows = 0;
   // execution
   cudaGraphExec_t graph_exec = nullptr;
+  // peer exchange of the PHI columns (push + flag over NVLink peer memory instead of an NCCL allgather)
+  GBuf<double> xbuf;                     // [2 chains][2 sweeps][world][nloc_max * Kp]: what the peers pushed (parity of the chain count, of the sweep)
+  GBuf<unsigned long long> xflag;        // [world]: (epoch << 32 | sweep + 1) of the last block pushed by each peer
+  GBuf<double*> peer_xbuf;               // device tables of the peers' xbuf / xflag
+  GBuf<unsigned long long*> peer_xflag;
+  GBuf<int> xcnt;                        // [world]: slices of the current push that are out (self-resetting)
+  std::vector<void*> ipc_opened;
+  bool p2p = false, p2p_wanted = false;
+  unsigned long long epoch_base = 0;
   char* stage = nullptr;                 // pinned staging arena of the set-up uploads
   size_t stage_cap = 0, stage_off = 0;
   bool graph_stale = false;   // chain recycled: re-capture and cudaGraphExecUpdate before the next replay

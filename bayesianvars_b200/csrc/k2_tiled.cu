@@ -947,6 +947,8 @@ __global__ void __launch_bounds__(KTL_THREADS, 1) k2_tiled_backsolve_ll(const K2
     y[i] = (i < n) ? __ldcg(om + colb[i] + n) + p.z[(size_t)eq * p.ldz + i] : 0.0;   // row n of L = the forward-solved rhs
   __syncthreads();
   bool bad = false;
+  const int xworld = (p.xch.peer_xbuf != nullptr) ? p.xch.world : 1;
+  const size_t xoff = xworld > 1 ? ((((p.xch.epoch_base >> 32) & 1ull) * 2 + (*p.xch.sweep_p & 1u)) * (size_t)p.xch.world + p.xch.rank) * p.xch.blk : 0;
   for (int k = nbk - 1; k >= 0; --k) {
     const int c0 = k * KT_NB, w = min(KT_NB, n - c0), rb = c0 + KT_NB;
     double lk[KT_NB];
@@ -991,11 +993,37 @@ __global__ void __launch_bounds__(KTL_THREADS, 1) k2_tiled_backsolve_ll(const K2
       }
       const double xv = (lane < w) ? (x0 + x1) + (x2 + x3) : 0.0;
       y[c0 + lane] = xv;
-      if (lane < w) { p.phi[(size_t)eq * p.ldphi + c0 + lane] = xv; bad |= !isfinite(xv); }
+      if (lane < w) {
+        p.phi[(size_t)eq * p.ldphi + c0 + lane] = xv;
+        bad |= !isfinite(xv);
+        // fused exchange: the same 32 values straight into every peer's exchange buffer (remote stores over NVLink,
+        // in flight while the remaining block columns are solved)
+        for (int pi = 0; pi + 1 < xworld; ++pi) {
+          const int pp = pi < p.xch.rank ? pi : pi + 1;
+          p.xch.peer_xbuf[pp][xoff + (size_t)eq * p.ldphi + c0 + lane] = xv;
+        }
+      }
     }
     __syncthreads();
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
+  if (xworld > 1) {
+    if (warp == 0) __threadfence_system();           // (warp 0 issued the remote stores)
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(p.xch.cnt, 1);
+      __threadfence();
+      if (old == (int)gridDim.x - 1) {               // every equation of this rank is out: stamp the peers' flags
+        *p.xch.cnt = 0;
+        __threadfence_system();
+        const unsigned long long stamp = p.xch.epoch_base + *p.xch.sweep_p + 1ull;
+        for (int pi = 0; pi + 1 < xworld; ++pi) {
+          const int pp = pi < p.xch.rank ? pi : pi + 1;
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.xch.peer_xflag[pp] + p.xch.rank), "l"(stamp) : "memory");
+        }
+      }
+    }
+  }
   if (tid == 0) {
     if (anybad) atomicCAS(&p.status[eq], 0, -1);
     bvb_stamp_end(p.tstamp);
@@ -1121,6 +1149,7 @@ cudaError_t launch_k2_tiled(const K2Params& p, cudaStream_t s) {
   if (fastbs < 0) { const char* ev = getenv("BVB_K2T_FASTBS"); fastbs = ev ? atoi(ev) : 2; }   // 2: left-looking (default), 1: right-looking, 0: generic
   if (fastbs == 2 && p.n <= KTL_MAXN) {
     k2_tiled_backsolve_ll<<<p.M, KTL_THREADS, 0, s>>>(p, lws, nbk);
+    if (p.xch_fused && p.xch.peer_xbuf != nullptr && p.xch.world > 1) *p.xch_fused = true;   // (this kernel pushed the columns itself)
     return cudaGetLastError();
   }
   if (fastbs && KT_NB * (nbk - 1) <= KTF_THREADS) {
