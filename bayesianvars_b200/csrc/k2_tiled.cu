@@ -996,19 +996,20 @@ __global__ void __launch_bounds__(KTL_THREADS, 1) k2_tiled_backsolve_ll(const K2
       if (lane < w) {
         p.phi[(size_t)eq * p.ldphi + c0 + lane] = xv;
         bad |= !isfinite(xv);
-        // fused exchange: the same 32 values straight into every peer's exchange buffer (remote stores over NVLink,
-        // in flight while the remaining block columns are solved)
-        for (int pi = 0; pi + 1 < xworld; ++pi) {
-          const int pp = pi < p.xch.rank ? pi : pi + 1;
-          p.xch.peer_xbuf[pp][xoff + (size_t)eq * p.ldphi + c0 + lane] = xv;
-        }
       }
     }
     __syncthreads();
   }
   const int anybad = __syncthreads_or(bad ? 1 : 0);
   if (xworld > 1) {
-    if (warp == 0) __threadfence_system();           // (warp 0 issued the remote stores)
+    // fused exchange: the solved column (complete in shared memory) straight into every peer's exchange buffer - one
+    // coalesced remote store per thread and peer over NVLink, off the 13-step chain above
+    for (int pi = 0; pi + 1 < xworld; ++pi) {
+      const int pp = pi < p.xch.rank ? pi : pi + 1;
+      double* dst = p.xch.peer_xbuf[pp] + xoff + (size_t)eq * p.ldphi;
+      for (int i = tid; i < n; i += KTL_THREADS) dst[i] = y[i];
+    }
+    __threadfence_system();
     __syncthreads();
     if (tid == 0) {
       const int old = atomicAdd(p.xch.cnt, 1);
