@@ -6,19 +6,21 @@
 // walk every equation's 13 block columns in lock step inside one CTA (321 us however few equations a GPU owns).  Here
 // the left-looking block algorithm is cut into tile tasks that any CTA can run:
 //
-//   DIAG(e, k)        diagonal tile of block column k of equation e:  A_kk + D_k - L(k,k-1) L(k,k-1)' -> chol, inverse
-//   SUB(e, k, I0:I1)  row blocks I0..I1-1 (<= 128 rows) of block column k:  A - L(rows, <k) L(k, <k)'  (FP64 DMMA,
-//                     operands straight from L2, columns consumed as they become final), times Linv_k', stored; and
-//                     for every row block I >= k+2 of the tile the contribution - L(I,k) L(I,k)' is folded into the
-//                     running diagonal accumulator D_I, so DIAG(I) never walks its own history.
+//   chain(e)          one CTA per equation walks the diagonal: block column k = the diagonal tile (A_kk + D_k -
+//                     L(k,k-1) L(k,k-1)' -> Cholesky -> inverse) and the tile below it, by four warp roles (kt_chain_role)
+//   SUB(e, k, I0:I1)  row blocks I0..I1-1 (<= 128 rows) of block column k, I0 >= k+2:  A - L(rows, <k) L(k, <k)'  (FP64
+//                     DMMA, operands straight from L2, columns consumed as they become final), times Linv_k', stored; the
+//                     task nearest the diagonal (I0 == k+2) also forms the look-ahead products P (old history of the
+//                     chain's next tile) and D (the diagonal accumulator two block columns ahead).
 //
-// Tasks sit in ONE list in a topological order (stage k: DIAG(.,k), the far tiles of column k-1, the first tile of
-// column k); persistent CTAs take the next index with an atomic and wait for what a task needs through per-(equation,
-// row block) progress counters (release / acquire at gpu scope).  A waiting CTA only ever waits for tasks with a
-// smaller index, which some resident CTA has already taken, so the scheme cannot deadlock whatever the number of
-// resident CTAs, and every tile is computed by exactly one task from fixed inputs in a fixed order: results do not
-// depend on which CTA ran what, on the grid size, or on how many equations share the launch (bitwise identical for
-// 13 or 100 equations - the equation-sharded multi-GPU chain is the single-GPU chain).
+// SUB tasks sit in ONE list in a topological order (stage k: the far tiles of column k, nearest chunk first);
+// persistent CTAs take the next index with an atomic and wait for what a task needs through per-(equation, row block)
+// progress counters (relaxed polls with back-off, one acquire fence; publication = barrier + one fence + relaxed
+// flags).  A waiting CTA only ever waits for tasks with a smaller index, which some resident CTA has already taken, or
+// for a chain CTA, all of which are resident, so the scheme cannot deadlock; every tile is computed by exactly one
+// task from fixed inputs in a fixed order: results do not depend on which CTA ran what or on the grid size (the same
+// launch is bitwise reproducible; against the one-CTA-per-equation kernels the summation order differs, ~1e-15).
+// What bounds it, and the measurements behind the rolled / software-pipelined chain code: DESIGN.md, section K2.
 #include "bvb_internal.cuh"
 
 #include <stdlib.h>
