@@ -417,6 +417,10 @@ int setup_hyper(bvb_handle* h, GibbsHyper& H, int prior, int n, const std::vecto
   if ((rc = upload(h, H.loc2, loc2_init.data(), n))) return rc;
   GB_TRY(H.red.ensure((size_t)n * HYP_NRED));
   GB_TRY(H.gsum.ensure((size_t)std::max(G, 1) * HYP_NRED));
+  // few large groups (one global group of 40 000 coefficients at the headline shape): several CTAs per group
+  const int nsplit = std::max(1, std::min(32, (int)((size_t)n / ((size_t)std::max(G, 1) * 2048))));
+  GB_TRY(H.gpart.ensure((size_t)std::max(G, 1) * nsplit));
+  GB_TRY(H.gcnt.ensure((size_t)std::max(G, 1), true));
   if (grid_len > 0) {
     if ((rc = upload(h, H.a_vec, a_vec, grid_len))) return rc;
     if ((rc = upload(h, H.a_weight, a_weight, grid_len))) return rc;
@@ -430,7 +434,7 @@ int setup_hyper(bvb_handle* h, GibbsHyper& H, int prior, int n, const std::vecto
   if (prior == BVB_PRIOR_HMP) if ((rc = upload(h, H.V_prep, V_prep.data(), n))) return rc;
   (void)V_i_fixed; (void)p_init;
   d.grp = H.grp.p; d.coef = H.coef.p; d.V_i = H.V_i.p; d.loc1 = H.loc1.p; d.loc2 = H.loc2.p; d.gpar = H.gpar.p;
-  d.gstart = H.gstart.p; d.gmem = H.gmem.p; d.red = H.red.p; d.gsum = H.gsum.p; d.a_vec = H.a_vec.p; d.a_weight = H.a_weight.p;
+  d.gstart = H.gstart.p; d.gmem = H.gmem.p; d.red = H.red.p; d.gsum = H.gsum.p; d.gpart = H.gpart.p; d.gcnt = H.gcnt.p; d.nsplit = nsplit; d.a_vec = H.a_vec.p; d.a_weight = H.a_weight.p;
   d.norm_consts = H.norm_consts.p; d.c_vec = H.c_vec.p; d.tau0 = H.tau0.p; d.tau1 = H.tau1.p; d.V_prep = H.V_prep.p;
   return BVB_OK;
 }

@@ -39,8 +39,8 @@ struct GBuf {
 
 struct GibbsHyper {
   HyperDev d;
-  GBuf<int> grp, gstart, gmem;
-  GBuf<double> coef, V_i, loc1, loc2, gpar, red, gsum, a_vec, a_weight, norm_consts, c_vec, tau0, tau1, V_prep;
+  GBuf<int> grp, gstart, gmem, gcnt;
+  GBuf<double> coef, V_i, loc1, loc2, gpar, red, gsum, gpart, a_vec, a_weight, norm_consts, c_vec, tau0, tau1, V_prep;
 };
 
 struct GibbsSeg {

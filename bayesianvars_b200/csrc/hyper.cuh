@@ -33,6 +33,9 @@ struct HyperDev {
   const int* gmem = nullptr;   // [number of grouped coefficients]
   double* red = nullptr;       // [HYP_NRED][n] per-coefficient terms of the group sums
   double* gsum = nullptr;      // [G][HYP_NRED]   reduced sums of the last pass
+  double* gpart = nullptr;     // [G][nsplit] partial sums of a split group reduction
+  int* gcnt = nullptr;         // [G] CTAs of a split reduction that have arrived (self-resetting)
+  int nsplit = 1;              // CTAs per group in the reductions (few large groups: up to 32)
   // grids for the hyper-hyper update of `a` (DL/GT)
   double *a_vec = nullptr, *a_weight = nullptr, *norm_consts = nullptr, *c_vec = nullptr;
   int grid_len = 0;
