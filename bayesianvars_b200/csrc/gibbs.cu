@@ -891,8 +891,32 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
       G.epoch_base = h->p2p_epoch << 32;
       G.p2p_wanted = true;
       if (!h->inproc) {
-        if (old_x != G.xbuf.p || old_f != G.xflag.p || G.ipc_opened.empty()) { if ((rc = p2p_bootstrap_ipc(h, G))) return rc; }
-        G.p2p = true;
+        if (old_x != G.xbuf.p || old_f != G.xflag.p || G.ipc_opened.empty()) {
+          // all ranks or none: a rank that cannot open its peers' buffers (IPC disabled in a container, no peer access)
+          // must not leave the others waiting on flags - the outcome is agreed on through one more tiny allgather, and
+          // the per-sweep NCCL allgather remains the fallback
+          const int brc = p2p_bootstrap_ipc(h, G);
+          GBuf<double> okv, okall;
+          GB_TRY(okv.ensure(1)); GB_TRY(okall.ensure((size_t)G.world));
+          const double mine_ok = (brc == BVB_OK) ? 1.0 : 0.0;
+          GB_TRY(cudaMemcpyAsync(okv.p, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+          ncclResult_t nr = nccl_api().AllGather(okv.p, okall.p, 1, ncclDouble, (ncclComm_t)G.comm, h->stream);
+          if (nr != ncclSuccess) { bvb_set_error(h, BVB_ERR_COMM, "ncclAllGather (set-up): %s", nccl_api().GetErrorString(nr)); return BVB_ERR_COMM; }
+          GB_TRY(cudaStreamSynchronize(h->stream));
+          std::vector<double> oks((size_t)G.world, 0.0);
+          GB_TRY(cudaMemcpy(oks.data(), okall.p, sizeof(double) * G.world, cudaMemcpyDeviceToHost));
+          bool all_ok = true;
+          for (double v : oks) all_ok = all_ok && v > 0.5;
+          if (!all_ok) {
+            for (void* q : G.ipc_opened) cudaIpcCloseMemHandle(q);
+            G.ipc_opened.clear();
+            cudaGetLastError();
+            h->err_code = 0; h->err_msg[0] = 0;
+          }
+          G.p2p = all_ok;
+        } else {
+          G.p2p = true;
+        }
       }                                        // (in-process ranks are wired by bvb_gibbs_init_multi)
     }
     // the pair geometry (80 k pairs at the headline shape: 0.4 ms of host loops and 1.3 MB of tables) only depends on

@@ -1138,7 +1138,7 @@ cudaError_t launch_k2(const K2Params& p, cudaStream_t s) {
   if (!linv_ws) return cudaErrorMemoryAllocation;
   {
     // The tile-queue form (k2_tiled.cu) when the equations alone cannot fill the chip: measured at n = 401 on 148 SMs,
-    // tiled / one-CTA-per-equation: 13 equations 242 / 303 us, 25: 250 / 307, 50: 277 / 334, 100: 483 / 338 (the look-ahead
+    // tiled / one-CTA-per-equation: 13 equations 201 / 303 us, 25: 213 / 307, 50: 230 / 334, 100: 459 / 319 (the look-ahead
     // kernel below keeps the headline shape).  BVB_K2_TILED=0 / 1 forces one or the other; the phase-profile and
     // timing-experiment switches of the kernels below select them too.
     static int tiled = -2, num_sms_t = 0;

@@ -262,6 +262,9 @@ int bvb_gibbs_state(bvb_handle* h, double* PHI, double* V_prior, double* logvar,
 /* Multi-GPU plumbing: one process per GPU.  unique_id is the 128-byte
  * ncclUniqueId produced by bvb_comm_unique_id on rank 0 and broadcast by the
  * launcher (torch.distributed / MPI / a file). */
+/* (The per-sweep exchange of the freshly drawn PHI columns is a push over NVLink peer memory fused into the solve kernel,
+ * with CUDA IPC handles exchanged once through the communicator; the communicator's allgather is the fallback when the
+ * peers' buffers cannot be opened - BVB_NCCL_EXCHANGE=1 forces it.) */
 int bvb_comm_unique_id(char* unique_id_128);
 int bvb_comm_init(bvb_handle* h, int rank, int world, const char* unique_id_128);
 
