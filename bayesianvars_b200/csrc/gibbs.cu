@@ -873,7 +873,10 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
   }
   GB_TRY(G.eqstatus.ensure(std::max(M, 1), true));
   if (Kp > 0) {
-    if ((rc = upload(h, G.X, X, (size_t)T * Kp))) return rc;
+    // (a recycled chain on the same regressors - the usual case: bvar() again on the same data - keeps X and the
+    // pair-product matrix Z on the device)
+    const bool sameX = reuse && G.Xhost.size() == (size_t)T * Kp && memcmp(G.Xhost.data(), X, sizeof(double) * (size_t)T * Kp) == 0;
+    if (!sameX) { if ((rc = upload(h, G.X, X, (size_t)T * Kp))) return rc; }
     if ((rc = upload(h, G.PHI0, PHI0, (size_t)Kp * M))) return rc;
     GB_TRY(G.PHI.ensure((size_t)Kp * std::max(M, G.nloc_max * G.world)));
     if ((rc = upload(h, G.PHI, sv->PHI, (size_t)Kp * M))) return rc;
@@ -934,7 +937,6 @@ int bvb_gibbs_init(bvb_handle* h, const double* Y, const double* X, int M, int T
     if (!use_huge) GB_TRY(G.omega.ensure((size_t)std::max(G.nloc, 1) * G.geom.ldo));
     GB_TRY(G.Zn.ensure((size_t)Kp * std::max(use_huge ? M : G.nloc, 1)));
     // the pair-product matrix Z is built ONCE per chain (X never changes) - and kept when the next chain has the same X
-    const bool sameX = reuse && G.Xhost.size() == (size_t)T * Kp && memcmp(G.Xhost.data(), X, sizeof(double) * (size_t)T * Kp) == 0;
     if (!sameX) G.Xhost.assign(X, X + (size_t)T * Kp);
     if (!use_huge && !sameX) GB_TRY(launch_build_A(G.A.p, G.X.p, G.pairs.p, T, G.geom.Tp, Kp, G.geom.nArows, 0, s));
     if (use_huge) {
