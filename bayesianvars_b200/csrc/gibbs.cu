@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(512) gibbs_pull_kernel(double* __restrict__ PH
     const unsigned long long want = epoch_base + sweep + 1ull;
     const long long t0 = clock64();
     while (ld_acquire_sys_u64(xflag + p) < want) {
-      if (clock64() - t0 > (4ll << 30)) { atomicExch(status + 3, 1 + p); break; }   // ~2 s: a peer is gone; reported, not hung
+      if (clock64() - t0 > (1ll << 36)) { atomicExch(status + 3, 1 + p); break; }   // ~35 s: a peer is gone; reported, not hung
     }
   }
   __syncthreads();
@@ -1392,7 +1392,7 @@ static int check_status(bvb_handle* h, Gibbs& G) {
   }
   if (hst[3] != 0) {
     h->err_step = 1; h->err_sweep = G.rep;
-    bvb_set_error(h, BVB_ERR_COMM, "peer exchange: no PHI block from rank %i within 2 s (run <= %i)", hst[3] - 1, G.rep);
+    bvb_set_error(h, BVB_ERR_COMM, "peer exchange: no PHI block from rank %i within ~35 s (run <= %i)", hst[3] - 1, G.rep);
     return BVB_ERR_COMM;
   }
   if (hst[2] != 0) {
