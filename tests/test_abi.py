@@ -43,3 +43,18 @@ def test_no_cpu_fallback_without_device(lib_built):
         assert e.code == 1
     else:
         raise AssertionError("Handle() succeeded without a GPU")
+
+
+def test_multi_handle_fails_loudly_without_devices(lib_built):
+    """bvb_create_multi has no CPU fallback either: without CUDA devices it must return an error, never a handle."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    from bayesianvars_b200 import BvbError
+    from bayesianvars_b200 import bvar as B
+    try:
+        B.MultiHandle([0, 1])
+    except BvbError as e:
+        assert e.code != 0
+    else:
+        raise AssertionError("MultiHandle() succeeded without GPUs")
