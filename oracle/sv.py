@@ -70,6 +70,53 @@ def draw_latent(ystar, r, mu, phi, sigma, h0_var, rng):
     return hh[0], hh[1:]
 
 
+def draw_latent_parallel(ystar, r, mu, phi, sigma, h0_var, rng):
+    """The SAME law as draw_latent - h_{0:T} | r, theta ~ N(Omega^-1 c, Omega^-1) - drawn the way the CUDA series kernel
+    does it (k8_fsv.cu::sv_state_draw_parallel): perturb, then solve.  Omega = B'B + D with B the bidiagonal AR(1)
+    innovation map (row 0: sqrt(B0inv)/sigma, row t: (h_t - phi h_{t-1})/sigma) and D = diag(0, 1/v^2_{r_1}, ..), so
+    eta = B'xi + sqrt(D) zeta (xi ~ N(0, I_{T+1}), zeta ~ N(0, I_T)) has covariance Omega and h = Omega^-1 (c + eta) has
+    the required law; the tridiagonal solve is a parallel cyclic reduction (log2(T+1) sweeps, every row eliminates its
+    neighbours at distance 1, 2, 4, ..).  Written for one series (ystar, r: (T,)); returns (h0, h (T,)).
+    Test infrastructure: tests/test_oracle_sv_parallel.py checks both samplers against the exact moments on the CPU."""
+    ystar = np.asarray(ystar, float); r = np.asarray(r, int)
+    T = ystar.size
+    s2inv, phi2 = 1.0 / sigma ** 2, phi ** 2
+    B0inv = (1.0 - phi2) if h0_var <= 0 else 1.0 / h0_var
+    prec = 1.0 / MIX_V2[r]
+    b = np.empty(T + 1); c = np.empty(T + 1)
+    b[0] = (B0inv + phi2) * s2inv
+    c[0] = mu * (B0inv - phi * (1 - phi)) * s2inv
+    b[1:T] = prec[:T - 1] + (1 + phi2) * s2inv
+    b[T] = prec[T - 1] + s2inv
+    c[1:] = (ystar - MIX_M[r]) * prec
+    c[1:T] += mu * (1 - phi) ** 2 * s2inv
+    c[T] += mu * (1 - phi) * s2inv
+    off = -phi * s2inv
+    xi, zeta = rng.standard_normal(T + 1), rng.standard_normal(T)
+    sinv = 1.0 / sigma
+    eta = np.empty(T + 1)
+    eta[0] = np.sqrt(B0inv) * sinv * xi[0] - phi * sinv * xi[1]
+    eta[1:T] = sinv * xi[1:T] - phi * sinv * xi[2:T + 1] + zeta[:T - 1] * np.sqrt(prec[:T - 1])
+    eta[T] = sinv * xi[T] + zeta[T - 1] * np.sqrt(prec[T - 1])
+    rhs = c + eta
+    a = np.full(T + 1, off); a[0] = 0.0          # sub-diagonal
+    g = np.full(T + 1, off); g[T] = 0.0          # super-diagonal
+    st = 1
+    idx = np.arange(T + 1)
+    while st <= T:
+        im, ip = idx - st, idx + st
+        k1 = np.where(im >= 0, a / b[np.maximum(im, 0)], 0.0)
+        k2 = np.where(ip <= T, g / b[np.minimum(ip, T)], 0.0)
+        bn = b - np.where(im >= 0, g[np.maximum(im, 0)], 0.0) * k1 - np.where(ip <= T, a[np.minimum(ip, T)], 0.0) * k2
+        rn = rhs - np.where(im >= 0, rhs[np.maximum(im, 0)], 0.0) * k1 - np.where(ip <= T, rhs[np.minimum(ip, T)], 0.0) * k2
+        an = -np.where(im >= 0, a[np.maximum(im, 0)], 0.0) * k1
+        gn = -np.where(ip <= T, g[np.minimum(ip, T)], 0.0) * k2
+        a, b, g, rhs = an, bn, gn, rn
+        st *= 2
+    hh = rhs / b
+    return hh[0], hh[1:]
+
+
 def draw_theta_centered(h0, h, mu, phi, sigma, prior, rng):
     T, S = h.shape
     hp = np.vstack([h0[None, :], h[:-1]])
